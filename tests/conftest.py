@@ -1,0 +1,35 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu)")
+
+
+def _load(name):
+    with np.load(os.path.join(GOLDEN, name)) as z:
+        return {k: z[k] for k in z.files}
+
+
+@pytest.fixture(scope="session")
+def golden_plugins():
+    return _load("plugins.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_core():
+    return _load("core.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_lownoise():
+    return _load("lownoise.npz")

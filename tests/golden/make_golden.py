@@ -1,0 +1,255 @@
+"""Generate golden vectors by running the REAL reference (acerbilab/gpyreg).
+
+Run in the build container only (it needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+It imports the unmodified reference through the matplotlib stub of SURVEY.md
+Appendix B, runs the hot path (plugin ``compute`` methods, ``_GP__compute_nlZ``,
+``update`` -> posteriors, ``predict``) on seeded inputs and writes inputs AND
+outputs to ``tests/golden/*.npz``.  The .npz files are committed; the tests and
+the GPU box never read /root/reference.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+
+for name in ("matplotlib", "matplotlib.pyplot"):
+    sys.modules.setdefault(name, types.ModuleType(name))
+sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+sys.path.insert(0, os.environ.get("GPYREG_REFERENCE", "/root/reference"))
+import gpyreg  # noqa: E402
+from gpyreg.covariance_functions import (Matern, RationalQuadraticARD,  # noqa: E402
+                                         SquaredExponential)
+from gpyreg.isotropic_covariance_functions import (MaternIsotropic,  # noqa: E402
+                                                   SquaredExponentialIsotropic)
+from gpyreg.mean_functions import ConstantMean, NegativeQuadratic, ZeroMean  # noqa: E402
+from gpyreg.noise_functions import GaussianNoise  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+# (tag, cov_kind, degree, ard, factory)
+COVS = [
+    ("se_ard", 0, 0, 1, lambda: SquaredExponential()),
+    ("mat1_ard", 1, 1, 1, lambda: Matern(1)),
+    ("mat3_ard", 1, 3, 1, lambda: Matern(3)),
+    ("mat5_ard", 1, 5, 1, lambda: Matern(5)),
+    ("rq_ard", 2, 0, 1, lambda: RationalQuadraticARD()),
+    ("se_iso", 0, 0, 0, lambda: SquaredExponentialIsotropic()),
+    ("mat1_iso", 1, 1, 0, lambda: MaternIsotropic(1)),
+    ("mat3_iso", 1, 3, 0, lambda: MaternIsotropic(3)),
+    ("mat5_iso", 1, 5, 0, lambda: MaternIsotropic(5)),
+]
+MEANS = [lambda: ZeroMean(), lambda: ConstantMean(), lambda: NegativeQuadratic()]
+
+
+def synth(rng, N, D):
+    """SURVEY.md 8(d) synthetic data."""
+    X = rng.uniform(-3, 3, (N, D))
+    y = (np.sin(X.sum(1)) - 0.125 * (X ** 2).sum(1)
+         + 0.1 * rng.standard_normal(N)).reshape(-1, 1)
+    return X, y
+
+
+def benign_hyp(rng, B, D, cov, mean_kind, noise_params, y):
+    """SURVEY.md 8(d) 'benign' hyperparameter distribution."""
+    cols = []
+    nl = D if cov[3] else 1
+    cols.append(np.log(1.5) + 0.3 * rng.standard_normal((B, nl)))
+    cols.append(0.3 * rng.standard_normal((B, 1)))
+    if cov[1] == 2:
+        cols.append(0.3 * rng.standard_normal((B, 1)))
+    if noise_params[0] == 1:
+        cols.append(np.log(0.1) + 0.3 * rng.standard_normal((B, 1)))
+    if noise_params[1] == 2:
+        cols.append(0.2 * rng.standard_normal((B, 1)))
+    if noise_params[2] == 1:
+        cols.append(np.median(y) + 0.3 * rng.standard_normal((B, 1)))
+        cols.append(np.log(0.05) + 0.2 * rng.standard_normal((B, 1)))
+    if mean_kind >= 1:
+        cols.append(y.mean() + 0.1 * rng.standard_normal((B, 1)))
+    if mean_kind == 2:
+        cols.append(0.3 * rng.standard_normal((B, D)))
+        cols.append(np.log(3) + 0.2 * rng.standard_normal((B, D)))
+    return np.concatenate(cols, axis=1)
+
+
+def make_gp(D, cov, mean_kind, noise_params):
+    noise = GaussianNoise(constant_add=noise_params[0] == 1,
+                          user_provided_add=noise_params[1] >= 1,
+                          scale_user_provided=noise_params[1] == 2,
+                          rectified_linear_output_dependent_add=noise_params[2] == 1)
+    return gpyreg.GP(D, cov[4](), MEANS[mean_kind](), noise)
+
+
+def gen_plugins():
+    rng = np.random.default_rng(100)
+    N, M, D = 20, 7, 3
+    X = rng.uniform(-2, 2, (N, D))
+    Xs = rng.uniform(-2, 2, (M, D))
+    X[5] = X[2]            # duplicate rows: r = 0 off the diagonal
+    out = {"X": X, "Xs": Xs}
+    for cov in COVS:
+        tag = cov[0]
+        c = cov[4]()
+        n = c.hyperparameter_count(D)
+        hyp = 0.5 * rng.standard_normal(n)
+        with np.errstate(all="ignore"):
+            K, dK = c.compute(hyp, X, compute_grad=True)
+        out[f"{tag}.hyp"] = hyp
+        out[f"{tag}.K"] = K
+        out[f"{tag}.dK"] = np.ascontiguousarray(dK)
+        out[f"{tag}.Kx"] = c.compute(hyp, X, Xs)
+        out[f"{tag}.Kd"] = c.compute(hyp, X, compute_diag=True)
+    # means
+    for mk in (0, 1, 2):
+        mobj = MEANS[mk]()
+        hyp = rng.standard_normal(mobj.hyperparameter_count(D))
+        m, dm = mobj.compute(hyp, X, compute_grad=True)
+        out[f"mean{mk}.hyp"] = hyp
+        out[f"mean{mk}.m"] = m
+        out[f"mean{mk}.dm"] = np.asarray(dm, dtype=float).reshape(N, -1) if mk else np.zeros((N, 0))
+    # noise: every flag combination
+    y = rng.standard_normal((N, 1))
+    s2 = rng.uniform(0.01, 0.1, (N, 1))
+    out["noise.y"] = y
+    out["noise.s2"] = s2
+    for p0 in (0, 1):
+        for p1 in (0, 1, 2):
+            for p2 in (0, 1):
+                nobj = GaussianNoise(p0 == 1, p1 >= 1, p1 == 2, p2 == 1)
+                hyp = 0.3 * rng.standard_normal(nobj.hyperparameter_count())
+                sn2, dsn2 = nobj.compute(hyp, X, y, s2, compute_grad=True)
+                key = f"noise{p0}{p1}{p2}"
+                out[f"{key}.hyp"] = hyp
+                out[f"{key}.sn2"] = np.asarray(sn2, dtype=float)
+                out[f"{key}.dsn2"] = dsn2
+    np.savez_compressed(os.path.join(HERE, "plugins.npz"), **out)
+    print("plugins.npz", len(out), "arrays")
+
+
+CORE_CASES = [
+    # tag, cov index, mean_kind, noise_params, N, D, B, use_s2
+    ("cfg2_se_const", 0, 1, (1, 0, 0), 60, 3, 4, False),
+    ("cfg3_mat5_negquad", 3, 2, (1, 0, 0), 70, 4, 4, False),
+    ("cfg4_rq_const", 4, 1, (1, 0, 0), 50, 3, 3, False),
+    ("cfg5_mat3iso_const", 7, 1, (1, 0, 0), 50, 5, 3, False),
+    ("ex1_mat3_negquad_user", 2, 2, (1, 1, 0), 31, 1, 3, True),
+    ("se_zero_allnoise", 0, 0, (1, 2, 1), 40, 2, 3, True),
+    ("mat1_zero", 1, 0, (1, 0, 0), 30, 2, 2, False),
+    ("seiso_negquad", 5, 2, (1, 0, 0), 45, 3, 3, False),
+    ("mat5iso_zero_user", 8, 0, (1, 2, 0), 36, 2, 2, True),
+    ("multi_tile_se", 0, 1, (1, 0, 0), 300, 4, 2, False),   # > 2 tiles of 128
+]
+
+
+def run_core(gp, hyps):
+    nlz, dnlz, posts = [], [], []
+    for h in hyps:
+        with np.errstate(all="ignore"):
+            a, g = gp._GP__compute_nlZ(h, True, False)
+            a0 = gp._GP__compute_nlZ(h, False, False)
+        assert a == a0 or (np.isnan(a) and np.isnan(a0))
+        nlz.append(a)
+        dnlz.append(g)
+    gp.update(hyp=np.asarray(hyps), compute_posterior=True)
+    return np.asarray(nlz), np.asarray(dnlz), gp.posteriors
+
+
+def gen_core():
+    out = {}
+    rng = np.random.default_rng(200)
+    for tag, ci, mk, npar, N, D, B, use_s2 in CORE_CASES:
+        cov = COVS[ci]
+        X, y = synth(rng, N, D)
+        s2 = rng.uniform(0.005, 0.05, (N, 1)) if use_s2 else None
+        gp = make_gp(D, cov, mk, npar)
+        hyps = benign_hyp(rng, B, D, cov, mk, npar, y)
+        gp.X, gp.y, gp.s2 = X, y, s2
+        nlz, dnlz, posts = run_core(gp, hyps)
+        out[f"{tag}.spec"] = np.array([D, cov[1], cov[2], cov[3], mk, *npar])
+        out[f"{tag}.X"], out[f"{tag}.y"] = X, y
+        if use_s2:
+            out[f"{tag}.s2"] = s2
+        out[f"{tag}.hyp"] = hyps
+        out[f"{tag}.nlZ"], out[f"{tag}.dnlZ"] = nlz, dnlz
+        out[f"{tag}.alpha"] = np.stack([p.alpha[:, 0] for p in posts])
+        out[f"{tag}.sW"] = np.array([p.sW[0, 0] for p in posts])
+        out[f"{tag}.sn2_mult"] = np.array([float(p.sn2_mult) for p in posts])
+        out[f"{tag}.L_chol"] = np.array([int(p.L_chol) for p in posts])
+        if N <= 100:
+            out[f"{tag}.L"] = np.stack([p.L for p in posts])
+        # predictions at M test points, every flag combination
+        M = 25
+        Xs = rng.uniform(-3.5, 3.5, (M, D))
+        ys = rng.standard_normal((M, 1))
+        s2s = rng.uniform(0.005, 0.05, (M, 1)) if use_s2 else None
+        out[f"{tag}.Xs"], out[f"{tag}.ys"] = Xs, ys
+        if use_s2:
+            out[f"{tag}.s2s"] = s2s
+        for add_noise in (0, 1):
+            for sep in (0, 1):
+                r = gp.predict(Xs, ys, s2s, add_noise=bool(add_noise),
+                               separate_samples=bool(sep), return_lpd=True)
+                k = f"{tag}.pred{add_noise}{sep}"
+                out[k + ".mu"], out[k + ".s2"], out[k + ".lpd"] = r
+    np.savez_compressed(os.path.join(HERE, "core.npz"), **out)
+    print("core.npz", len(out), "arrays")
+
+
+def gen_lownoise():
+    """SURVEY.md section 7 recipe: noiseless GaussianNoise() -> low-noise branch
+    and the x10 jitter retries; plus explicit tiny constant noise."""
+    out = {}
+    rng = np.random.default_rng(300)
+    N, D = 150, 2
+    X = rng.uniform(-3, 3, (N, D))
+    y = np.sin(X.sum(1)).reshape(-1, 1)
+    cov = COVS[0]
+    # (a) GaussianNoise(): sn2 = eps
+    gp = make_gp(D, cov, 0, (0, 0, 0))
+    gp.X, gp.y, gp.s2 = X, y, None
+    hyps = np.array([[0.0, 0.0, 0.0], [1.0, 1.0, 0.0], [2.0, 2.0, 0.0],
+                     [-1.0, -1.0, 0.0]])
+    nlz, dnlz, posts = run_core(gp, hyps)
+    out["eps.spec"] = np.array([D, 0, 0, 1, 0, 0, 0, 0])
+    out["eps.X"], out["eps.y"], out["eps.hyp"] = X, y, hyps
+    out["eps.nlZ"], out["eps.dnlZ"] = nlz, dnlz
+    out["eps.alpha"] = np.stack([p.alpha[:, 0] for p in posts])
+    out["eps.sW"] = np.array([p.sW[0, 0] for p in posts])
+    out["eps.sn2_mult"] = np.array([float(p.sn2_mult) for p in posts])
+    out["eps.L_chol"] = np.array([int(p.L_chol) for p in posts])
+    Xs = rng.uniform(-3, 3, (20, D))
+    out["eps.Xs"] = Xs
+    r = gp.predict(Xs, add_noise=True, separate_samples=True)
+    out["eps.pred.mu"], out["eps.pred.s2"] = r
+    print("eps: sn2_mult", out["eps.sn2_mult"], "L_chol", out["eps.L_chol"])
+    # (b) constant noise straddling the 1e-6 threshold
+    gp = make_gp(D, cov, 1, (1, 0, 0))
+    gp.X, gp.y, gp.s2 = X, y, None
+    hyps = np.array([[0.0, 0.0, 0.0, np.log(1e-6) / 1.0, 0.1],
+                     [0.0, 0.0, 0.0, np.log(2e-3), 0.1],
+                     [-0.5, -0.3, 0.2, np.log(3e-4), -0.1],
+                     [1.5, 1.5, 0.0, np.log(2e-3), 0.0]])
+    nlz, dnlz, posts = run_core(gp, hyps)
+    out["thr.spec"] = np.array([D, 0, 0, 1, 1, 1, 0, 0])
+    out["thr.X"], out["thr.y"], out["thr.hyp"] = X, y, hyps
+    out["thr.nlZ"], out["thr.dnlZ"] = nlz, dnlz
+    out["thr.alpha"] = np.stack([p.alpha[:, 0] for p in posts])
+    out["thr.sW"] = np.array([p.sW[0, 0] for p in posts])
+    out["thr.sn2_mult"] = np.array([float(p.sn2_mult) for p in posts])
+    out["thr.L_chol"] = np.array([int(p.L_chol) for p in posts])
+    out["thr.Xs"] = Xs
+    r = gp.predict(Xs, add_noise=True, separate_samples=True)
+    out["thr.pred.mu"], out["thr.pred.s2"] = r
+    print("thr: sn2_mult", out["thr.sn2_mult"], "L_chol", out["thr.L_chol"])
+    np.savez_compressed(os.path.join(HERE, "lownoise.npz"), **out)
+    print("lownoise.npz", len(out), "arrays")
+
+
+if __name__ == "__main__":
+    gen_plugins()
+    gen_core()
+    gen_lownoise()
