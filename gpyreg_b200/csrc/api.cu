@@ -1,0 +1,1263 @@
+// C ABI of gpyreg_b200 (see include/gpyreg_b200.h): host orchestration of the batched
+// GP hot path on one B200.  One translation unit; build with
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
+#include "../../include/gpyreg_b200.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "chol.cuh"
+#include "common.cuh"
+#include "cov.cuh"
+#include "gemm.cuh"
+#include "predict.cuh"
+
+using namespace gpb;
+
+// ---------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------
+struct Bufs {              // device storage for `cap` batch slots
+  int cap = 0;
+  bool has_w = false;
+  int Np = 0, Nt = 0, D = 0, P = 0;
+  double *Abuf = nullptr, *Wbuf = nullptr, *Dbuf = nullptr, *DTbuf = nullptr;
+  double *xs = nullptr, *resid = nullptr, *sn2v = nullptr, *bvec = nullptr, *zvec = nullptr,
+         *alpha = nullptr, *logdet = nullptr, *mult = nullptr, *hyp = nullptr, *nlz = nullptr,
+         *dnlz = nullptr, *gpart = nullptr;
+  SlotP* sp = nullptr;
+  int *fail = nullptr, *sel = nullptr, *sel2 = nullptr;
+  long long smat() const { return (long long)Np * Np; }
+};
+
+struct gpb_ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  std::string err;
+  Model md{};
+  bool has_model = false, has_data = false;
+  long long N = 0;
+  int D = 0, Np = 0, Nt = 0;
+  double *dX = nullptr, *dy = nullptr, *ds2 = nullptr;
+  size_t ws_limit = 0;
+  Bufs ws;
+  double timings[6] = {0, 0, 0, 0, 0, 0};
+  long long launches = 0;
+  cudaEvent_t ev[8] = {};
+  // predict scratch
+  double *pXs = nullptr, *pys = nullptr, *ps2s = nullptr, *pBt = nullptr, *pmu = nullptr,
+         *pv = nullptr, *psamp = nullptr, *pout = nullptr;
+  size_t pXs_n = 0, pBt_n = 0, ppart_n = 0, psamp_n = 0, pout_n = 0;
+};
+
+struct gpb_post {
+  gpb_ctx* ctx = nullptr;
+  Bufs b;                   // b.cap == number of samples
+  long long N = 0;
+  Model md{};
+  std::vector<SlotP> sp;    // host copy
+  std::vector<int> status;  // 1 = Cholesky failed
+  std::vector<double> hyp;  // host copy (B,P)
+  bool w_ready = false;
+};
+
+static std::string g_create_err;
+
+#define CK(call)                                                                       \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess) {                                                           \
+      char buf_[512];                                                                  \
+      snprintf(buf_, sizeof buf_, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, \
+               cudaGetErrorString(e_));                                                \
+      ctx->err = buf_;                                                                 \
+      return GPB_ECUDA;                                                                \
+    }                                                                                  \
+  } while (0)
+
+#define FAIL(code, msg) \
+  do {                  \
+    ctx->err = (msg);   \
+    return (code);      \
+  } while (0)
+
+#define LAUNCHED(ctx) ((ctx)->launches++)
+
+static inline int round_up(long long v, int m) { return (int)(((v + m - 1) / m) * m); }
+static inline unsigned grid1d(long long n, int block = 256) {
+  return (unsigned)std::min<long long>((n + block - 1) / block, 148LL * 16);
+}
+
+template <class Op>
+static cudaError_t gemm_attr() {
+  return cudaFuncSetAttribute(gemm_nt_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)GEMM_SMEM);
+}
+template <class Op>
+static void launch_gemm(gpb_ctx* ctx, const Op& op, dim3 grid) {
+  gemm_nt_kernel<Op><<<grid, GEMM_THREADS, GEMM_SMEM, ctx->stream>>>(op);
+  LAUNCHED(ctx);
+}
+
+constexpr int COV_SMEM_MAX = (2 * MAXD * T + 2 * T + 8 * (MAXD + 2) + 8 * T) * 8;
+
+template <int KIND>
+static cudaError_t kind_attrs() {
+  cudaError_t e;
+  e = cudaFuncSetAttribute(build_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, COV_SMEM_MAX);
+  if (e) return e;
+  e = cudaFuncSetAttribute(ks_build_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, COV_SMEM_MAX);
+  if (e) return e;
+  e = cudaFuncSetAttribute(grad_kernel<KIND, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, COV_SMEM_MAX);
+  if (e) return e;
+  e = cudaFuncSetAttribute(grad_kernel<KIND, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, COV_SMEM_MAX);
+  if (e) return e;
+  e = cudaFuncSetAttribute(grad_kernel<KIND, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, COV_SMEM_MAX);
+  if (e) return e;
+  e = cudaFuncSetAttribute(grad_kernel<KIND, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, COV_SMEM_MAX);
+  return e;
+}
+
+static int init_attrs(gpb_ctx* ctx) {
+  CK(gemm_attr<OpGeneric>());
+  CK(gemm_attr<OpPanel>());
+  CK(gemm_attr<OpSyrk>());
+  CK(gemm_attr<OpHpass>());
+  CK(gemm_attr<OpWrec>());
+  CK(gemm_attr<OpSyrk2>());
+  CK(gemm_attr<OpPred>());
+  CK(cudaFuncSetAttribute(diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
+  CK(kind_attrs<0>());
+  CK(kind_attrs<1>());
+  CK(kind_attrs<3>());
+  CK(kind_attrs<5>());
+  CK(kind_attrs<2>());
+  return GPB_OK;
+}
+
+extern "C" int gpb_version(void) { return 100; }
+
+extern "C" int gpb_create(int device, gpb_ctx** out) {
+  if (!out) return GPB_EINVAL;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_err = std::string("no CUDA device available: ") + cudaGetErrorString(e);
+    return GPB_ECUDA;
+  }
+  if (device < 0 || device >= ndev) {
+    g_create_err = "device index out of range";
+    return GPB_EINVAL;
+  }
+  gpb_ctx* ctx = new gpb_ctx();
+  ctx->device = device;
+  e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    g_create_err = std::string("cudaSetDevice/StreamCreate: ") + cudaGetErrorString(e);
+    delete ctx;
+    return GPB_ECUDA;
+  }
+  ctx->stream = ctx->own_stream;
+  for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+  int rc = init_attrs(ctx);
+  if (rc != GPB_OK) {
+    g_create_err = ctx->err;
+    delete ctx;
+    return rc;
+  }
+  *out = ctx;
+  return GPB_OK;
+}
+
+static void free_bufs(Bufs& b) {
+  double** ptrs[] = {&b.Abuf, &b.Wbuf, &b.Dbuf, &b.DTbuf, &b.xs, &b.resid, &b.sn2v, &b.bvec, &b.zvec,
+                     &b.alpha, &b.logdet, &b.mult, &b.hyp, &b.nlz, &b.dnlz, &b.gpart};
+  for (auto p : ptrs) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+  }
+  if (b.sp) cudaFree(b.sp);
+  b.sp = nullptr;
+  int** ip[] = {&b.fail, &b.sel, &b.sel2};
+  for (auto p : ip) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+  }
+  b.cap = 0;
+  b.has_w = false;
+}
+
+extern "C" void gpb_destroy(gpb_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  free_bufs(ctx->ws);
+  double* p[] = {ctx->dX, ctx->dy, ctx->ds2, ctx->pXs, ctx->pys, ctx->ps2s, ctx->pBt, ctx->pmu,
+                 ctx->pv, ctx->psamp, ctx->pout};
+  for (auto q : p)
+    if (q) cudaFree(q);
+  for (auto& ev : ctx->ev)
+    if (ev) cudaEventDestroy(ev);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+extern "C" const char* gpb_last_error(const gpb_ctx* ctx) {
+  return ctx ? ctx->err.c_str() : g_create_err.c_str();
+}
+
+extern "C" int gpb_set_stream(gpb_ctx* ctx, uint64_t s) {
+  if (!ctx) return GPB_EINVAL;
+  ctx->stream = s ? (cudaStream_t)(uintptr_t)s : ctx->own_stream;
+  return GPB_OK;
+}
+
+extern "C" int gpb_set_workspace_limit(gpb_ctx* ctx, uint64_t bytes) {
+  if (!ctx) return GPB_EINVAL;
+  ctx->ws_limit = (size_t)bytes;
+  return GPB_OK;
+}
+
+extern "C" int64_t gpb_launch_count(const gpb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int gpb_last_timings(const gpb_ctx* ctx, double out[6]) {
+  if (!ctx || !out) return GPB_EINVAL;
+  for (int i = 0; i < 6; ++i) out[i] = ctx->timings[i];
+  return GPB_OK;
+}
+
+static int fill_model(Model& md, int cov_kind, int degree, int ard, int mean_kind, const int nz[3],
+                      int D) {
+  if (cov_kind < 0 || cov_kind > 2) return GPB_EINVAL;
+  if (cov_kind == GPB_COV_MATERN && degree != 1 && degree != 3 && degree != 5) return GPB_EINVAL;
+  if (cov_kind == GPB_COV_RQ && !ard) return GPB_EINVAL;   // the reference has no isotropic RQ
+  if (mean_kind < 0 || mean_kind > 2) return GPB_EINVAL;
+  if (nz[0] < 0 || nz[0] > 1 || nz[1] < 0 || nz[1] > 2 || nz[2] < 0 || nz[2] > 1) return GPB_EINVAL;
+  md.cov_kind = cov_kind;
+  md.degree = degree;
+  md.ard = ard ? 1 : 0;
+  md.mean_kind = mean_kind;
+  md.nz0 = nz[0];
+  md.nz1 = nz[1];
+  md.nz2 = nz[2];
+  md.D = D;
+  md.cov_n = cov_count(cov_kind, md.ard, D);
+  md.noise_n = noise_count(nz[0], nz[1], nz[2]);
+  md.mean_n = mean_count(mean_kind, D);
+  md.P = md.cov_n + md.noise_n + md.mean_n;
+  return GPB_OK;
+}
+
+extern "C" int gpb_set_model(gpb_ctx* ctx, int cov_kind, int matern_degree, int ard, int mean_kind,
+                             const int noise_flags[3]) {
+  if (!ctx || !noise_flags) return GPB_EINVAL;
+  Model md{};
+  if (fill_model(md, cov_kind, matern_degree, ard, mean_kind, noise_flags, ctx->D) != GPB_OK)
+    FAIL(GPB_EINVAL, "gpb_set_model: unsupported model descriptor");
+  ctx->md = md;
+  ctx->has_model = true;
+  return GPB_OK;
+}
+
+extern "C" int gpb_set_data(gpb_ctx* ctx, const double* X, const double* y, const double* s2,
+                            int64_t N, int D) {
+  if (!ctx || !X || !y || N <= 0 || D <= 0) return GPB_EINVAL;
+  if (D > MAXD) FAIL(GPB_EINVAL, "gpb_set_data: D > 32 is not supported by the fused kernels");
+  if (N > 1000000) FAIL(GPB_EINVAL, "gpb_set_data: N too large");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->dX) cudaFree(ctx->dX);
+  if (ctx->dy) cudaFree(ctx->dy);
+  if (ctx->ds2) cudaFree(ctx->ds2);
+  ctx->dX = ctx->dy = ctx->ds2 = nullptr;
+  CK(cudaMalloc(&ctx->dX, sizeof(double) * N * D));
+  CK(cudaMalloc(&ctx->dy, sizeof(double) * N));
+  CK(cudaMemcpy(ctx->dX, X, sizeof(double) * N * D, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->dy, y, sizeof(double) * N, cudaMemcpyHostToDevice));
+  if (s2) {
+    CK(cudaMalloc(&ctx->ds2, sizeof(double) * N));
+    CK(cudaMemcpy(ctx->ds2, s2, sizeof(double) * N, cudaMemcpyHostToDevice));
+  }
+  const int Np = round_up(N, T);
+  if (Np != ctx->Np || D != ctx->D) free_bufs(ctx->ws);
+  ctx->N = N;
+  ctx->D = D;
+  ctx->Np = Np;
+  ctx->Nt = Np / T;
+  ctx->has_data = true;
+  if (ctx->has_model) {
+    const int nz[3] = {ctx->md.nz0, ctx->md.nz1, ctx->md.nz2};
+    fill_model(ctx->md, ctx->md.cov_kind, ctx->md.degree, ctx->md.ard, ctx->md.mean_kind, nz, D);
+  }
+  return GPB_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// buffers
+// ---------------------------------------------------------------------------------
+static size_t per_slot_bytes(int Np, int D, int P, int cov_n, bool with_w) {
+  const size_t nt = Np / T;
+  size_t b = (size_t)Np * Np * 8 * (with_w ? 2 : 1);
+  b += 2 * nt * T * T * 8;                     // Dbuf, DTbuf
+  b += (size_t)D * Np * 8 + 6 * (size_t)Np * 8;
+  b += nt * 8 + (size_t)P * 16 + 64;
+  b += nt * (nt + 1) / 2 * (size_t)cov_n * 8;  // gpart
+  return b;
+}
+
+static int alloc_bufs(gpb_ctx* ctx, Bufs& b, int cap, bool with_w, int Np, int D, const Model& md) {
+  free_bufs(b);
+  b.Np = Np;
+  b.Nt = Np / T;
+  b.D = D;
+  b.P = md.P;
+  const size_t smat = (size_t)Np * Np;
+  const size_t nt = b.Nt;
+  CK(cudaMalloc(&b.Abuf, smat * 8 * cap));
+  if (with_w) CK(cudaMalloc(&b.Wbuf, smat * 8 * cap));
+  CK(cudaMalloc(&b.Dbuf, nt * T * T * 8 * cap));
+  CK(cudaMalloc(&b.DTbuf, nt * T * T * 8 * cap));
+  CK(cudaMalloc(&b.xs, (size_t)D * Np * 8 * cap));
+  CK(cudaMalloc(&b.resid, (size_t)Np * 8 * cap));
+  CK(cudaMalloc(&b.sn2v, (size_t)Np * 8 * cap));
+  CK(cudaMalloc(&b.bvec, (size_t)Np * 8 * cap));
+  CK(cudaMalloc(&b.zvec, (size_t)Np * 8 * cap));
+  CK(cudaMalloc(&b.alpha, (size_t)Np * 8 * cap));
+  CK(cudaMalloc(&b.logdet, nt * 8 * cap));
+  CK(cudaMalloc(&b.mult, (size_t)8 * cap));
+  CK(cudaMalloc(&b.hyp, (size_t)std::max(md.P, 1) * 8 * cap));
+  CK(cudaMalloc(&b.nlz, (size_t)8 * cap));
+  CK(cudaMalloc(&b.dnlz, (size_t)std::max(md.P, 1) * 8 * cap));
+  CK(cudaMalloc(&b.gpart, nt * (nt + 1) / 2 * (size_t)std::max(md.cov_n, 1) * 8 * cap));
+  CK(cudaMalloc(&b.sp, sizeof(SlotP) * cap));
+  CK(cudaMalloc(&b.fail, sizeof(int) * cap));
+  CK(cudaMalloc(&b.sel, sizeof(int) * cap));
+  CK(cudaMalloc(&b.sel2, sizeof(int) * cap));
+  b.cap = cap;
+  b.has_w = with_w;
+  return GPB_OK;
+}
+
+static int ensure_ws(gpb_ctx* ctx, long long B, bool with_w) {
+  Bufs& w = ctx->ws;
+  const Model& md = ctx->md;
+  size_t freeb = 0, totalb = 0;
+  CK(cudaMemGetInfo(&freeb, &totalb));
+  size_t have = 0;
+  if (w.cap) have = per_slot_bytes(w.Np, w.D, w.P, md.cov_n, w.has_w) * w.cap;
+  size_t limit = ctx->ws_limit ? ctx->ws_limit : (size_t)((freeb + have) * 0.70);
+  const size_t per = per_slot_bytes(ctx->Np, ctx->D, md.P, md.cov_n, with_w || w.has_w);
+  long long fit = (long long)(limit / per);
+  if (fit < 1) FAIL(GPB_ENOMEM, "workspace for one matrix does not fit in device memory");
+  const int want = (int)std::min<long long>(std::min<long long>(B, fit), 32768);
+  const bool ok = w.cap >= want && (w.has_w || !with_w) && w.Np == ctx->Np && w.D == ctx->D &&
+                  w.P == md.P;
+  if (ok) return GPB_OK;
+  return alloc_bufs(ctx, w, want, with_w || w.has_w, ctx->Np, ctx->D, md);
+}
+
+// ---------------------------------------------------------------------------------
+// pipeline pieces (all asynchronous on ctx->stream)
+// ---------------------------------------------------------------------------------
+static BatchBufs batch_bufs(const Bufs& b, const int* sel) {
+  BatchBufs bb;
+  bb.Abuf = b.Abuf;
+  bb.Wbuf = b.Wbuf;
+  bb.Dbuf = b.Dbuf;
+  bb.DTbuf = b.DTbuf;
+  bb.sel = sel;
+  bb.smat = b.smat();
+  bb.Np = b.Np;
+  bb.Nt = b.Nt;
+  return bb;
+}
+
+template <int KIND>
+static void launch_build(gpb_ctx* ctx, const BuildArgs& a, dim3 grid, size_t smem) {
+  build_kernel<KIND><<<grid, 256, smem, ctx->stream>>>(a);
+  LAUNCHED(ctx);
+}
+
+static void run_prep_build(gpb_ctx* ctx, Bufs& b, const Model& md, long long N, const int* sel,
+                           int nsel) {
+  PrepArgs pa;
+  pa.md = md;
+  pa.N = (int)N;
+  pa.Np = b.Np;
+  pa.X = ctx->dX;
+  pa.y = ctx->dy;
+  pa.s2 = ctx->ds2;
+  pa.hyp = b.hyp;
+  pa.sel = sel;
+  pa.mult = b.mult;
+  pa.xs = b.xs;
+  pa.resid = b.resid;
+  pa.sn2v = b.sn2v;
+  pa.sp = b.sp;
+  prep_kernel<<<nsel, 256, 0, ctx->stream>>>(pa);
+  LAUNCHED(ctx);
+
+  BuildArgs ba;
+  ba.D = md.D;
+  ba.N = (int)N;
+  ba.Np = b.Np;
+  ba.Nt = b.Nt;
+  ba.sel = sel;
+  ba.xs = b.xs;
+  ba.sn2v = b.sn2v;
+  ba.sp = b.sp;
+  ba.Abuf = b.Abuf;
+  ba.smat = b.smat();
+  ba.full = 0;
+  dim3 grid((unsigned)(b.Nt * (b.Nt + 1) / 2), (unsigned)nsel);
+  const size_t smem = (size_t)2 * md.D * T * 8;
+  switch (kind_code(md.cov_kind, md.degree)) {
+    case 0: launch_build<0>(ctx, ba, grid, smem); break;
+    case 1: launch_build<1>(ctx, ba, grid, smem); break;
+    case 3: launch_build<3>(ctx, ba, grid, smem); break;
+    case 5: launch_build<5>(ctx, ba, grid, smem); break;
+    default: launch_build<2>(ctx, ba, grid, smem); break;
+  }
+  // right-hand side of the forward solve: b = y - m
+  copy_kernel<<<grid1d((long long)b.Np * b.cap), 256, 0, ctx->stream>>>(b.bvec, b.resid,
+                                                                        (long long)b.Np * b.cap);
+  LAUNCHED(ctx);
+}
+
+// blocked right-looking Cholesky of every selected slot (lower, in place) with the forward
+// substitution z = L^-1 (y - m) carried along.
+static void run_potrf(gpb_ctx* ctx, Bufs& b, long long N, const int* sel, int nsel, bool write_w,
+                      bool with_rhs = true) {
+  const BatchBufs bb = batch_bufs(b, sel);
+  for (int k = 0; k < b.Nt; ++k) {
+    DiagArgs da;
+    da.Abuf = b.Abuf;
+    da.Wbuf = write_w ? b.Wbuf : nullptr;
+    da.Dbuf = b.Dbuf;
+    da.DTbuf = b.DTbuf;
+    da.sel = sel;
+    da.smat = b.smat();
+    da.Np = b.Np;
+    da.Nt = b.Nt;
+    da.N = (int)N;
+    da.k = k;
+    da.bvec = with_rhs ? b.bvec : nullptr;
+    da.zvec = with_rhs ? b.zvec : nullptr;
+    da.logdet = b.logdet;
+    da.fail = b.fail;
+    diag_kernel<<<nsel, 256, DIAG_SMEM, ctx->stream>>>(da);
+    LAUNCHED(ctx);
+    const int n = b.Nt - k - 1;
+    if (n <= 0) break;
+    launch_gemm(ctx, OpPanel{bb, k}, dim3((unsigned)n, (unsigned)nsel));
+    if (with_rhs) {
+      VecArgs va;
+      va.Abuf = b.Abuf;
+      va.DTbuf = b.DTbuf;
+      va.sel = sel;
+      va.smat = b.smat();
+      va.Np = b.Np;
+      va.Nt = b.Nt;
+      va.k = k;
+      va.bvec = b.bvec;
+      va.zvec = b.zvec;
+      va.alpha = b.alpha;
+      va.sp = b.sp;
+      fwd_update_kernel<<<dim3((unsigned)n, (unsigned)nsel), T, 0, ctx->stream>>>(va);
+      LAUNCHED(ctx);
+    }
+    launch_gemm(ctx, OpSyrk{bb, k}, dim3((unsigned)(n * (n + 1) / 2), (unsigned)nsel));
+  }
+}
+
+// alpha = L^-T z / sl
+static void run_bwd(gpb_ctx* ctx, Bufs& b, const int* sel, int nsel) {
+  copy_kernel<<<grid1d((long long)b.Np * b.cap), 256, 0, ctx->stream>>>(b.bvec, b.zvec,
+                                                                        (long long)b.Np * b.cap);
+  LAUNCHED(ctx);
+  for (int i = b.Nt - 1; i >= 0; --i) {
+    VecArgs va;
+    va.Abuf = b.Abuf;
+    va.DTbuf = b.DTbuf;
+    va.sel = sel;
+    va.smat = b.smat();
+    va.Np = b.Np;
+    va.Nt = b.Nt;
+    va.k = i;
+    va.bvec = b.bvec;
+    va.zvec = b.zvec;
+    va.alpha = b.alpha;
+    va.sp = b.sp;
+    bwd_step_kernel<<<dim3((unsigned)std::max(i, 1), (unsigned)nsel), T, 0, ctx->stream>>>(va);
+    LAUNCHED(ctx);
+  }
+}
+
+// W = L^-1 (lower tiles of Wbuf; dual: also W^T in the upper tiles); then optionally
+// Ainv = W^T W into the lower tiles of Abuf.
+static void run_inverse(gpb_ctx* ctx, Bufs& b, const int* sel, int nsel, bool dual, bool syrk2) {
+  const BatchBufs bb = batch_bufs(b, sel);
+  const int Nt = b.Nt;
+  if (Nt > 1) {
+    launch_gemm(ctx, OpHpass{bb}, dim3((unsigned)(Nt * (Nt - 1) / 2), (unsigned)nsel));
+    for (int j = Nt - 2; j >= 0; --j)
+      launch_gemm(ctx, OpWrec{bb, j, dual ? 1 : 0}, dim3((unsigned)(Nt - 1 - j), (unsigned)nsel));
+  }
+  if (syrk2) launch_gemm(ctx, OpSyrk2{bb}, dim3((unsigned)(Nt * (Nt + 1) / 2), (unsigned)nsel));
+}
+
+template <int KIND>
+static void launch_grad(gpb_ctx* ctx, const GradArgs& a, dim3 grid, int ard, int D) {
+  const int dp = !ard ? 0 : (D <= 8 ? 8 : (D <= 16 ? 16 : 32));
+  const size_t smem = ((size_t)2 * D * T + 2 * T + 8 * (size_t)((dp ? dp : 1) + 2)) * 8;
+  switch (dp) {
+    case 0: grad_kernel<KIND, 0><<<grid, 256, smem, ctx->stream>>>(a); break;
+    case 8: grad_kernel<KIND, 8><<<grid, 256, smem, ctx->stream>>>(a); break;
+    case 16: grad_kernel<KIND, 16><<<grid, 256, smem, ctx->stream>>>(a); break;
+    default: grad_kernel<KIND, 32><<<grid, 256, smem, ctx->stream>>>(a); break;
+  }
+  LAUNCHED(ctx);
+}
+
+static void run_grad(gpb_ctx* ctx, Bufs& b, const Model& md, long long N, const int* sel, int nsel) {
+  GradArgs ga;
+  ga.D = md.D;
+  ga.N = (int)N;
+  ga.Np = b.Np;
+  ga.Nt = b.Nt;
+  ga.cov_n = md.cov_n;
+  ga.sel = sel;
+  ga.xs = b.xs;
+  ga.sp = b.sp;
+  ga.Abuf = b.Abuf;
+  ga.alpha = b.alpha;
+  ga.gpart = b.gpart;
+  ga.smat = b.smat();
+  dim3 grid((unsigned)(b.Nt * (b.Nt + 1) / 2), (unsigned)nsel);
+  switch (kind_code(md.cov_kind, md.degree)) {
+    case 0: launch_grad<0>(ctx, ga, grid, md.ard, md.D); break;
+    case 1: launch_grad<1>(ctx, ga, grid, md.ard, md.D); break;
+    case 3: launch_grad<3>(ctx, ga, grid, md.ard, md.D); break;
+    case 5: launch_grad<5>(ctx, ga, grid, md.ard, md.D); break;
+    default: launch_grad<2>(ctx, ga, grid, md.ard, md.D); break;
+  }
+  GradFinalArgs fa;
+  fa.md = md;
+  fa.N = (int)N;
+  fa.Np = b.Np;
+  fa.Nt = b.Nt;
+  fa.sel = sel;
+  fa.X = ctx->dX;
+  fa.y = ctx->dy;
+  fa.s2 = ctx->ds2;
+  fa.hyp = b.hyp;
+  fa.sp = b.sp;
+  fa.Abuf = b.Abuf;
+  fa.alpha = b.alpha;
+  fa.gpart = b.gpart;
+  fa.dnlZ = b.dnlz;
+  fa.smat = b.smat();
+  grad_final_kernel<<<nsel, 256, 0, ctx->stream>>>(fa);
+  LAUNCHED(ctx);
+}
+
+// Factor `n` slots (hyp already in b.hyp): build + potrf with the reference's x10 jitter
+// retry per element (gaussian_process.py:2413-2421, :2430-2438).  On return b.sel holds the
+// identity list, status_h[s] = 1 for slots that failed all 10 attempts.
+static int factor_with_retry(gpb_ctx* ctx, Bufs& b, const Model& md, long long N, int n, bool write_w,
+                             std::vector<int>& status_h) {
+  std::vector<int> ident(n), failh(n);
+  for (int i = 0; i < n; ++i) ident[i] = i;
+  CK(cudaMemcpyAsync(b.sel, ident.data(), sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
+  fill_kernel<<<grid1d(b.cap), 256, 0, ctx->stream>>>(b.mult, 1.0, b.cap);
+  LAUNCHED(ctx);
+  CK(cudaMemsetAsync(b.fail, 0, sizeof(int) * b.cap, ctx->stream));
+  status_h.assign(n, 0);
+  const int* sel = b.sel;
+  int nsel = n;
+  std::vector<int> cur = ident;
+  for (int attempt = 0; attempt < 10; ++attempt) {
+    run_prep_build(ctx, b, md, N, sel, nsel);
+    run_potrf(ctx, b, N, sel, nsel, write_w);
+    CK(cudaMemcpyAsync(failh.data(), b.fail, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<int> next;
+    for (int s : cur)
+      if (failh[s]) next.push_back(s);
+    if (next.empty()) break;
+    if (attempt == 9) {
+      for (int s : next) status_h[s] = 1;
+      break;
+    }
+    // sn2_mult *= 10 for the failed slots, clear their flags, go again on the compacted list
+    CK(cudaMemcpyAsync(b.sel2, next.data(), sizeof(int) * next.size(), cudaMemcpyHostToDevice,
+                       ctx->stream));
+    scale_mult_kernel<<<(unsigned)((next.size() + 255) / 256), 256, 0, ctx->stream>>>(
+        b.mult, b.fail, b.sel2, (int)next.size());
+    LAUNCHED(ctx);
+    CK(cudaMemsetAsync(b.fail, 0, sizeof(int) * b.cap, ctx->stream));
+    cur = next;
+    sel = b.sel2;
+    nsel = (int)next.size();
+  }
+  return GPB_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// nlZ (+ gradient), batched
+// ---------------------------------------------------------------------------------
+static int nlz_batch_impl(gpb_ctx* ctx, const double* hyp, bool hyp_on_device, int64_t B,
+                          int want_grad, double* nlZ, double* dnlZ, double* sn2_mult,
+                          int32_t* status, bool out_on_device) {
+  if (!ctx) return GPB_EINVAL;
+  if (!ctx->has_model || !ctx->has_data) FAIL(GPB_ESTATE, "gpb_nlz_batch: set model and data first");
+  if (!hyp || !nlZ || B <= 0) FAIL(GPB_EINVAL, "gpb_nlz_batch: bad arguments");
+  if (want_grad && !dnlZ) FAIL(GPB_EINVAL, "gpb_nlz_batch: dnlZ is NULL");
+  CK(cudaSetDevice(ctx->device));
+  const Model md = ctx->md;
+  const int P = md.P;
+  int rc = ensure_ws(ctx, B, want_grad != 0);
+  if (rc != GPB_OK) return rc;
+  Bufs& b = ctx->ws;
+  const cudaMemcpyKind kin = hyp_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  const cudaMemcpyKind kout = out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  for (int i = 0; i < 6; ++i) ctx->timings[i] = 0.0;
+  std::vector<int> status_h;
+  std::vector<double> mult_h;
+
+  for (int64_t row0 = 0; row0 < B; row0 += b.cap) {
+    const int n = (int)std::min<int64_t>(b.cap, B - row0);
+    if (P > 0) CK(cudaMemcpyAsync(b.hyp, hyp + row0 * P, sizeof(double) * n * P, kin, ctx->stream));
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    rc = factor_with_retry(ctx, b, md, ctx->N, n, want_grad != 0, status_h);
+    if (rc != GPB_OK) return rc;
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    NlzArgs na;
+    na.sel = b.sel;
+    na.N = (int)ctx->N;
+    na.Np = b.Np;
+    na.Nt = b.Nt;
+    na.zvec = b.zvec;
+    na.logdet = b.logdet;
+    na.sp = b.sp;
+    na.nlz = b.nlz;
+    nlz_kernel<<<n, 256, 0, ctx->stream>>>(na);
+    LAUNCHED(ctx);
+    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    if (want_grad) {
+      run_bwd(ctx, b, b.sel, n);
+      CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+      run_inverse(ctx, b, b.sel, n, /*dual=*/true, /*syrk2=*/true);
+      CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+      run_grad(ctx, b, md, ctx->N, b.sel, n);
+    } else {
+      CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+      CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+    }
+    CK(cudaEventRecord(ctx->ev[5], ctx->stream));
+    // results
+    bool anyfail = false;
+    for (int s = 0; s < n; ++s) anyfail |= status_h[s] != 0;
+    if (anyfail) {
+      // the reference raises for these rows; report NaN and status 1
+      std::vector<double> nl(n);
+      CK(cudaMemcpyAsync(nl.data(), b.nlz, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      for (int s = 0; s < n; ++s)
+        if (status_h[s]) nl[s] = NAN;
+      CK(cudaMemcpyAsync(b.nlz, nl.data(), sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+    }
+    CK(cudaMemcpyAsync(nlZ + row0, b.nlz, sizeof(double) * n, kout, ctx->stream));
+    if (want_grad && P > 0)
+      CK(cudaMemcpyAsync(dnlZ + row0 * P, b.dnlz, sizeof(double) * n * P, kout, ctx->stream));
+    if (sn2_mult) CK(cudaMemcpyAsync(sn2_mult + row0, b.mult, sizeof(double) * n, kout, ctx->stream));
+    if (status) {
+      if (out_on_device) {
+        CK(cudaMemcpyAsync(status + row0, status_h.data(), sizeof(int) * n, cudaMemcpyHostToDevice,
+                           ctx->stream));
+      } else {
+        for (int s = 0; s < n; ++s) status[row0 + s] = status_h[s];
+      }
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms;
+    const int pairs[5][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 4}, {4, 5}};
+    // {build+potrf (with retries), nlz, solve, inverse, gradient}
+    for (int i = 0; i < 5; ++i) {
+      CK(cudaEventElapsedTime(&ms, ctx->ev[pairs[i][0]], ctx->ev[pairs[i][1]]));
+      ctx->timings[i] += ms;
+    }
+    CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[5]));
+    ctx->timings[5] += ms;
+  }
+  return GPB_OK;
+}
+
+extern "C" int gpb_nlz_batch(gpb_ctx* ctx, const double* hyp, int64_t B, int want_grad, double* nlZ,
+                             double* dnlZ, double* sn2_mult, int32_t* status) {
+  return nlz_batch_impl(ctx, hyp, false, B, want_grad, nlZ, dnlZ, sn2_mult, status, false);
+}
+
+extern "C" int gpb_nlz_batch_dev(gpb_ctx* ctx, const double* d_hyp, int64_t B, int want_grad,
+                                 double* d_nlZ, double* d_dnlZ, double* d_sn2_mult,
+                                 int32_t* d_status) {
+  return nlz_batch_impl(ctx, d_hyp, true, B, want_grad, d_nlZ, d_dnlZ, d_sn2_mult, d_status, true);
+}
+
+// ---------------------------------------------------------------------------------
+// posteriors
+// ---------------------------------------------------------------------------------
+extern "C" int gpb_posterior_batch(gpb_ctx* ctx, const double* hyp, int64_t B, gpb_post** out) {
+  if (!ctx || !out) return GPB_EINVAL;
+  *out = nullptr;
+  if (!ctx->has_model || !ctx->has_data) FAIL(GPB_ESTATE, "gpb_posterior_batch: set model and data first");
+  if (!hyp || B <= 0 || B > 32768) FAIL(GPB_EINVAL, "gpb_posterior_batch: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  const Model md = ctx->md;
+  size_t freeb = 0, totalb = 0;
+  CK(cudaMemGetInfo(&freeb, &totalb));
+  if (per_slot_bytes(ctx->Np, ctx->D, md.P, md.cov_n, true) * (size_t)B > freeb * 0.95)
+    FAIL(GPB_ENOMEM, "gpb_posterior_batch: the posterior factors do not fit in device memory");
+  gpb_post* post = new gpb_post();
+  post->ctx = ctx;
+  post->N = ctx->N;
+  post->md = md;
+  int rc = alloc_bufs(ctx, post->b, (int)B, true, ctx->Np, ctx->D, md);
+  if (rc != GPB_OK) {
+    free_bufs(post->b);
+    delete post;
+    return rc;
+  }
+  Bufs& b = post->b;
+  post->hyp.assign(hyp, hyp + B * md.P);
+  auto bail = [&](int code) {
+    free_bufs(post->b);
+    delete post;
+    return code;
+  };
+  if (md.P > 0) {
+    cudaError_t e = cudaMemcpyAsync(b.hyp, hyp, sizeof(double) * B * md.P, cudaMemcpyHostToDevice,
+                                    ctx->stream);
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return bail(GPB_ECUDA); }
+  }
+  rc = factor_with_retry(ctx, b, md, ctx->N, (int)B, true, post->status);
+  if (rc != GPB_OK) return bail(rc);
+  run_bwd(ctx, b, b.sel, (int)B);
+  post->sp.resize(B);
+  cudaError_t e = cudaMemcpyAsync(post->sp.data(), b.sp, sizeof(SlotP) * B, cudaMemcpyDeviceToHost,
+                                  ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return bail(GPB_ECUDA); }
+  // low-noise samples store L = -(K + sn2_mult*diag(sn2))^-1 (gaussian_process.py:2440-2448):
+  // build the full inverse now; L_chol samples get W = L^-1 lazily at the first predict.
+  std::vector<int> low;
+  for (int s = 0; s < (int)B; ++s)
+    if (!post->sp[s].lchol && !post->status[s]) low.push_back(s);
+  if (!low.empty()) {
+    e = cudaMemcpyAsync(b.sel2, low.data(), sizeof(int) * low.size(), cudaMemcpyHostToDevice,
+                        ctx->stream);
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return bail(GPB_ECUDA); }
+    run_inverse(ctx, b, b.sel2, (int)low.size(), true, true);
+    for (int s : low) {
+      symmetrize_kernel<<<grid1d(b.smat()), 256, 0, ctx->stream>>>(b.Abuf + s * b.smat(), b.Np);
+      LAUNCHED(ctx);
+    }
+    e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return bail(GPB_ECUDA); }
+  }
+  *out = post;
+  return GPB_OK;
+}
+
+extern "C" int64_t gpb_posterior_count(const gpb_post* post) { return post ? post->b.cap : 0; }
+
+extern "C" void gpb_posterior_free(gpb_post* post) {
+  if (!post) return;
+  cudaSetDevice(post->ctx->device);
+  cudaStreamSynchronize(post->ctx->stream);
+  free_bufs(post->b);
+  delete post;
+}
+
+extern "C" int gpb_posterior_fetch(const gpb_post* post, int64_t s, int field, double* out) {
+  if (!post || !out) return GPB_EINVAL;
+  gpb_ctx* ctx = post->ctx;
+  if (s < 0 || s >= post->b.cap) FAIL(GPB_EINVAL, "gpb_posterior_fetch: sample index out of range");
+  CK(cudaSetDevice(ctx->device));
+  const Bufs& b = post->b;
+  const SlotP& p = post->sp[s];
+  const long long N = post->N;
+  switch (field) {
+    case GPB_POST_ALPHA:
+      CK(cudaMemcpyAsync(out, b.alpha + s * b.Np, sizeof(double) * N, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      return GPB_OK;
+    case GPB_POST_SW:
+      out[0] = 1.0 / sqrt(p.sn2_min * p.mult);     // gaussian_process.py:2517
+      return GPB_OK;
+    case GPB_POST_SN2MULT: out[0] = p.mult; return GPB_OK;
+    case GPB_POST_LCHOL: out[0] = p.lchol ? 1.0 : 0.0; return GPB_OK;
+    case GPB_POST_STATUS: out[0] = post->status[s]; return GPB_OK;
+    case GPB_POST_L: {
+      double* tmp = nullptr;
+      CK(cudaMalloc(&tmp, sizeof(double) * N * N));
+      fetch_L_kernel<<<grid1d(N * N), 256, 0, ctx->stream>>>(b.Abuf + s * b.smat(), b.Np, (int)N,
+                                                             p.lchol, tmp);
+      LAUNCHED(ctx);
+      cudaError_t e = cudaMemcpyAsync(out, tmp, sizeof(double) * N * N, cudaMemcpyDeviceToHost, ctx->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+      cudaFree(tmp);
+      if (e != cudaSuccess) FAIL(GPB_ECUDA, cudaGetErrorString(e));
+      return GPB_OK;
+    }
+    default: FAIL(GPB_EINVAL, "gpb_posterior_fetch: unknown field");
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// predict
+// ---------------------------------------------------------------------------------
+static int grow(gpb_ctx* ctx, double** p, size_t* have, size_t need) {
+  if (*have >= need) return GPB_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *have = 0;
+  CK(cudaMalloc(p, need * sizeof(double)));
+  *have = need;
+  return GPB_OK;
+}
+
+static int ensure_w(gpb_ctx* ctx, gpb_post* post) {
+  if (post->w_ready) return GPB_OK;
+  Bufs& b = post->b;
+  std::vector<int> high;
+  for (int s = 0; s < b.cap; ++s)
+    if (post->sp[s].lchol && !post->status[s]) high.push_back(s);
+  if (!high.empty()) {
+    CK(cudaMemcpyAsync(b.sel2, high.data(), sizeof(int) * high.size(), cudaMemcpyHostToDevice, ctx->stream));
+    run_inverse(ctx, b, b.sel2, (int)high.size(), false, false);
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  post->w_ready = true;
+  return GPB_OK;
+}
+
+template <int KIND>
+static void launch_ks(gpb_ctx* ctx, const KsArgs& a, dim3 grid, size_t smem) {
+  ks_build_kernel<KIND><<<grid, 256, smem, ctx->stream>>>(a);
+  LAUNCHED(ctx);
+}
+
+static int predict_impl(gpb_ctx* ctx, const gpb_post* cpost, const double* Xs, const double* ys,
+                        const double* s2s, int64_t M, int add_noise, int separate, int want_lpd,
+                        double* mu, double* s2, double* lpd, bool on_device) {
+  if (!ctx || !cpost) return GPB_EINVAL;
+  gpb_post* post = const_cast<gpb_post*>(cpost);
+  if (!Xs || !mu || !s2 || M <= 0) FAIL(GPB_EINVAL, "gpb_predict: bad arguments");
+  if (want_lpd && (!ys || !lpd)) FAIL(GPB_EINVAL, "Cannot calculate log predictive density without y_star.");
+  CK(cudaSetDevice(ctx->device));
+  for (int st : post->status)
+    if (st) FAIL(GPB_ESTATE, "gpb_predict: a posterior sample has no valid factorisation");
+  int rc = ensure_w(ctx, post);
+  if (rc != GPB_OK) return rc;
+  const Bufs& b = post->b;
+  const Model md = post->md;
+  const int Ns = b.cap, D = md.D, Np = b.Np, Nt = b.Nt;
+  const int need_ys2 = (add_noise || want_lpd) ? 1 : 0;
+  const int Mc = (int)std::min<int64_t>(M, 8192);
+  const int McpMax = round_up(Mc, T);
+  if ((rc = grow(ctx, &ctx->pXs, &ctx->pXs_n, (size_t)3 * McpMax * std::max(D, 1))) != GPB_OK) return rc;
+  if ((rc = grow(ctx, &ctx->pBt, &ctx->pBt_n, (size_t)McpMax * Np)) != GPB_OK) return rc;
+  if ((rc = grow(ctx, &ctx->pmu, &ctx->ppart_n, (size_t)2 * Nt * McpMax)) != GPB_OK) return rc;
+  if ((rc = grow(ctx, &ctx->psamp, &ctx->psamp_n, (size_t)4 * Ns * McpMax)) != GPB_OK) return rc;
+  if ((rc = grow(ctx, &ctx->pout, &ctx->pout_n, (size_t)3 * McpMax * (separate ? Ns : 1))) != GPB_OK) return rc;
+  double* dXs = ctx->pXs;
+  double* dys = ctx->pXs + (size_t)McpMax * D;
+  double* ds2s = dys + McpMax;
+  double* mupart = ctx->pmu;
+  double* vpart = ctx->pmu + (size_t)Nt * McpMax;
+  const int kc = kind_code(md.cov_kind, md.degree);
+  const size_t ks_smem = ((size_t)2 * D * T + T + 8 * T) * 8;
+
+  for (int64_t c0 = 0; c0 < M; c0 += Mc) {
+    const int mc = (int)std::min<int64_t>(Mc, M - c0);
+    const int Mcp = round_up(mc, T);
+    const double *cXs, *cys = nullptr, *cs2s = nullptr;
+    if (on_device) {
+      cXs = Xs + c0 * D;
+    } else {
+      CK(cudaMemcpyAsync(dXs, Xs + c0 * D, sizeof(double) * mc * D, cudaMemcpyHostToDevice, ctx->stream));
+      cXs = dXs;
+      if (ys) {
+        CK(cudaMemcpyAsync(dys, ys + c0, sizeof(double) * mc, cudaMemcpyHostToDevice, ctx->stream));
+        cys = dys;
+      }
+      if (s2s) {
+        CK(cudaMemcpyAsync(ds2s, s2s + c0, sizeof(double) * mc, cudaMemcpyHostToDevice, ctx->stream));
+        cs2s = ds2s;
+      }
+    }
+    double* mu_s = ctx->psamp;
+    double* s2_s = mu_s + (size_t)Ns * Mcp;
+    double* ys2_s = s2_s + (size_t)Ns * Mcp;
+    double* lpd_s = ys2_s + (size_t)Ns * Mcp;
+    for (int s = 0; s < Ns; ++s) {
+      const SlotP& p = post->sp[s];
+      KsArgs ka;
+      ka.md = md;
+      ka.N = (int)post->N;
+      ka.Np = Np;
+      ka.Nt = Nt;
+      ka.mc = mc;
+      ka.Mcp = Mcp;
+      ka.Xs = cXs;
+      ka.hyp = b.hyp + (size_t)s * md.P;
+      ka.xs = b.xs + (size_t)s * D * Np;
+      ka.alpha = b.alpha + (size_t)s * Np;
+      ka.sp = p;
+      ka.scale = p.lchol ? 1.0 / sqrt(p.sn2_min * p.mult) : 1.0;
+      ka.Bt = ctx->pBt;
+      ka.mupart = mupart;
+      dim3 kgrid((unsigned)(Mcp / T), (unsigned)Nt);
+      switch (kc) {
+        case 0: launch_ks<0>(ctx, ka, kgrid, ks_smem); break;
+        case 1: launch_ks<1>(ctx, ka, kgrid, ks_smem); break;
+        case 3: launch_ks<3>(ctx, ka, kgrid, ks_smem); break;
+        case 5: launch_ks<5>(ctx, ka, kgrid, ks_smem); break;
+        default: launch_ks<2>(ctx, ka, kgrid, ks_smem); break;
+      }
+      OpPred op;
+      op.Bt = ctx->pBt;
+      op.ldbt = Mcp;
+      op.Wm = p.lchol ? b.Wbuf + (size_t)s * b.smat() : b.Abuf + (size_t)s * b.smat();
+      op.ldw = Np;
+      op.part = vpart;
+      op.Mcp = Mcp;
+      op.tri = p.lchol ? 1 : 0;
+      op.Np = Np;
+      launch_gemm(ctx, op, dim3((unsigned)(Mcp / T), (unsigned)Nt));
+      FinishArgs fa;
+      fa.md = md;
+      fa.Nt = Nt;
+      fa.mc = mc;
+      fa.Mcp = Mcp;
+      fa.has_data = 1;
+      fa.lchol = p.lchol;
+      fa.Xs = cXs;
+      fa.ys = cys;
+      fa.s2s = cs2s;
+      fa.hyp = b.hyp + (size_t)s * md.P;
+      fa.sp = p;
+      fa.mupart = mupart;
+      fa.vpart = vpart;
+      fa.need_ys2 = need_ys2;
+      fa.want_lpd = want_lpd && separate;
+      fa.mu_s = mu_s + (size_t)s * Mcp;
+      fa.s2_s = s2_s + (size_t)s * Mcp;
+      fa.ys2_s = ys2_s + (size_t)s * Mcp;
+      fa.lpd_s = lpd_s + (size_t)s * Mcp;
+      pred_finish_kernel<<<(unsigned)((mc + 255) / 256), 256, 0, ctx->stream>>>(fa);
+      LAUNCHED(ctx);
+    }
+    const size_t ocols = separate ? Ns : 1;
+    CombineArgs ca;
+    ca.Ns = Ns;
+    ca.mc = mc;
+    ca.Mcp = Mcp;
+    ca.add_noise = add_noise;
+    ca.separate = separate;
+    ca.want_lpd = want_lpd;
+    ca.ys = cys;
+    ca.mu_s = mu_s;
+    ca.s2_s = s2_s;
+    ca.ys2_s = ys2_s;
+    ca.lpd_s = lpd_s;
+    if (on_device) {
+      ca.mu = mu + c0 * ocols;
+      ca.s2 = s2 + c0 * ocols;
+      ca.lpd = nullptr;
+    } else {
+      ca.mu = ctx->pout;
+      ca.s2 = ctx->pout + (size_t)McpMax * ocols;
+      ca.lpd = ctx->pout + (size_t)2 * McpMax * ocols;
+    }
+    pred_combine_kernel<<<(unsigned)((mc + 255) / 256), 256, 0, ctx->stream>>>(ca);
+    LAUNCHED(ctx);
+    if (!on_device) {
+      CK(cudaMemcpyAsync(mu + c0 * ocols, ca.mu, sizeof(double) * mc * ocols, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaMemcpyAsync(s2 + c0 * ocols, ca.s2, sizeof(double) * mc * ocols, cudaMemcpyDeviceToHost, ctx->stream));
+      if (want_lpd)
+        CK(cudaMemcpyAsync(lpd + c0 * ocols, ca.lpd, sizeof(double) * mc * ocols, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));   // scratch is reused by the next chunk
+    }
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GPB_OK;
+}
+
+extern "C" int gpb_predict(gpb_ctx* ctx, const gpb_post* post, const double* Xs, const double* ys,
+                           const double* s2s, int64_t M, int add_noise, int separate, int want_lpd,
+                           double* mu, double* s2, double* lpd) {
+  return predict_impl(ctx, post, Xs, ys, s2s, M, add_noise, separate, want_lpd, mu, s2, lpd, false);
+}
+
+extern "C" int gpb_predict_dev(gpb_ctx* ctx, const gpb_post* post, const double* d_Xs, int64_t M,
+                               int add_noise, int separate, double* d_mu, double* d_s2) {
+  return predict_impl(ctx, post, d_Xs, nullptr, nullptr, M, add_noise, separate, 0, d_mu, d_s2,
+                      nullptr, true);
+}
+
+// ---------------------------------------------------------------------------------
+// plugin surface
+// ---------------------------------------------------------------------------------
+template <int KIND>
+static void launch_cov(gpb_ctx* ctx, const CovArgs& a, long long total) {
+  cov_plugin_kernel<KIND><<<grid1d(total), 256, 0, ctx->stream>>>(a);
+  LAUNCHED(ctx);
+}
+
+extern "C" int gpb_cov(gpb_ctx* ctx, int cov_kind, int matern_degree, int ard, const double* hyp,
+                       const double* X, int64_t N, int D, const double* Xs, int64_t M, int diag,
+                       double* K, double* dK) {
+  if (!ctx) return GPB_EINVAL;
+  if (!hyp || !X || !K || N <= 0 || D <= 0) FAIL(GPB_EINVAL, "gpb_cov: bad arguments");
+  if (dK && (Xs || diag)) FAIL(GPB_EINVAL, "X_star should be None when compute_grad is True.");
+  Model md{};
+  const int nz[3] = {0, 0, 0};
+  if (fill_model(md, cov_kind, matern_degree, ard, 0, nz, D) != GPB_OK)
+    FAIL(GPB_EINVAL, "gpb_cov: unsupported covariance descriptor");
+  CK(cudaSetDevice(ctx->device));
+  const long long cols = diag ? 1 : (Xs ? M : N);
+  const long long total = N * cols;
+  double *dh = nullptr, *dX = nullptr, *dXs = nullptr, *dKd = nullptr, *ddK = nullptr;
+  auto cleanup = [&]() {
+    for (double* p : {dh, dX, dXs, dKd, ddK})
+      if (p) cudaFree(p);
+  };
+#define CKC(call)                                   \
+  do {                                              \
+    cudaError_t e_ = (call);                        \
+    if (e_ != cudaSuccess) {                        \
+      ctx->err = cudaGetErrorString(e_);            \
+      cleanup();                                    \
+      return GPB_ECUDA;                             \
+    }                                               \
+  } while (0)
+  CKC(cudaMalloc(&dh, sizeof(double) * md.cov_n));
+  CKC(cudaMalloc(&dX, sizeof(double) * N * D));
+  CKC(cudaMalloc(&dKd, sizeof(double) * total));
+  CKC(cudaMemcpyAsync(dh, hyp, sizeof(double) * md.cov_n, cudaMemcpyHostToDevice, ctx->stream));
+  CKC(cudaMemcpyAsync(dX, X, sizeof(double) * N * D, cudaMemcpyHostToDevice, ctx->stream));
+  if (Xs && !diag) {
+    CKC(cudaMalloc(&dXs, sizeof(double) * M * D));
+    CKC(cudaMemcpyAsync(dXs, Xs, sizeof(double) * M * D, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (dK) CKC(cudaMalloc(&ddK, sizeof(double) * md.cov_n * N * N));
+  CovArgs a;
+  a.cov_kind = cov_kind;
+  a.degree = matern_degree;
+  a.ard = md.ard;
+  a.D = D;
+  a.N = N;
+  a.M = M;
+  a.hyp = dh;
+  a.X = dX;
+  a.Xs = diag ? nullptr : dXs;
+  a.diag = diag;
+  a.K = dKd;
+  a.dK = ddK;
+  switch (kind_code(cov_kind, matern_degree)) {
+    case 0: launch_cov<0>(ctx, a, total); break;
+    case 1: launch_cov<1>(ctx, a, total); break;
+    case 3: launch_cov<3>(ctx, a, total); break;
+    case 5: launch_cov<5>(ctx, a, total); break;
+    default: launch_cov<2>(ctx, a, total); break;
+  }
+  CKC(cudaMemcpyAsync(K, dKd, sizeof(double) * total, cudaMemcpyDeviceToHost, ctx->stream));
+  if (dK) CKC(cudaMemcpyAsync(dK, ddK, sizeof(double) * md.cov_n * N * N, cudaMemcpyDeviceToHost, ctx->stream));
+  CKC(cudaStreamSynchronize(ctx->stream));
+  CKC(cudaGetLastError());
+  cleanup();
+  return GPB_OK;
+}
+
+extern "C" int gpb_mean(gpb_ctx* ctx, int mean_kind, const double* hyp, const double* X, int64_t N,
+                        int D, double* m, double* dm) {
+  if (!ctx) return GPB_EINVAL;
+  if (!X || !m || N <= 0 || D <= 0 || mean_kind < 0 || mean_kind > 2) FAIL(GPB_EINVAL, "gpb_mean: bad arguments");
+  const int mn = mean_count(mean_kind, D);
+  if (mn > 0 && !hyp) FAIL(GPB_EINVAL, "gpb_mean: hyp is NULL");
+  CK(cudaSetDevice(ctx->device));
+  double *dh = nullptr, *dX = nullptr, *dm_ = nullptr, *ddm = nullptr;
+  auto cleanup = [&]() {
+    for (double* p : {dh, dX, dm_, ddm})
+      if (p) cudaFree(p);
+  };
+  CKC(cudaMalloc(&dh, sizeof(double) * std::max(mn, 1)));
+  CKC(cudaMalloc(&dX, sizeof(double) * N * D));
+  CKC(cudaMalloc(&dm_, sizeof(double) * N));
+  if (mn > 0) CKC(cudaMemcpyAsync(dh, hyp, sizeof(double) * mn, cudaMemcpyHostToDevice, ctx->stream));
+  CKC(cudaMemcpyAsync(dX, X, sizeof(double) * N * D, cudaMemcpyHostToDevice, ctx->stream));
+  if (dm && mn > 0) CKC(cudaMalloc(&ddm, sizeof(double) * N * mn));
+  MeanArgs a;
+  a.mean_kind = mean_kind;
+  a.D = D;
+  a.N = N;
+  a.hyp = dh;
+  a.X = dX;
+  a.m = dm_;
+  a.dm = ddm;
+  mean_plugin_kernel<<<grid1d(N), 256, 0, ctx->stream>>>(a);
+  LAUNCHED(ctx);
+  CKC(cudaMemcpyAsync(m, dm_, sizeof(double) * N, cudaMemcpyDeviceToHost, ctx->stream));
+  if (ddm) CKC(cudaMemcpyAsync(dm, ddm, sizeof(double) * N * mn, cudaMemcpyDeviceToHost, ctx->stream));
+  CKC(cudaStreamSynchronize(ctx->stream));
+  CKC(cudaGetLastError());
+  cleanup();
+  return GPB_OK;
+}
+
+extern "C" int gpb_noise(gpb_ctx* ctx, const int noise_flags[3], const double* hyp, const double* y,
+                         const double* s2, int64_t N, double* sn2, double* dsn2) {
+  if (!ctx) return GPB_EINVAL;
+  if (!noise_flags || !sn2 || N <= 0) FAIL(GPB_EINVAL, "gpb_noise: bad arguments");
+  const int nn = noise_count(noise_flags[0], noise_flags[1], noise_flags[2]);
+  if (nn > 0 && !hyp) FAIL(GPB_EINVAL, "gpb_noise: hyp is NULL");
+  CK(cudaSetDevice(ctx->device));
+  double *dh = nullptr, *dy = nullptr, *ds2 = nullptr, *dsn = nullptr, *ddsn = nullptr;
+  auto cleanup = [&]() {
+    for (double* p : {dh, dy, ds2, dsn, ddsn})
+      if (p) cudaFree(p);
+  };
+  CKC(cudaMalloc(&dh, sizeof(double) * std::max(nn, 1)));
+  CKC(cudaMalloc(&dsn, sizeof(double) * N));
+  if (nn > 0) CKC(cudaMemcpyAsync(dh, hyp, sizeof(double) * nn, cudaMemcpyHostToDevice, ctx->stream));
+  if (y) {
+    CKC(cudaMalloc(&dy, sizeof(double) * N));
+    CKC(cudaMemcpyAsync(dy, y, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (s2) {
+    CKC(cudaMalloc(&ds2, sizeof(double) * N));
+    CKC(cudaMemcpyAsync(ds2, s2, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (dsn2 && nn > 0) CKC(cudaMalloc(&ddsn, sizeof(double) * N * nn));
+  NoiseArgs a;
+  a.nz0 = noise_flags[0];
+  a.nz1 = noise_flags[1];
+  a.nz2 = noise_flags[2];
+  a.N = N;
+  a.hyp = dh;
+  a.y = dy;
+  a.s2 = ds2;
+  a.sn2 = dsn;
+  a.dsn2 = ddsn;
+  noise_plugin_kernel<<<grid1d(N), 256, 0, ctx->stream>>>(a);
+  LAUNCHED(ctx);
+  CKC(cudaMemcpyAsync(sn2, dsn, sizeof(double) * N, cudaMemcpyDeviceToHost, ctx->stream));
+  if (ddsn) CKC(cudaMemcpyAsync(dsn2, ddsn, sizeof(double) * N * nn, cudaMemcpyDeviceToHost, ctx->stream));
+  CKC(cudaStreamSynchronize(ctx->stream));
+  CKC(cudaGetLastError());
+  cleanup();
+  return GPB_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// test / measurement hooks
+// ---------------------------------------------------------------------------------
+extern "C" int gpb_debug_gemm_nt(gpb_ctx* ctx, const double* A, const double* B, double* C, int M,
+                                 int N, int K, double alpha, double beta) {
+  if (!ctx) return GPB_EINVAL;
+  if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0 || M % BM || N % BN || K % BK)
+    FAIL(GPB_EINVAL, "gpb_debug_gemm_nt: M,N must be multiples of 128 and K of 16");
+  CK(cudaSetDevice(ctx->device));
+  double *dA = nullptr, *dB = nullptr, *dC = nullptr;
+  auto cleanup = [&]() {
+    for (double* p : {dA, dB, dC})
+      if (p) cudaFree(p);
+  };
+  CKC(cudaMalloc(&dA, sizeof(double) * M * K));
+  CKC(cudaMalloc(&dB, sizeof(double) * N * K));
+  CKC(cudaMalloc(&dC, sizeof(double) * M * N));
+  CKC(cudaMemcpyAsync(dA, A, sizeof(double) * M * K, cudaMemcpyHostToDevice, ctx->stream));
+  CKC(cudaMemcpyAsync(dB, B, sizeof(double) * N * K, cudaMemcpyHostToDevice, ctx->stream));
+  CKC(cudaMemcpyAsync(dC, C, sizeof(double) * M * N, cudaMemcpyHostToDevice, ctx->stream));
+  OpGeneric op{dA, dB, dC, M, N, M, K, alpha, beta};
+  launch_gemm(ctx, op, dim3(M / BM, N / BN));
+  CKC(cudaMemcpyAsync(C, dC, sizeof(double) * M * N, cudaMemcpyDeviceToHost, ctx->stream));
+  CKC(cudaStreamSynchronize(ctx->stream));
+  CKC(cudaGetLastError());
+  cleanup();
+  return GPB_OK;
+}
+
+extern "C" int gpb_debug_gemm_bench(gpb_ctx* ctx, int M, int N, int K, int reps, double* ms) {
+  if (!ctx) return GPB_EINVAL;
+  if (!ms || M <= 0 || N <= 0 || K <= 0 || M % BM || N % BN || K % BK || reps <= 0)
+    FAIL(GPB_EINVAL, "gpb_debug_gemm_bench: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  double *dA = nullptr, *dB = nullptr, *dC = nullptr;
+  auto cleanup = [&]() {
+    for (double* p : {dA, dB, dC})
+      if (p) cudaFree(p);
+  };
+  CKC(cudaMalloc(&dA, sizeof(double) * M * K));
+  CKC(cudaMalloc(&dB, sizeof(double) * N * K));
+  CKC(cudaMalloc(&dC, sizeof(double) * M * N));
+  fill_kernel<<<grid1d((long long)M * K), 256, 0, ctx->stream>>>(dA, 0.5, (long long)M * K);
+  fill_kernel<<<grid1d((long long)N * K), 256, 0, ctx->stream>>>(dB, 0.25, (long long)N * K);
+  fill_kernel<<<grid1d((long long)M * N), 256, 0, ctx->stream>>>(dC, 0.0, (long long)M * N);
+  OpGeneric op{dA, dB, dC, M, N, M, K, 1.0, 0.0};
+  for (int i = 0; i < 3; ++i) launch_gemm(ctx, op, dim3(M / BM, N / BN));
+  CKC(cudaEventRecord(ctx->ev[6], ctx->stream));
+  for (int i = 0; i < reps; ++i) launch_gemm(ctx, op, dim3(M / BM, N / BN));
+  CKC(cudaEventRecord(ctx->ev[7], ctx->stream));
+  CKC(cudaStreamSynchronize(ctx->stream));
+  CKC(cudaGetLastError());
+  float t = 0;
+  CKC(cudaEventElapsedTime(&t, ctx->ev[6], ctx->ev[7]));
+  *ms = t / reps;
+  cleanup();
+  return GPB_OK;
+}
+
+extern "C" int gpb_debug_potrf(gpb_ctx* ctx, double* A, int n, int32_t* info) {
+  if (!ctx) return GPB_EINVAL;
+  if (!A || n <= 0 || !info) FAIL(GPB_EINVAL, "gpb_debug_potrf: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  Model md{};
+  const int nz[3] = {1, 0, 0};
+  fill_model(md, 0, 0, 1, 0, nz, 1);
+  const int Np = round_up(n, T);
+  Bufs b;
+  int rc = alloc_bufs(ctx, b, 1, false, Np, 1, md);
+  if (rc != GPB_OK) { free_bufs(b); return rc; }
+  std::vector<double> pad((size_t)Np * Np, 0.0);
+  for (int c = 0; c < Np; ++c)
+    for (int r = 0; r < Np; ++r)
+      pad[(size_t)c * Np + r] = (r < n && c < n) ? A[(size_t)c * n + r] : (r == c ? 1.0 : 0.0);
+  int zero = 0;
+  cudaError_t e = cudaMemcpy(b.Abuf, pad.data(), sizeof(double) * pad.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(b.sel, &zero, sizeof(int), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemset(b.fail, 0, sizeof(int));
+  if (e == cudaSuccess) {
+    run_potrf(ctx, b, n, b.sel, 1, false, false);
+    e = cudaStreamSynchronize(ctx->stream);
+  }
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpy(pad.data(), b.Abuf, sizeof(double) * pad.size(), cudaMemcpyDeviceToHost);
+  int failh = 0;
+  if (e == cudaSuccess) e = cudaMemcpy(&failh, b.fail, sizeof(int), cudaMemcpyDeviceToHost);
+  free_bufs(b);
+  if (e != cudaSuccess) FAIL(GPB_ECUDA, cudaGetErrorString(e));
+  for (int c = 0; c < n; ++c)
+    for (int r = 0; r < n; ++r) A[(size_t)c * n + r] = (r >= c) ? pad[(size_t)c * Np + r] : 0.0;
+  *info = failh;
+  return GPB_OK;
+}

@@ -1,0 +1,343 @@
+// FP64 tensor-core tile GEMM for sm_100a:  C(m,n) = alpha * sum_k A(m,k) * B(n,k) + beta * C(m,n)
+//
+// Blackwell's tcgen05/UMMA path has no f64 kind; the FP64 tensor instruction on
+// sm_100a is the warp-level DMMA (PTX mma.sync.aligned.m8n8k4.f64 -> SASS DMMA.8x8x4).
+// Every dense contraction of the GP hot path (Cholesky panel + trailing update,
+// triangular inverse, K^-1 = W^T W, predictive-variance solve) is phrased as this ONE
+// "NT" product on column-major operands, so both operand tiles are contiguous along
+// M / N and stream into shared memory with 16-byte async copies.
+//
+// CTA tile 128x128, K step 16, 8 warps (4 along M x 2 along N, 32x64 per warp),
+// 4-stage cp.async ring (132 KB of the 227 KB shared memory), one CTA per SM.
+// Shared tiles are stored [k][m] with a pitch of 132 doubles so the DMMA fragment
+// loads (lane -> (m = lane/4, k = lane%4)) hit 16 distinct 8-byte banks per half warp.
+#pragma once
+#include "common.cuh"
+
+namespace gpb {
+
+constexpr int BM = 128, BN = 128, BK = 16, NSTAGE = 4;
+constexpr int PITCH = BM + 4;
+constexpr int GEMM_THREADS = 256;
+constexpr size_t GEMM_SMEM = (size_t)NSTAGE * 2 * BK * PITCH * sizeof(double);   // 135168
+
+struct GemmTile {
+  const double* A;  long long lda;    // A(m,k) at A[m + k*lda]
+  const double* B;  long long ldb;    // B(n,k) at B[n + k*ldb]
+  const double* A0; long long lda0;   // optional alternate source for k in [0,T)
+  const double* B0; long long ldb0;
+  double* C;  long long ldc;          // C(m,n) at C[m + n*ldc]       (may be null)
+  double* Ct; long long ldct;         // also/only store C(m,n) at Ct[n + m*ldct]
+  const double* E; long long lde;     // reduce mode: rowsum[m] = sum_n C(m,n)*E(m,n) (E null: C^2)
+  double* rowsum;
+  int K;
+  double alpha, beta;
+  bool valid;
+};
+
+__device__ __forceinline__ void dmma8x8x4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async16(double* smem, const double* gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// MODE bits
+constexpr int GM_BETA = 1;     // read C (beta != 0)
+constexpr int GM_STORE = 2;    // normal store
+constexpr int GM_STORET = 4;   // transposed store
+constexpr int GM_REDUCE = 8;   // row-sum epilogue (no store)
+
+template <class Op>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_kernel(const __grid_constant__ Op op) {
+  extern __shared__ __align__(16) double gsm[];
+  const GemmTile t = op.resolve();
+  if (!t.valid) return;
+  constexpr int MODE = Op::MODE;
+
+  double* As = gsm;
+  double* Bs = gsm + NSTAGE * BK * PITCH;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, tq = lane & 3;
+  const int wm = (warp & 3) * 32, wn = (warp >> 2) * 64;
+  const int KT = t.K / BK;
+
+  auto load_stage = [&](int kt, int stage) {
+    const int k0 = kt * BK;
+    const bool alt = (k0 < T);
+    const double* Ap = (alt && t.A0) ? t.A0 : t.A;
+    const long long la = (alt && t.A0) ? t.lda0 : t.lda;
+    const double* Bp = (alt && t.B0) ? t.B0 : t.B;
+    const long long lb = (alt && t.B0) ? t.ldb0 : t.ldb;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = tid + GEMM_THREADS * i;
+      const int kk = c >> 6, mc = (c & 63) * 2;
+      cp_async16(As + (stage * BK + kk) * PITCH + mc, Ap + (long long)(k0 + kk) * la + mc);
+      cp_async16(Bs + (stage * BK + kk) * PITCH + mc, Bp + (long long)(k0 + kk) * lb + mc);
+    }
+  };
+
+  double acc[4][8][2];
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 8; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+#pragma unroll
+  for (int s = 0; s < NSTAGE - 1; ++s) {
+    if (s < KT) load_stage(s, s);
+    cp_async_commit();
+  }
+  for (int kt = 0; kt < KT; ++kt) {
+    cp_async_wait<NSTAGE - 2>();
+    __syncthreads();
+    {
+      const int nk = kt + NSTAGE - 1;
+      if (nk < KT) load_stage(nk, nk % NSTAGE);
+      cp_async_commit();
+    }
+    const double* as = As + (kt % NSTAGE) * BK * PITCH;
+    const double* bs = Bs + (kt % NSTAGE) * BK * PITCH;
+#pragma unroll
+    for (int k4 = 0; k4 < BK / 4; ++k4) {
+      double a[4], b[8];
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi) a[mi] = as[(k4 * 4 + tq) * PITCH + wm + mi * 8 + g];
+#pragma unroll
+      for (int ni = 0; ni < 8; ++ni) b[ni] = bs[(k4 * 4 + tq) * PITCH + wn + ni * 8 + g];
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni) dmma8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+    }
+  }
+  cp_async_wait<0>();
+
+  // ---- epilogue: thread owns C(m = wm + mi*8 + g, n = wn + ni*8 + 2*tq + {0,1})
+  if (MODE & GM_REDUCE) {
+    __syncthreads();            // all warps done with the ring; reuse it for the N-direction reduce
+    double* red = gsm;          // [2][BM]
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+      const int m = wm + mi * 8 + g;
+      double s = 0.0;
+#pragma unroll
+      for (int ni = 0; ni < 8; ++ni) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int n = wn + ni * 8 + 2 * tq + j;
+          const double c = t.alpha * acc[mi][ni][j];
+          const double e = t.E ? t.E[m + (long long)n * t.lde] : c;
+          s += c * e;
+        }
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (tq == 0) red[(warp >> 2) * BM + m] = s;
+    }
+    __syncthreads();
+    if (tid < BM) t.rowsum[tid] = red[tid] + red[BM + tid];
+    return;
+  }
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi) {
+    const int m = wm + mi * 8 + g;
+#pragma unroll
+    for (int ni = 0; ni < 8; ++ni) {
+      const int n = wn + ni * 8 + 2 * tq;
+      double c0 = t.alpha * acc[mi][ni][0];
+      double c1 = t.alpha * acc[mi][ni][1];
+      if (MODE & GM_BETA) {
+        c0 += t.beta * t.C[m + (long long)n * t.ldc];
+        c1 += t.beta * t.C[m + (long long)(n + 1) * t.ldc];
+      }
+      if (MODE & GM_STORE) {
+        t.C[m + (long long)n * t.ldc] = c0;
+        t.C[m + (long long)(n + 1) * t.ldc] = c1;
+      }
+      if (MODE & GM_STORET) {
+        if (t.Ct) {
+          double2 v = make_double2(c0, c1);
+          *reinterpret_cast<double2*>(t.Ct + n + (long long)m * t.ldct) = v;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Tile -> problem maps.  All matrices are column-major, padded to Np = Nt*T with an
+// identity block, one Np x Np buffer per batch slot (stride Np*Np); `sel` lists the
+// slots this launch works on (blockIdx.y).
+// ------------------------------------------------------------------------------------
+struct BatchBufs {
+  double* Abuf;     // A -> L (lower) ; later H^T (upper) ; later K^-1 (lower)
+  double* Wbuf;     // W = L^-1 (lower), W^T (upper, gradient path)
+  double* Dbuf;     // [slot][Nt][T*T]  D_k = inv(L_kk), column-major, zeros above the diagonal
+  double* DTbuf;    // [slot][Nt][T*T]  D_k^T
+  const int* sel;
+  long long smat;   // Np*Np
+  int Np, Nt;
+};
+
+__device__ __forceinline__ GemmTile empty_tile() {
+  GemmTile t;
+  t.A = t.B = t.A0 = t.B0 = nullptr;
+  t.lda = t.ldb = t.lda0 = t.ldb0 = 0;
+  t.C = t.Ct = nullptr;
+  t.ldc = t.ldct = 0;
+  t.E = nullptr;
+  t.lde = 0;
+  t.rowsum = nullptr;
+  t.K = 0;
+  t.alpha = 1.0;
+  t.beta = 0.0;
+  t.valid = true;
+  return t;
+}
+
+// debug / benchmark: plain C = alpha A B^T + beta C
+struct OpGeneric {
+  static constexpr int MODE = GM_BETA | GM_STORE;
+  const double* A; const double* B; double* C;
+  long long lda, ldb, ldc;
+  int K;
+  double alpha, beta;
+  __device__ GemmTile resolve() const {
+    GemmTile t = empty_tile();
+    t.A = A + (long long)blockIdx.x * BM; t.lda = lda;
+    t.B = B + (long long)blockIdx.y * BN; t.ldb = ldb;
+    t.C = C + (long long)blockIdx.x * BM + (long long)blockIdx.y * BN * ldc; t.ldc = ldc;
+    t.K = K; t.alpha = alpha; t.beta = beta;
+    return t;
+  }
+};
+
+// potrf panel, step k:  L_ik = A_ik * D_k^T  (i > k), in place
+struct OpPanel {
+  static constexpr int MODE = GM_STORE;
+  BatchBufs b; int k;
+  __device__ GemmTile resolve() const {
+    GemmTile t = empty_tile();
+    const int slot = b.sel[blockIdx.y];
+    const int i = k + 1 + blockIdx.x;
+    double* tile = b.Abuf + slot * b.smat + (long long)i * T + (long long)k * T * b.Np;
+    t.A = tile; t.lda = b.Np;
+    t.B = b.Dbuf + ((long long)slot * b.Nt + k) * T * T; t.ldb = T;
+    t.C = tile; t.ldc = b.Np;
+    t.K = T;
+    return t;
+  }
+};
+
+// potrf trailing update, step k:  A_ij -= L_ik L_jk^T  (i >= j > k)
+struct OpSyrk {
+  static constexpr int MODE = GM_BETA | GM_STORE;
+  BatchBufs b; int k;
+  __device__ GemmTile resolve() const {
+    GemmTile t = empty_tile();
+    const int slot = b.sel[blockIdx.y];
+    int a, c;
+    tri_decode(blockIdx.x, a, c);
+    const int i = k + 1 + a, j = k + 1 + c;
+    double* base = b.Abuf + slot * b.smat;
+    t.A = base + (long long)i * T + (long long)k * T * b.Np; t.lda = b.Np;
+    t.B = base + (long long)j * T + (long long)k * T * b.Np; t.ldb = b.Np;
+    t.C = base + (long long)i * T + (long long)j * T * b.Np; t.ldc = b.Np;
+    t.K = T; t.alpha = -1.0; t.beta = 1.0;
+    return t;
+  }
+};
+
+// H pass:  upper tile (j,i) <- (L_ij * D_j)^T  for every i > j
+struct OpHpass {
+  static constexpr int MODE = GM_STORET;
+  BatchBufs b;
+  __device__ GemmTile resolve() const {
+    GemmTile t = empty_tile();
+    const int slot = b.sel[blockIdx.y];
+    int a, c;
+    tri_decode(blockIdx.x, a, c);
+    const int i = a + 1, j = c;
+    double* base = b.Abuf + slot * b.smat;
+    t.A = base + (long long)i * T + (long long)j * T * b.Np; t.lda = b.Np;
+    t.B = b.DTbuf + ((long long)slot * b.Nt + j) * T * T; t.ldb = T;
+    t.Ct = base + (long long)j * T + (long long)i * T * b.Np; t.ldct = b.Np;
+    t.K = T;
+    return t;
+  }
+};
+
+// triangular inverse, block column j (descending):  W_ij = - sum_{k=j+1..i} W_ik H_kj
+struct OpWrec {
+  static constexpr int MODE = GM_STORE | GM_STORET;
+  BatchBufs b; int j; int dual;
+  __device__ GemmTile resolve() const {
+    GemmTile t = empty_tile();
+    const int slot = b.sel[blockIdx.y];
+    const int i = j + 1 + blockIdx.x;
+    double* W = b.Wbuf + slot * b.smat;
+    const double* H = b.Abuf + slot * b.smat;
+    t.A = W + (long long)i * T + (long long)(j + 1) * T * b.Np; t.lda = b.Np;
+    t.B = H + (long long)j * T + (long long)(j + 1) * T * b.Np; t.ldb = b.Np;
+    t.C = W + (long long)i * T + (long long)j * T * b.Np; t.ldc = b.Np;
+    if (dual) { t.Ct = W + (long long)j * T + (long long)i * T * b.Np; t.ldct = b.Np; }
+    t.K = (i - j) * T; t.alpha = -1.0;
+    return t;
+  }
+};
+
+// K^-1 = W^T W (lower tiles a >= c) written over the lower triangle of Abuf
+struct OpSyrk2 {
+  static constexpr int MODE = GM_STORE;
+  BatchBufs b;
+  __device__ GemmTile resolve() const {
+    GemmTile t = empty_tile();
+    const int slot = b.sel[blockIdx.y];
+    int a, c;
+    tri_decode(blockIdx.x, a, c);
+    const double* W = b.Wbuf + slot * b.smat;
+    const double* DTa = b.DTbuf + ((long long)slot * b.Nt + a) * T * T;
+    // k runs over rows q = a*T .. Np-1 of W; the first T of them are the diagonal tile
+    t.A = W + (long long)a * T + (long long)a * T * b.Np; t.lda = b.Np;
+    t.B = W + (long long)c * T + (long long)a * T * b.Np; t.ldb = b.Np;
+    t.A0 = DTa; t.lda0 = T;
+    if (a == c) { t.B0 = DTa; t.ldb0 = T; }
+    t.C = b.Abuf + slot * b.smat + (long long)a * T + (long long)c * T * b.Np; t.ldc = b.Np;
+    t.K = (b.Nt - a) * T;
+    return t;
+  }
+};
+
+// predictive variance:  part[nt][j] = sum_{m in tile nt} ( sum_k Bt(j,k) Wm(m,k) )^2   (L_chol)
+//                    or sum_{m in tile nt} ( sum_k Bt(j,k) X(m,k) ) * Bt(j,m)            (low noise)
+struct OpPred {
+  static constexpr int MODE = GM_REDUCE;
+  const double* Bt; long long ldbt;   // (Mcp x Np) column-major
+  const double* Wm; long long ldw;    // (Np x Np) column-major
+  double* part;                       // [Nt][Mcp]
+  int Mcp; int tri;                   // tri = 1: Wm lower triangular -> K = (nt+1)*T
+  int Np;
+  __device__ GemmTile resolve() const {
+    GemmTile t = empty_tile();
+    const int jt = blockIdx.x, nt = blockIdx.y;
+    t.A = Bt + (long long)jt * BM; t.lda = ldbt;
+    t.B = Wm + (long long)nt * BN; t.ldb = ldw;
+    t.K = tri ? (nt + 1) * T : Np;
+    if (!tri) { t.E = Bt + (long long)jt * BM + (long long)nt * BN * ldbt; t.lde = ldbt; }
+    t.rowsum = part + (long long)nt * Mcp + (long long)jt * BM;
+    return t;
+  }
+};
+
+}  // namespace gpb
