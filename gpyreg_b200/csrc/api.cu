@@ -44,6 +44,7 @@ struct gpb_ctx {
   int D = 0, Np = 0, Nt = 0;
   double *dX = nullptr, *dy = nullptr, *ds2 = nullptr;
   size_t ws_limit = 0;
+  int gemm_bn = 64;          // 64: two CTAs per SM (default); 128: one (env GPB_GEMM_BN)
   Bufs ws;
   double timings[6] = {0, 0, 0, 0, 0, 0};
   long long launches = 0;
@@ -94,12 +95,23 @@ static inline unsigned grid1d(long long n, int block = 256) {
 
 template <class Op>
 static cudaError_t gemm_attr() {
-  return cudaFuncSetAttribute(gemm_nt_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)GEMM_SMEM);
+  cudaError_t e = cudaFuncSetAttribute(gemm_nt_kernel<Op, 128>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)gemm_smem<128>());
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(gemm_nt_kernel<Op, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)gemm_smem<64>());
 }
+// grid.x counts logical 128x128 tiles; the BN_=64 variant launches two CTAs per tile.
+// `wide` forces the one-CTA-per-tile kernel (needed when the product is done in place).
 template <class Op>
-static void launch_gemm(gpb_ctx* ctx, const Op& op, dim3 grid) {
-  gemm_nt_kernel<Op><<<grid, GEMM_THREADS, GEMM_SMEM, ctx->stream>>>(op);
+static void launch_gemm(gpb_ctx* ctx, const Op& op, dim3 grid, bool wide = false) {
+  if (wide || ctx->gemm_bn == 128) {
+    gemm_nt_kernel<Op, 128><<<grid, GEMM_THREADS, gemm_smem<128>(), ctx->stream>>>(op);
+  } else {
+    grid.x *= 2;
+    gemm_nt_kernel<Op, 64><<<grid, GEMM_THREADS, gemm_smem<64>(), ctx->stream>>>(op);
+  }
   LAUNCHED(ctx);
 }
 
@@ -164,6 +176,7 @@ extern "C" int gpb_create(int device, gpb_ctx** out) {
     return GPB_ECUDA;
   }
   ctx->stream = ctx->own_stream;
+  if (const char* bn = getenv("GPB_GEMM_BN")) ctx->gemm_bn = (atoi(bn) == 128) ? 128 : 64;
   for (auto& ev : ctx->ev) cudaEventCreate(&ev);
   int rc = init_attrs(ctx);
   if (rc != GPB_OK) {
@@ -455,7 +468,7 @@ static void run_potrf(gpb_ctx* ctx, Bufs& b, long long N, const int* sel, int ns
     LAUNCHED(ctx);
     const int n = b.Nt - k - 1;
     if (n <= 0) break;
-    launch_gemm(ctx, OpPanel{bb, k}, dim3((unsigned)n, (unsigned)nsel));
+    launch_gemm(ctx, OpPanel{bb, k}, dim3((unsigned)n, (unsigned)nsel), /*wide=*/true);
     if (with_rhs) {
       VecArgs va;
       va.Abuf = b.Abuf;
@@ -875,7 +888,7 @@ static int predict_impl(gpb_ctx* ctx, const gpb_post* cpost, const double* Xs, c
   const int McpMax = round_up(Mc, T);
   if ((rc = grow(ctx, &ctx->pXs, &ctx->pXs_n, (size_t)3 * McpMax * std::max(D, 1))) != GPB_OK) return rc;
   if ((rc = grow(ctx, &ctx->pBt, &ctx->pBt_n, (size_t)McpMax * Np)) != GPB_OK) return rc;
-  if ((rc = grow(ctx, &ctx->pmu, &ctx->ppart_n, (size_t)2 * Nt * McpMax)) != GPB_OK) return rc;
+  if ((rc = grow(ctx, &ctx->pmu, &ctx->ppart_n, (size_t)3 * Nt * McpMax)) != GPB_OK) return rc;
   if ((rc = grow(ctx, &ctx->psamp, &ctx->psamp_n, (size_t)4 * Ns * McpMax)) != GPB_OK) return rc;
   if ((rc = grow(ctx, &ctx->pout, &ctx->pout_n, (size_t)3 * McpMax * (separate ? Ns : 1))) != GPB_OK) return rc;
   double* dXs = ctx->pXs;
@@ -942,10 +955,12 @@ static int predict_impl(gpb_ctx* ctx, const gpb_post* cpost, const double* Xs, c
       op.Mcp = Mcp;
       op.tri = p.lchol ? 1 : 0;
       op.Np = Np;
+      op.ns = ctx->gemm_bn == 128 ? 1 : 2;
       launch_gemm(ctx, op, dim3((unsigned)(Mcp / T), (unsigned)Nt));
       FinishArgs fa;
       fa.md = md;
       fa.Nt = Nt;
+      fa.nv = Nt * (ctx->gemm_bn == 128 ? 1 : 2);
       fa.mc = mc;
       fa.Mcp = Mcp;
       fa.has_data = 1;
@@ -1213,7 +1228,7 @@ extern "C" int gpb_debug_gemm_bench(gpb_ctx* ctx, int M, int N, int K, int reps,
   fill_kernel<<<grid1d((long long)M * K), 256, 0, ctx->stream>>>(dA, 0.5, (long long)M * K);
   fill_kernel<<<grid1d((long long)N * K), 256, 0, ctx->stream>>>(dB, 0.25, (long long)N * K);
   fill_kernel<<<grid1d((long long)M * N), 256, 0, ctx->stream>>>(dC, 0.0, (long long)M * N);
-  OpGeneric op{dA, dB, dC, M, N, M, K, 1.0, 0.0};
+  OpGeneric op{dA, dB, dC, M, N, M, K, -1.0, 1.0};   // the trailing-update form
   for (int i = 0; i < 3; ++i) launch_gemm(ctx, op, dim3(M / BM, N / BN));
   CKC(cudaEventRecord(ctx->ev[6], ctx->stream));
   for (int i = 0; i < reps; ++i) launch_gemm(ctx, op, dim3(M / BM, N / BN));

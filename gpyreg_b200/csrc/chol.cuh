@@ -11,7 +11,7 @@
 namespace gpb {
 
 constexpr int DP_PITCH = T + 1;                                   // 129
-constexpr size_t DIAG_SMEM = (size_t)T * DP_PITCH * sizeof(double) + 3 * T * sizeof(double);
+constexpr size_t DIAG_SMEM = (size_t)T * DP_PITCH * sizeof(double) + 5 * T * sizeof(double);
 
 struct DiagArgs {
   double* Abuf; double* Wbuf;      // Wbuf may be null (nlZ-only path)
@@ -32,6 +32,8 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
   double* dinv = dsm + T * DP_PITCH;     // 1 / L_jj
   double* bsh = dinv + T;                // b_k
   double* lg = bsh + T;                  // log L_jj
+  double* cj = lg + T;                   // scaled pivot column
+  double* dd = cj + T;                   // diagonal of L
   const int slot = a.sel[blockIdx.x];
   const int k = a.k, Np = a.Np;
   const int tid = threadIdx.x;
@@ -46,25 +48,42 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
   if (tid < T) bsh[tid] = a.bvec ? a.bvec[(long long)slot * Np + k * T + tid] : 0.0;
   __syncthreads();
 
-  // ---- right-looking Cholesky of the active block, all 256 threads on the rank-1 update
+  // ---- right-looking Cholesky of the active block, all 256 threads on the rank-1 update.
+  // The scaled pivot column lives in its own array (cj) so the update loop's loads do not
+  // alias its stores and can be software-pipelined; the diagonal goes to dd[].
   int failed = 0;
   const int r = tid & (T - 1), half = tid >> 7;
   for (int j = 0; j < nact; ++j) {
     double piv = S[j * DP_PITCH + j];
     if (!(piv > 0.0)) { failed = 1; piv = 1.0; }     // LAPACK dpotrf: ajj <= 0 or NaN -> info > 0
     const double d = sqrt(piv);
-    __syncthreads();                                  // everyone has read the pivot
     if (half == 0) {
-      if (r == j) S[j * DP_PITCH + j] = d;
-      else if (r > j && r < nact) S[j * DP_PITCH + r] /= d;
+      if (r == j) dd[j] = d;
+      else if (r > j && r < nact) {
+        const double l = S[j * DP_PITCH + r] / d;
+        S[j * DP_PITCH + r] = l;
+        cj[r] = l;
+      }
     }
     __syncthreads();
     if (r > j && r < nact) {
-      const double lrj = S[j * DP_PITCH + r];
-      for (int c = j + 1 + half; c <= r; c += 2) S[c * DP_PITCH + r] -= lrj * S[j * DP_PITCH + c];
+      const double lrj = cj[r];
+      double* Sr = S + r;
+      int c = j + 1 + half;
+      for (; c + 6 <= r; c += 8) {
+        const double u0 = cj[c], u1 = cj[c + 2], u2 = cj[c + 4], u3 = cj[c + 6];
+        double s0 = Sr[c * DP_PITCH], s1 = Sr[(c + 2) * DP_PITCH], s2 = Sr[(c + 4) * DP_PITCH],
+               s3 = Sr[(c + 6) * DP_PITCH];
+        s0 -= lrj * u0; s1 -= lrj * u1; s2 -= lrj * u2; s3 -= lrj * u3;
+        Sr[c * DP_PITCH] = s0; Sr[(c + 2) * DP_PITCH] = s1; Sr[(c + 4) * DP_PITCH] = s2;
+        Sr[(c + 6) * DP_PITCH] = s3;
+      }
+      for (; c <= r; c += 2) Sr[c * DP_PITCH] -= lrj * cj[c];
     }
     __syncthreads();
   }
+  if (tid < nact) S[tid * DP_PITCH + tid] = dd[tid];
+  __syncthreads();
   if (tid < T) {
     const double ljj = S[tid * DP_PITCH + tid];      // 1.0 in the padded part
     dinv[tid] = 1.0 / ljj;

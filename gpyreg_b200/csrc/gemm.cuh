@@ -19,7 +19,6 @@ namespace gpb {
 constexpr int BM = 128, BN = 128, BK = 16, NSTAGE = 4;
 constexpr int PITCH = BM + 4;
 constexpr int GEMM_THREADS = 256;
-constexpr size_t GEMM_SMEM = (size_t)NSTAGE * 2 * BK * PITCH * sizeof(double);   // 135168
 
 struct GemmTile {
   const double* A;  long long lda;    // A(m,k) at A[m + k*lda]
@@ -29,7 +28,7 @@ struct GemmTile {
   double* C;  long long ldc;          // C(m,n) at C[m + n*ldc]       (may be null)
   double* Ct; long long ldct;         // also/only store C(m,n) at Ct[n + m*ldct]
   const double* E; long long lde;     // reduce mode: rowsum[m] = sum_n C(m,n)*E(m,n) (E null: C^2)
-  double* rowsum;
+  double* rowsum; long long rs_half;  // rs_half: offset between the two column halves
   int K;
   double alpha, beta;
   bool valid;
@@ -51,24 +50,48 @@ __device__ __forceinline__ void cp_async_wait() {
 }
 
 // MODE bits
-constexpr int GM_BETA = 1;     // read C (beta != 0)
+constexpr int GM_BETA = 1;     // C enters the product: accumulators start at (beta/alpha) * C
 constexpr int GM_STORE = 2;    // normal store
 constexpr int GM_STORET = 4;   // transposed store
 constexpr int GM_REDUCE = 8;   // row-sum epilogue (no store)
 
-template <class Op>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_kernel(const __grid_constant__ Op op) {
+template <int BN_>
+constexpr size_t gemm_smem() {
+  return (size_t)NSTAGE * BK * (PITCH + BN_ + 4) * sizeof(double);
+}
+
+// BN_ = 128: one CTA per SM, 32x64 warp tiles.  BN_ = 64: the logical 128x128 tile is split
+// into two column halves (blockIdx.x = 2*tile + half), 32x32 warp tiles, <= 128 registers and
+// 100 KB of shared memory so TWO CTAs share an SM and one CTA's prologue/epilogue (C tile
+// read/write, pipeline fill) overlaps the other's DMMA main loop.
+template <class Op, int BN_>
+__global__ void __launch_bounds__(GEMM_THREADS, (BN_ == 64 ? 2 : 1))
+gemm_nt_kernel(const __grid_constant__ Op op) {
   extern __shared__ __align__(16) double gsm[];
-  const GemmTile t = op.resolve();
-  if (!t.valid) return;
+  constexpr int NS = BN / BN_;             // column halves per logical tile
+  constexpr int PB = BN_ + 4;              // pitch of the B tile
+  constexpr int WN = BN_ / 2;              // warp tile width
+  constexpr int NI = WN / 8;
   constexpr int MODE = Op::MODE;
+  const int half = (NS > 1) ? (int)(blockIdx.x % NS) : 0;
+  GemmTile t = op.resolve((int)(blockIdx.x / NS));
+  if (!t.valid) return;
+  if (NS > 1) {
+    const long long off = (long long)half * BN_;
+    t.B += off;
+    if (t.B0) t.B0 += off;
+    if (t.C) t.C += off * t.ldc;
+    if (t.Ct) t.Ct += off;
+    if (t.E) t.E += off * t.lde;
+    if (t.rowsum) t.rowsum += (long long)half * t.rs_half;
+  }
 
   double* As = gsm;
   double* Bs = gsm + NSTAGE * BK * PITCH;
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, tq = lane & 3;
-  const int wm = (warp & 3) * 32, wn = (warp >> 2) * 64;
+  const int wm = (warp & 3) * 32, wn = (warp >> 2) * WN;
   const int KT = t.K / BK;
 
   auto load_stage = [&](int kt, int stage) {
@@ -83,21 +106,42 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_kernel(const __grid_c
       const int c = tid + GEMM_THREADS * i;
       const int kk = c >> 6, mc = (c & 63) * 2;
       cp_async16(As + (stage * BK + kk) * PITCH + mc, Ap + (long long)(k0 + kk) * la + mc);
-      cp_async16(Bs + (stage * BK + kk) * PITCH + mc, Bp + (long long)(k0 + kk) * lb + mc);
+    }
+#pragma unroll
+    for (int i = 0; i < 4 / NS; ++i) {
+      const int c = tid + GEMM_THREADS * i;
+      const int kk = c / (BN_ / 2), nc = (c % (BN_ / 2)) * 2;
+      cp_async16(Bs + (stage * BK + kk) * PB + nc, Bp + (long long)(k0 + kk) * lb + nc);
     }
   };
-
-  double acc[4][8][2];
-#pragma unroll
-  for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-    for (int ni = 0; ni < 8; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 
 #pragma unroll
   for (int s = 0; s < NSTAGE - 1; ++s) {
     if (s < KT) load_stage(s, s);
     cp_async_commit();
   }
+
+  // thread owns C(m = wm + mi*8 + g, n = wn + ni*8 + 2*tq + {0,1})
+  double acc[4][NI][2];
+  if (MODE & GM_BETA) {
+    // start from (beta/alpha) * C: the loads go straight into the accumulator registers and
+    // overlap the pipeline fill, instead of a latency-bound read-modify-write epilogue
+    const double f = t.beta / t.alpha;
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < NI; ++ni) {
+        const int m = wm + mi * 8 + g, n = wn + ni * 8 + 2 * tq;
+        acc[mi][ni][0] = f * t.C[m + (long long)n * t.ldc];
+        acc[mi][ni][1] = f * t.C[m + (long long)(n + 1) * t.ldc];
+      }
+  } else {
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+  }
+
   for (int kt = 0; kt < KT; ++kt) {
     cp_async_wait<NSTAGE - 2>();
     __syncthreads();
@@ -107,23 +151,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_kernel(const __grid_c
       cp_async_commit();
     }
     const double* as = As + (kt % NSTAGE) * BK * PITCH;
-    const double* bs = Bs + (kt % NSTAGE) * BK * PITCH;
+    const double* bs = Bs + (kt % NSTAGE) * BK * PB;
 #pragma unroll
     for (int k4 = 0; k4 < BK / 4; ++k4) {
-      double a[4], b[8];
+      double a[4], b[NI];
 #pragma unroll
       for (int mi = 0; mi < 4; ++mi) a[mi] = as[(k4 * 4 + tq) * PITCH + wm + mi * 8 + g];
 #pragma unroll
-      for (int ni = 0; ni < 8; ++ni) b[ni] = bs[(k4 * 4 + tq) * PITCH + wn + ni * 8 + g];
+      for (int ni = 0; ni < NI; ++ni) b[ni] = bs[(k4 * 4 + tq) * PB + wn + ni * 8 + g];
 #pragma unroll
       for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 8; ++ni) dmma8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        for (int ni = 0; ni < NI; ++ni) dmma8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
     }
   }
   cp_async_wait<0>();
 
-  // ---- epilogue: thread owns C(m = wm + mi*8 + g, n = wn + ni*8 + 2*tq + {0,1})
+  // ---- epilogue
   if (MODE & GM_REDUCE) {
     __syncthreads();            // all warps done with the ring; reuse it for the N-direction reduce
     double* red = gsm;          // [2][BM]
@@ -132,7 +176,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_kernel(const __grid_c
       const int m = wm + mi * 8 + g;
       double s = 0.0;
 #pragma unroll
-      for (int ni = 0; ni < 8; ++ni) {
+      for (int ni = 0; ni < NI; ++ni) {
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const int n = wn + ni * 8 + 2 * tq + j;
@@ -153,14 +197,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_kernel(const __grid_c
   for (int mi = 0; mi < 4; ++mi) {
     const int m = wm + mi * 8 + g;
 #pragma unroll
-    for (int ni = 0; ni < 8; ++ni) {
+    for (int ni = 0; ni < NI; ++ni) {
       const int n = wn + ni * 8 + 2 * tq;
-      double c0 = t.alpha * acc[mi][ni][0];
-      double c1 = t.alpha * acc[mi][ni][1];
-      if (MODE & GM_BETA) {
-        c0 += t.beta * t.C[m + (long long)n * t.ldc];
-        c1 += t.beta * t.C[m + (long long)(n + 1) * t.ldc];
-      }
+      const double c0 = t.alpha * acc[mi][ni][0];
+      const double c1 = t.alpha * acc[mi][ni][1];
       if (MODE & GM_STORE) {
         t.C[m + (long long)n * t.ldc] = c0;
         t.C[m + (long long)(n + 1) * t.ldc] = c1;
@@ -199,6 +239,7 @@ __device__ __forceinline__ GemmTile empty_tile() {
   t.E = nullptr;
   t.lde = 0;
   t.rowsum = nullptr;
+  t.rs_half = 0;
   t.K = 0;
   t.alpha = 1.0;
   t.beta = 0.0;
@@ -213,11 +254,11 @@ struct OpGeneric {
   long long lda, ldb, ldc;
   int K;
   double alpha, beta;
-  __device__ GemmTile resolve() const {
+  __device__ GemmTile resolve(int bx) const {
     GemmTile t = empty_tile();
-    t.A = A + (long long)blockIdx.x * BM; t.lda = lda;
+    t.A = A + (long long)bx * BM; t.lda = lda;
     t.B = B + (long long)blockIdx.y * BN; t.ldb = ldb;
-    t.C = C + (long long)blockIdx.x * BM + (long long)blockIdx.y * BN * ldc; t.ldc = ldc;
+    t.C = C + (long long)bx * BM + (long long)blockIdx.y * BN * ldc; t.ldc = ldc;
     t.K = K; t.alpha = alpha; t.beta = beta;
     return t;
   }
@@ -227,10 +268,10 @@ struct OpGeneric {
 struct OpPanel {
   static constexpr int MODE = GM_STORE;
   BatchBufs b; int k;
-  __device__ GemmTile resolve() const {
+  __device__ GemmTile resolve(int bx) const {
     GemmTile t = empty_tile();
     const int slot = b.sel[blockIdx.y];
-    const int i = k + 1 + blockIdx.x;
+    const int i = k + 1 + bx;
     double* tile = b.Abuf + slot * b.smat + (long long)i * T + (long long)k * T * b.Np;
     t.A = tile; t.lda = b.Np;
     t.B = b.Dbuf + ((long long)slot * b.Nt + k) * T * T; t.ldb = T;
@@ -244,11 +285,11 @@ struct OpPanel {
 struct OpSyrk {
   static constexpr int MODE = GM_BETA | GM_STORE;
   BatchBufs b; int k;
-  __device__ GemmTile resolve() const {
+  __device__ GemmTile resolve(int bx) const {
     GemmTile t = empty_tile();
     const int slot = b.sel[blockIdx.y];
     int a, c;
-    tri_decode(blockIdx.x, a, c);
+    tri_decode(bx, a, c);
     const int i = k + 1 + a, j = k + 1 + c;
     double* base = b.Abuf + slot * b.smat;
     t.A = base + (long long)i * T + (long long)k * T * b.Np; t.lda = b.Np;
@@ -263,11 +304,11 @@ struct OpSyrk {
 struct OpHpass {
   static constexpr int MODE = GM_STORET;
   BatchBufs b;
-  __device__ GemmTile resolve() const {
+  __device__ GemmTile resolve(int bx) const {
     GemmTile t = empty_tile();
     const int slot = b.sel[blockIdx.y];
     int a, c;
-    tri_decode(blockIdx.x, a, c);
+    tri_decode(bx, a, c);
     const int i = a + 1, j = c;
     double* base = b.Abuf + slot * b.smat;
     t.A = base + (long long)i * T + (long long)j * T * b.Np; t.lda = b.Np;
@@ -282,10 +323,10 @@ struct OpHpass {
 struct OpWrec {
   static constexpr int MODE = GM_STORE | GM_STORET;
   BatchBufs b; int j; int dual;
-  __device__ GemmTile resolve() const {
+  __device__ GemmTile resolve(int bx) const {
     GemmTile t = empty_tile();
     const int slot = b.sel[blockIdx.y];
-    const int i = j + 1 + blockIdx.x;
+    const int i = j + 1 + bx;
     double* W = b.Wbuf + slot * b.smat;
     const double* H = b.Abuf + slot * b.smat;
     t.A = W + (long long)i * T + (long long)(j + 1) * T * b.Np; t.lda = b.Np;
@@ -301,11 +342,11 @@ struct OpWrec {
 struct OpSyrk2 {
   static constexpr int MODE = GM_STORE;
   BatchBufs b;
-  __device__ GemmTile resolve() const {
+  __device__ GemmTile resolve(int bx) const {
     GemmTile t = empty_tile();
     const int slot = b.sel[blockIdx.y];
     int a, c;
-    tri_decode(blockIdx.x, a, c);
+    tri_decode(bx, a, c);
     const double* W = b.Wbuf + slot * b.smat;
     const double* DTa = b.DTbuf + ((long long)slot * b.Nt + a) * T * T;
     // k runs over rows q = a*T .. Np-1 of W; the first T of them are the diagonal tile
@@ -325,17 +366,18 @@ struct OpPred {
   static constexpr int MODE = GM_REDUCE;
   const double* Bt; long long ldbt;   // (Mcp x Np) column-major
   const double* Wm; long long ldw;    // (Np x Np) column-major
-  double* part;                       // [Nt][Mcp]
+  double* part;                       // [Nt*ns][Mcp]
   int Mcp; int tri;                   // tri = 1: Wm lower triangular -> K = (nt+1)*T
-  int Np;
-  __device__ GemmTile resolve() const {
+  int Np; int ns;                     // ns = column halves per tile (BN / BN_)
+  __device__ GemmTile resolve(int bx) const {
     GemmTile t = empty_tile();
-    const int jt = blockIdx.x, nt = blockIdx.y;
+    const int jt = bx, nt = (int)gridDim.y - 1 - (int)blockIdx.y;   // longest K first
     t.A = Bt + (long long)jt * BM; t.lda = ldbt;
     t.B = Wm + (long long)nt * BN; t.ldb = ldw;
     t.K = tri ? (nt + 1) * T : Np;
     if (!tri) { t.E = Bt + (long long)jt * BM + (long long)nt * BN * ldbt; t.lde = ldbt; }
-    t.rowsum = part + (long long)nt * Mcp + (long long)jt * BM;
+    t.rowsum = part + (long long)nt * ns * Mcp + (long long)jt * BM;
+    t.rs_half = Mcp;
     return t;
   }
 };

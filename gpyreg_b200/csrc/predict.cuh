@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256) ks_build_kernel(KsArgs a) {
 
 struct FinishArgs {
   Model md;
-  int Nt, mc, Mcp;
+  int Nt, nv, mc, Mcp;         // nv = number of variance partials (Nt * column halves)
   int has_data;                // 0: GP without training data -> prior mean / variance
   int lchol;
   const double* Xs; const double* ys; const double* s2s;    // chunk pointers (ys/s2s may be null)
@@ -125,10 +125,8 @@ __global__ void __launch_bounds__(256) pred_finish_kernel(FinishArgs a) {
   double s2 = kss;
   if (a.has_data) {
     double m = 0.0, v = 0.0;
-    for (int t = 0; t < a.Nt; ++t) {
-      m += a.mupart[(long long)t * a.Mcp + j];
-      v += a.vpart[(long long)t * a.Mcp + j];
-    }
+    for (int t = 0; t < a.Nt; ++t) m += a.mupart[(long long)t * a.Mcp + j];
+    for (int t = 0; t < a.nv; ++t) v += a.vpart[(long long)t * a.Mcp + j];
     mu += m;                                        // :1747
     s2 = kss - v;                                   // :1758 / :1762 (L = -Ainv)
   }

@@ -153,9 +153,14 @@ def test_lownoise_golden(eng, golden_lownoise, tag):
     nlz, dnlz, mult, status = eng.nlz_batch(c["hyp"], want_grad=True)
     assert not status.any()
     same = mult == c["sn2_mult"]
-    # rows whose matrix is numerically singular may take a different number of retries than
-    # LAPACK; compare values only where the multiplier agrees
-    assert same.sum() >= len(same) - 1
+    # Rows the reference factors at the first attempt must agree exactly.  Rows whose matrix
+    # is numerically singular (K + 2.2e-16*I; the reference needs x100 jitter) succeed or fail
+    # on rounding alone, so a blocked GPU Cholesky may take a different number of retries than
+    # LAPACK: there the multiplier only has to stay a small power of ten.
+    easy = c["sn2_mult"] == 1
+    assert same[easy].all()
+    assert np.all(np.isin(mult[~easy], [1.0, 10.0, 100.0, 1e3, 1e4])), mult
+    assert np.all(np.isfinite(nlz))
     post = eng.posterior_batch(c["hyp"])
     for b in np.nonzero(same)[0]:
         assert int(post.fetch(b, "L_chol")) == c["L_chol"][b]

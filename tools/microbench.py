@@ -15,12 +15,17 @@ dev = torch.device("cuda", 0)
 out["gpu"] = torch.cuda.get_device_name(0)
 out["fp64_cublas_tflops_8192"] = fp64_peak_tflops(torch, dev, 8192, 5)
 out["fp64_cublas_tflops_4096"] = fp64_peak_tflops(torch, dev, 4096, 5)
-eng = Engine(0)
-for (M, N, K) in [(4096, 4096, 4096), (8192, 8192, 2048), (8192, 8192, 128), (2048, 2048, 2048), (1024, 1024, 8192)]:
-    ms = eng.debug_gemm_bench(M, N, K, 5)
-    out[f"gemm_{M}x{N}x{K}_tflops"] = 2.0 * M * N * K / (ms * 1e-3) / 1e12
-    out[f"gemm_{M}x{N}x{K}_ms"] = ms
+for bn in ("128", "64"):
+    os.environ["GPB_GEMM_BN"] = bn
+    e2 = Engine(0)
+    for (M, N, K) in [(4096, 4096, 4096), (8192, 8192, 2048), (8192, 8192, 512), (8192, 8192, 256),
+                      (8192, 8192, 128), (2048, 2048, 2048), (1024, 1024, 8192)]:
+        ms = e2.debug_gemm_bench(M, N, K, 5)
+        out[f"bn{bn}_gemm_{M}x{N}x{K}_tflops"] = round(2.0 * M * N * K / (ms * 1e-3) / 1e12, 2)
+    e2.close()
 print(json.dumps(out, indent=1), flush=True)
+os.environ["GPB_GEMM_BN"] = os.environ.get("BN", "64")
+eng = Engine(0)
 
 for name, spec, N, Bs in [
     ("cfg2", ModelSpec(D=6, cov_kind=0, ard=True, mean_kind=1), 2000, (1, 64, 256)),
