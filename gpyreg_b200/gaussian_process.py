@@ -1,0 +1,725 @@
+"""Drop-in ``GP`` for the path BASELINE.json's north_star names, behind the reference's
+API (gpyreg/gaussian_process.py): ``update``, ``fit``, ``predict``, the private nlZ /
+posterior entry points, hyperparameter / bounds / prior plumbing.
+
+Every numerical evaluation goes to the B200 through :class:`gpyreg_b200.Engine`
+(C ABI, include/gpyreg_b200.h); there is no NumPy fallback for the hot path.  The three
+places where the reference loops over hyperparameter vectors one at a time are batched:
+the ``f_min_fill`` design (f_min_fill.py:174-176), the posterior rebuild in ``update``
+(gaussian_process.py:870-879) and the per-sample loop of ``predict`` (:1727).
+
+Not built in this round (SURVEY.md 8f "next" rows): ``quad``, ``predict_full``,
+``random_function``, ``plot``; a one-point ``update`` is done as a full (batched)
+recompute instead of the reference's rank-1 append -- same posterior, different cost.
+"""
+import math
+import zlib
+
+import numpy as np
+import scipy as sp
+import scipy.linalg
+import scipy.optimize
+import scipy.special
+import scipy.stats
+
+from .engine import Engine
+from .f_min_fill import (f_min_fill, smoothbox_cdf, smoothbox_student_t_cdf)
+from .slice_sample import SliceSampler
+from .spec import ModelSpec
+
+
+class Posterior:
+    """The record the reference keeps per hyperparameter sample (gaussian_process.py:2568-2586):
+    ``hyp, alpha, sW, L, sn2_mult, L_chol``.  Here the factors live on the GPU; ``alpha``,
+    ``sW`` and ``L`` are fetched into NumPy arrays the first time they are read."""
+
+    _FIELDS = ("alpha", "sW", "L", "sn2_mult", "L_chol")
+
+    def __init__(self, hyp, alpha, sW, L, sn2_mult, Lchol, _batch=None, _index=0):
+        self.hyp = hyp
+        self._batch, self._index = _batch, _index
+        self._val = {"alpha": alpha, "sW": sW, "L": L, "sn2_mult": sn2_mult, "L_chol": Lchol}
+        self._have = {k: (_batch is None) for k in self._FIELDS}
+
+    def _get(self, name):
+        if not self._have[name]:
+            b, s = self._batch, self._index
+            if name == "alpha":
+                v = b.fetch(s, "alpha").reshape(-1, 1)
+            elif name == "sW":
+                v = np.ones((b.N, 1)) * b.fetch(s, "sW")      # constant vector, :2517
+            elif name == "L":
+                v = b.fetch(s, "L")
+            elif name == "sn2_mult":
+                m = b.fetch(s, "sn2_mult")
+                v = int(m) if float(m).is_integer() else float(m)
+            else:
+                v = bool(b.fetch(s, "L_chol"))
+            self._val[name], self._have[name] = v, True
+        return self._val[name]
+
+    def _set(self, name, v):
+        self._val[name], self._have[name] = v, True
+
+    alpha = property(lambda s: s._get("alpha"), lambda s, v: s._set("alpha", v))
+    sW = property(lambda s: s._get("sW"), lambda s, v: s._set("sW", v))
+    L = property(lambda s: s._get("L"), lambda s, v: s._set("L", v))
+    sn2_mult = property(lambda s: s._get("sn2_mult"), lambda s, v: s._set("sn2_mult", v))
+    L_chol = property(lambda s: s._get("L_chol"), lambda s, v: s._set("L_chol", v))
+
+
+def _spec_of(D, covariance, mean, noise):
+    """Read the model descriptor off the plugin objects."""
+    try:
+        return ModelSpec(D=D, cov_kind=covariance._cov_kind, degree=int(getattr(covariance, "degree", 0)),
+                         ard=bool(covariance._ard), mean_kind=mean._mean_kind,
+                         noise_params=tuple(int(v) for v in noise.parameters))
+    except AttributeError as e:
+        raise TypeError("gpyreg_b200.GP needs covariance/mean/noise objects from gpyreg_b200 "
+                        "(the fused CUDA kernels implement exactly those families)") from e
+
+
+class GP:
+    """A single Gaussian-process model (gaussian_process.py:15-62)."""
+
+    def __init__(self, D, covariance, mean, noise):
+        self.D = D
+        self.covariance, self.mean, self.noise = covariance, mean, noise
+        self._spec = _spec_of(D, covariance, mean, noise)
+        self.s2 = self.X = self.y = None
+        self.posteriors = None
+        self.no_prior = None
+        self.normalization_constants = None
+        self._engine = None
+        self._data_key = None
+        self._post_batch = None
+        self.set_bounds()
+        self.set_priors()
+        self.temporary_data = {}
+
+    # ------------------------------------------------------------------ layout helpers
+    def _hyper_info(self):
+        """[(name, count)] in the order cov | noise | mean (gaussian_process.py:174)."""
+        return (self.covariance.hyperparameter_info(self.D) + self.noise.hyperparameter_info()
+                + self.mean.hyperparameter_info(self.D))
+
+    def _counts(self):
+        return (self.covariance.hyperparameter_count(self.D), self.noise.hyperparameter_count(),
+                self.mean.hyperparameter_count(self.D))
+
+    def _hyp_n(self):
+        return sum(self._counts())
+
+    def _slices(self):
+        lo = 0
+        for name, n in self._hyper_info():
+            yield name, slice(lo, lo + n)
+            lo += n
+
+    def __str__(self):
+        cov_n, noise_n, mean_n = self._counts()
+
+        def plural(n):
+            return f", {n} parameter\n" if n == 1 else f", {n} parameters\n"
+
+        cov = "Covariance function: " + type(self.covariance).__name__
+        if type(self.covariance).__name__ == "Matern":
+            cov += "(degree=" + str(self.covariance.degree) + ")\n"
+        cov += plural(cov_n)
+        mean = "Mean function: " + type(self.mean).__name__ + plural(mean_n)
+        noise = "Noise function: " + type(self.noise).__name__
+        p = self.noise.parameters
+        if np.any(p):
+            flags = []
+            if p[0] == 1:
+                flags.append("constant_add=True")
+            if p[1] == 1:
+                flags.append("user_provided_add=True")
+            if p[1] == 2:
+                flags.append("scale_user_provided=True")
+            if p[2] == 1:
+                flags.append("rectified_linear_output_dependent_add=True")
+            noise += "(" + ", ".join(flags) + ")"
+        noise += plural(noise_n)
+        priors = "Hyperparameter priors: " + ("none\n" if self.no_prior else "present\n")
+        samples = "Hyperparameter samples: " + str(0 if self.posteriors is None else np.size(self.posteriors))
+        body = "Dimension: " + str(self.D) + "\n" + cov + mean + noise + priors + samples
+        return "GP:\n" + "".join("    " + ln for ln in body.splitlines(True))
+
+    __repr__ = __str__
+
+    # ------------------------------------------------------------------ bounds
+    def set_bounds(self, bounds=None):
+        """gaussian_process.py:147-205"""
+        n = self._hyp_n()
+        lb, ub = np.full((n,), np.nan), np.full((n,), np.nan)
+        for name, sl in self._slices():
+            if bounds is None:
+                continue
+            if name not in bounds:
+                raise ValueError("Missing hyperparameter " + name)
+            if bounds[name] is not None:
+                lb[sl], ub[sl] = bounds[name]
+        self.lower_bounds, self.upper_bounds = lb, ub
+        if self.no_prior is not None:
+            self.__recompute_normalization_constants()
+
+    def get_bounds(self):
+        return self.bounds_to_dict(self.lower_bounds, self.upper_bounds)
+
+    def bounds_to_dict(self, lower_bounds, upper_bounds):
+        return {name: (lower_bounds[sl], upper_bounds[sl]) for name, sl in self._slices()}
+
+    def get_recommended_bounds(self, lower_bounds=None, upper_bounds=None):
+        """gaussian_process.py:245-359: NaN entries are replaced by the plugins' bounds."""
+        if self.X is None or self.y is None:
+            raise ValueError("GP does not have X or y set!")
+
+        def resolve(v, current):
+            if isinstance(v, (list, tuple, np.ndarray)):
+                return np.array(v, dtype=float)
+            if isinstance(v, str) and v == "current":
+                return current.copy()
+            if v is None or (isinstance(v, str) and v == "recommended"):
+                return np.full_like(current, np.nan)
+            raise ValueError("`lower_bounds` should be 'recommended'/`None`, 'current', or an array.")
+
+        lb = resolve(lower_bounds, self.lower_bounds)
+        ub = resolve(upper_bounds, self.upper_bounds)
+        info = [self.covariance.get_bounds_info(self.X, self.y),
+                self.noise.get_bounds_info(self.X, self.y),
+                self.mean.get_bounds_info(self.X, self.y)]
+        rec_lb = np.concatenate([i["LB"] for i in info])
+        rec_ub = np.concatenate([i["UB"] for i in info])
+        lb = np.where(np.isnan(lb), rec_lb, lb)
+        ub = np.where(np.isnan(ub), rec_ub, ub)
+        return self.bounds_to_dict(lb, np.maximum(lb, ub))
+
+    # ------------------------------------------------------------------ priors
+    def set_priors(self, priors=None):
+        """gaussian_process.py:421-514"""
+        n = self._hyp_n()
+        hp = {k: np.full((n,), np.nan) for k in ("mu", "sigma", "df", "a", "b")}
+        any_prior = False
+        for name, sl in self._slices():
+            if priors is None:
+                continue
+            if name not in priors:
+                raise ValueError("Missing hyperparameter " + name)
+            if priors[name] is None:
+                continue
+            any_prior = True
+            kind, par = priors[name]
+            if kind == "gaussian":
+                hp["mu"][sl], hp["sigma"][sl] = par
+                hp["df"][sl] = 0
+            elif kind == "student_t":
+                hp["mu"][sl], hp["sigma"][sl], hp["df"][sl] = par
+            elif kind == "smoothbox":
+                hp["a"][sl], hp["b"][sl], hp["sigma"][sl] = par
+                hp["df"][sl] = 0
+            elif kind == "smoothbox_student_t":
+                hp["a"][sl], hp["b"][sl], hp["sigma"][sl], hp["df"][sl] = par
+            else:
+                raise ValueError("Unknown hyperprior type " + kind)
+        self.hyper_priors = hp
+        self.no_prior = not any_prior
+        self.__recompute_normalization_constants()
+
+    def get_priors(self):
+        """gaussian_process.py:361-419"""
+        hp = self.hyper_priors
+        out = {}
+        for name, sl in self._slices():
+            mu, sigma, df, a, b = (hp[k][sl].copy() for k in ("mu", "sigma", "df", "a", "b"))
+            val = None
+            if np.all(np.isfinite(a)) and np.all(np.isfinite(b)) and np.all(np.isfinite(sigma)):
+                if np.all(df == 0) or np.all(df == np.inf):
+                    val = ("smoothbox", (a, b, sigma))
+                elif np.all(df > 0):
+                    val = ("smoothbox_student_t", (a, b, sigma, df))
+            elif np.all(np.isfinite(mu)) and np.all(np.isfinite(sigma)):
+                if np.all(df == 0) or np.all(df == np.inf):
+                    val = ("gaussian", (mu, sigma))
+                elif np.all(df > 0):
+                    val = ("student_t", (mu, sigma, df))
+            out[name] = val
+        return out
+
+    def __recompute_normalization_constants(self):
+        """Mass of each prior inside [LB, UB] (gaussian_process.py:1234-1273)."""
+        hp = self.hyper_priors
+        nc = np.full(self.lower_bounds.shape, 1.0)
+        for i in range(nc.size):
+            mu, sigma, df = hp["mu"][i], np.abs(hp["sigma"])[i], hp["df"][i]
+            a, b, lb, ub = hp["a"][i], hp["b"][i], self.lower_bounds[i], self.upper_bounds[i]
+            if lb == ub or (not np.isfinite(lb) and not np.isfinite(ub)):
+                continue
+            if not np.isfinite(mu) and not np.isfinite(sigma):
+                continue
+            gaussian_tails = df == 0 or not np.isfinite(df)
+            if np.isfinite(a) and np.isfinite(b):
+                if gaussian_tails:
+                    lo, hi = smoothbox_cdf(lb, sigma, a, b), smoothbox_cdf(ub, sigma, a, b)
+                else:
+                    lo = smoothbox_student_t_cdf(lb, df, sigma, a, b)
+                    hi = smoothbox_student_t_cdf(ub, df, sigma, a, b)
+            elif gaussian_tails:
+                lo, hi = sp.stats.norm.cdf([lb, ub], loc=mu, scale=sigma)
+            else:
+                lo, hi = sp.stats.t.cdf([lb, ub], df, loc=mu, scale=sigma)
+            nc[i] = hi - lo
+        self.normalization_constants = nc
+
+    def _log_priors_batch(self, hyp, compute_grad):
+        """log prior (and gradient) for a (B, P) array of hyperparameter rows: the
+        reference's per-vector formulas (gaussian_process.py:1275-1466) vectorised over B."""
+        hyp = np.atleast_2d(np.asarray(hyp, dtype=float))
+        B, P = hyp.shape
+        hp = self.hyper_priors
+        mu, sigma, df, a, b = hp["mu"], np.abs(hp["sigma"]), hp["df"], hp["a"], hp["b"]
+        lb, ub = self.lower_bounds, self.upper_bounds
+        fin = np.isfinite
+        # NB the reference writes `df == 0 | ~np.isfinite(df)`, which Python parses as
+        # `df == (0 | ~isfinite(df))`: true only where df == 0 (:1293, :1309).  Kept.
+        df0 = df == 0
+        fixed = lb == ub
+        box = fin(a) & fin(b) & df0 & ~fin(mu) & fin(sigma)
+        box_t = fin(a) & fin(b) & (df > 0) & ~fin(mu) & fin(sigma) & fin(df)
+        flat = ~fin(mu) & ~fin(sigma)
+        gauss = ~flat & ~box & df0 & fin(sigma)
+        stud = ~flat & ~box_t & (df > 0) & fin(df)
+        lp = np.zeros(B)
+        dlp = np.zeros((B, P)) if compute_grad else None
+        with np.errstate(all="ignore"):
+            if np.any(fixed):
+                lp[np.any(hyp[:, fixed] != lb[fixed], axis=1)] = -np.inf
+                if compute_grad:
+                    dlp[:, fixed] = np.nan
+            for idx, heavy in ((box, False), (box_t, True)):
+                if not np.any(idx):
+                    continue
+                h, s, aa, bb = hyp[:, idx], sigma[idx], a[idx], b[idx]
+                below, above = h < aa, h > bb
+                z2 = np.where(below, ((h - aa) / s) ** 2, 0.0) + np.where(above, ((h - bb) / s) ** 2, 0.0)
+                out = below | above
+                if heavy:
+                    nu = df[idx]
+                    C = 1.0 + (bb - aa) * sp.special.gamma(0.5 * (nu + 1)) / (
+                        sp.special.gamma(0.5 * nu) * s * np.sqrt(nu * np.pi))
+                    base = (sp.special.gammaln(0.5 * (nu + 1)) - sp.special.gammaln(0.5 * nu)
+                            - 0.5 * np.log(np.pi * nu) - np.log(C * s))
+                    lp += np.sum(base + np.where(out, -0.5 * (nu + 1) * np.log1p(z2 / nu), 0.0), axis=1)
+                    if compute_grad:
+                        edge = np.where(below, aa, bb)
+                        g = -(nu + 1) / nu / (1 + z2 / nu) * (h - edge) / s ** 2
+                        dlp[:, idx] = np.where(out, g, 0.0)
+                else:
+                    C = 1.0 + (bb - aa) / (s * np.sqrt(2 * np.pi))
+                    t_out = -0.5 * (np.log(C ** 2 * 2 * np.pi * s ** 2) + z2)
+                    t_in = -(np.log(C * s) + np.log(np.sqrt(2 * np.pi)))
+                    lp += np.sum(np.where(out, t_out, t_in), axis=1)
+                    if compute_grad:
+                        edge = np.where(below, aa, bb)
+                        dlp[:, idx] = np.where(out, -(h - edge) / s ** 2, 0.0)
+            if np.any(gauss):
+                h, s, m = hyp[:, gauss], sigma[gauss], mu[gauss]
+                lp -= 0.5 * np.sum(np.log(2 * np.pi * s ** 2) + ((h - m) / s) ** 2, axis=1)
+                if compute_grad:
+                    dlp[:, gauss] = -(h - m) / s ** 2
+            if np.any(stud):
+                h, s, m, nu = hyp[:, stud], sigma[stud], mu[stud], df[stud]
+                z2 = ((h - m) / s) ** 2
+                lp += np.sum(sp.special.gammaln(0.5 * (nu + 1)) - sp.special.gammaln(0.5 * nu)
+                             - 0.5 * np.log(np.pi * nu) - np.log(s)
+                             - 0.5 * (nu + 1) * np.log1p(z2 / nu), axis=1)
+                if compute_grad:
+                    dlp[:, stud] = -(nu + 1) / nu / (1 + z2 / nu) * (h - m) / s ** 2
+            lp -= np.sum(np.log(self.normalization_constants))
+        return (lp, dlp) if compute_grad else lp
+
+    def __compute_log_priors(self, hyp, compute_grad):
+        out = self._log_priors_batch(np.asarray(hyp, dtype=float)[None, :], compute_grad)
+        if compute_grad:
+            return out[0][0], out[1][0]
+        return out[0]
+
+    # ------------------------------------------------------------------ hyperparameters
+    def get_hyperparameters(self, as_array=False):
+        if self.posteriors is None:
+            hyp = np.full((1, self._hyp_n()), np.nan)
+        else:
+            hyp = np.stack([np.array(p.hyp, dtype=float) for p in self.posteriors])
+        return hyp if as_array else self.hyperparameters_to_dict(hyp)
+
+    def set_hyperparameters(self, hyp_new, compute_posterior=True):
+        if isinstance(hyp_new, np.ndarray):
+            if hyp_new.ndim == 1:
+                hyp_new = np.reshape(hyp_new, (1, -1))
+            if hyp_new.shape[1] != self._hyp_n():
+                raise ValueError("Input hyperparameter array is the wrong shape!")
+        else:
+            hyp_new = self.hyperparameters_from_dict(hyp_new)
+        self.update(hyp=hyp_new, compute_posterior=compute_posterior)
+
+    def hyperparameters_to_dict(self, hyp_arr):
+        hyp_arr = np.asarray(hyp_arr)
+        if hyp_arr.ndim == 1:
+            hyp_arr = np.reshape(hyp_arr, (1, -1))
+        if hyp_arr.shape[1] != self._hyp_n():
+            raise ValueError("Input hyperparameter array is the wrong shape!")
+        return [{name: row[sl].copy() for name, sl in self._slices()} for row in hyp_arr]
+
+    def hyperparameters_from_dict(self, hyp_dict_list):
+        if isinstance(hyp_dict_list, dict):
+            hyp_dict_list = [hyp_dict_list]
+        out = np.zeros((len(hyp_dict_list), self._hyp_n()))
+        for i, d in enumerate(hyp_dict_list):
+            for name, sl in self._slices():
+                out[i, sl] = d[name]
+        return out
+
+    # ------------------------------------------------------------------ device plumbing
+    @property
+    def engine(self):
+        if self._engine is None:
+            self._engine = Engine()
+        return self._engine
+
+    def _sync_engine(self):
+        """Upload (X, y, s2) when they changed since the last call."""
+        X = np.ascontiguousarray(self.X, dtype=float)
+        y = np.ascontiguousarray(self.y, dtype=float)
+        s2 = None if self.s2 is None else np.ascontiguousarray(self.s2, dtype=float)
+        key = (X.shape, zlib.crc32(X), zlib.crc32(y), None if s2 is None else zlib.crc32(s2))
+        if key != self._data_key:
+            eng = self.engine
+            sp_ = self._spec
+            eng.set_model(sp_.cov_kind, sp_.degree, sp_.ard, sp_.mean_kind, sp_.noise_params)
+            eng.set_data(X, y.reshape(-1), None if s2 is None else s2.reshape(-1))
+            self._data_key = key
+        return self.engine
+
+    def _convert_shapes(self, X, y, s2):
+        """gaussian_process.py:2523-2565"""
+        if X is None and y is None and s2 is None:
+            return X, y, s2
+        if X is not None:
+            if X.ndim == 1:
+                X = X[None, :]
+            if X.ndim != 2:
+                raise AssertionError("X need to be an array of shape (N, D)")
+            N, D = X.shape
+            if D != self.D:
+                raise AssertionError(f"The dimension of input data {D}"
+                                     f"doesn't match GP's input dimension {self.D}.")
+        else:
+            try:
+                N, D = self.X.shape
+            except AttributeError:
+                raise AttributeError(f"self.X is not a numpy array, self.X = {self.X}")
+        if y is not None:
+            y = y.reshape(N, 1)
+        if isinstance(s2, (float, int)):
+            s2 = s2 * np.ones((N, 1))
+        elif isinstance(s2, np.ndarray):
+            s2 = s2.reshape(N, 1)
+        elif s2 is not None:
+            raise TypeError("s2 type need to be Union[np.ndarray, float, int, None].")
+        return X, y, s2
+
+    # ------------------------------------------------------------------ core numerics
+    def _nlz_batch(self, hyp, compute_grad=False, compute_prior=False):
+        """Batched ``__compute_nlZ``: (B, P) rows -> nlZ (B,) [, dnlZ (B, P)].  Raises the
+        reference's LinAlgError if any row's Cholesky fails all 10 jitter retries."""
+        hyp = np.atleast_2d(np.asarray(hyp, dtype=float))
+        eng = self._sync_engine()
+        nlz, dnlz, _, status = eng.nlz_batch(hyp, want_grad=compute_grad)
+        if status.any():
+            raise sp.linalg.LinAlgError("Singular matrix for L Cholesky decomposition")
+        if compute_prior:
+            if compute_grad:
+                lp, dlp = self._log_priors_batch(hyp, True)
+                nlz, dnlz = nlz - lp, dnlz - dlp
+            else:
+                nlz = nlz - self._log_priors_batch(hyp, False)
+        return (nlz, dnlz) if compute_grad else nlz
+
+    def __compute_nlZ(self, hyp, compute_grad, compute_prior):
+        """gaussian_process.py:1520-1538"""
+        out = self._nlz_batch(np.asarray(hyp, dtype=float).reshape(1, -1), bool(compute_grad),
+                              bool(compute_prior))
+        if compute_grad:
+            return out[0][0], out[1][0]
+        return out[0]
+
+    _compute_nlZ = __compute_nlZ          # alias named by BASELINE.json
+
+    def __core_computation(self, hyp, compute_nlZ, compute_nlZ_grad):
+        """gaussian_process.py:2357-2521: nlZ, (nlZ, dnlZ) or a Posterior."""
+        if compute_nlZ:
+            return self.__compute_nlZ(hyp, bool(compute_nlZ_grad), False)
+        return self._posteriors_for(np.asarray(hyp, dtype=float).reshape(1, -1))[0][0]
+
+    def _compute_posterior(self, hyp):
+        """Alias named by BASELINE.json: the posterior record(s) for hyp (1-D or (B, P))."""
+        hyp = np.asarray(hyp, dtype=float)
+        posts, _ = self._posteriors_for(np.atleast_2d(hyp))
+        return posts[0] if hyp.ndim == 1 else posts
+
+    def _posteriors_for(self, hyp):
+        eng = self._sync_engine()
+        batch = eng.posterior_batch(hyp)
+        for s in range(batch.count):
+            if batch.fetch(s, "status") != 0:
+                raise sp.linalg.LinAlgError("Singular matrix for L Cholesky decomposition")
+        posts = np.empty((batch.count,), dtype=object)
+        for s in range(batch.count):
+            posts[s] = Posterior(hyp[s].copy(), None, None, None, None, None, _batch=batch, _index=s)
+        return posts, batch
+
+    def __gp_obj_fun(self, hyp, compute_grad, swap_sign):
+        """gaussian_process.py:1540-1559"""
+        out = self.__compute_nlZ(hyp, compute_grad, self.no_prior is not True)
+        sign = -1 if swap_sign else 1
+        if compute_grad:
+            return sign * out[0], sign * out[1]
+        return sign * out
+
+    def log_likelihood(self, hyp, compute_grad=False):
+        if isinstance(hyp, dict):
+            hyp = self.hyperparameters_from_dict(hyp)
+        out = self.__compute_nlZ(np.asarray(hyp, dtype=float).reshape(-1), compute_grad, False)
+        return (-out[0], -out[1]) if compute_grad else -out
+
+    def log_posterior(self, hyp, compute_grad=False):
+        if isinstance(hyp, dict):
+            hyp = self.hyperparameters_from_dict(hyp)
+        out = self.__compute_nlZ(np.asarray(hyp, dtype=float).reshape(-1), compute_grad, True)
+        return (-out[0], -out[1]) if compute_grad else -out
+
+    # ------------------------------------------------------------------ update / clean
+    def update(self, X_new=None, y_new=None, s2_new=None, hyp=None, compute_posterior=True):
+        """Add data and/or replace the hyperparameter samples (gaussian_process.py:691-884).
+        The posteriors of all samples are rebuilt in ONE batched GPU call."""
+        X_new, y_new, s2_new = self._convert_shapes(X_new, y_new, s2_new)
+        if X_new is not None:
+            self.X = X_new.copy() if self.X is None else np.concatenate((self.X, X_new))
+        if y_new is not None:
+            self.y = y_new.copy() if self.y is None else np.concatenate((self.y, y_new))
+        if s2_new is not None:
+            self.s2 = s2_new.copy() if self.s2 is None else np.concatenate((self.s2, s2_new))
+        hyp = self.get_hyperparameters(as_array=True) if hyp is None else np.array(hyp, dtype=float)
+        if hyp.ndim == 1:
+            hyp = hyp.reshape(1, -1)
+        if compute_posterior and self.X is not None and self.y is not None:
+            self.posteriors, self._post_batch = self._posteriors_for(hyp)
+        else:
+            self._post_batch = None
+            self.posteriors = np.empty((hyp.shape[0],), dtype=object)
+            for i in range(hyp.shape[0]):
+                self.posteriors[i] = Posterior(hyp[i, :], None, None, None, None, None)
+
+    def clean(self):
+        """Drop the factors (gaussian_process.py:886-905); ``update()`` rebuilds them."""
+        self.temporary_data = {}
+        if self.posteriors is not None:
+            for p in self.posteriors:
+                p._batch = None
+                for k in Posterior._FIELDS:
+                    p._set(k, None)
+        if self._post_batch is not None:
+            self._post_batch.free()
+            self._post_batch = None
+
+    # ------------------------------------------------------------------ predict
+    def predict(self, x_star, y_star=None, s2_star=None, add_noise=False, separate_samples=False,
+                return_lpd=False):
+        """Posterior mean and variance at x_star over all hyperparameter samples
+        (gaussian_process.py:1663-1816); one GPU call for all samples and points."""
+        x_star, y_star, s2_star = self._convert_shapes(x_star, y_star, s2_star)
+        if return_lpd and y_star is None:
+            raise ValueError("Cannot calculate log predictive density without y_star.")
+        if self.y is None:
+            return self._predict_prior(x_star, y_star, s2_star, add_noise, separate_samples, return_lpd)
+        batch = self._post_batch
+        if batch is None or batch._h is None or self.posteriors is None or \
+                any(p._batch is not batch for p in self.posteriors):
+            raise RuntimeError("GP.predict: the posteriors hold no device factors; call "
+                               "update(compute_posterior=True) first")
+        return self.engine.predict(batch, x_star, None if y_star is None else y_star.reshape(-1),
+                                   None if s2_star is None else s2_star.reshape(-1),
+                                   add_noise=add_noise, separate=separate_samples, want_lpd=return_lpd)
+
+    def _predict_prior(self, x_star, y_star, s2_star, add_noise, separate, return_lpd):
+        """GP without training data: prior mean and variance through the plugin kernels
+        (gaussian_process.py:1765-1767)."""
+        cov_n, noise_n, mean_n = self._counts()
+        s_N = self.posteriors.size
+        M = x_star.shape[0]
+        mu, s2, ys2 = np.zeros((M, s_N)), np.zeros((M, s_N)), np.zeros((M, s_N))
+        for s, post in enumerate(self.posteriors):
+            h = np.asarray(post.hyp, dtype=float)
+            mu[:, s] = np.reshape(self.mean.compute(h[cov_n + noise_n:cov_n + noise_n + mean_n], x_star), -1)
+            s2[:, s] = np.maximum(self.covariance.compute(h[:cov_n], x_star, compute_diag=True)[:, 0], 0)
+            if return_lpd or add_noise:
+                sn2 = self.noise.compute(h[cov_n:cov_n + noise_n], x_star, y_star, s2_star)
+                mult = post.sn2_mult if post.sn2_mult is not None else 1
+                ys2[:, s] = s2[:, s] + np.reshape(sn2 * mult, -1)
+        lpd = None
+        if return_lpd and separate:
+            lpd = -0.5 * (y_star - mu) ** 2 / ys2 - 0.5 * np.log(2 * np.pi * ys2)
+        if add_noise:
+            s2 = ys2
+        if not separate:
+            v = 0
+            if s_N > 1:
+                mbar = mu.sum(1, keepdims=True) / s_N
+                v = np.sum((mu - mbar) ** 2, 1) / (s_N - 1)
+                s2 = np.reshape(s2.sum(1) / s_N + v, (-1, 1))
+                mu = mbar
+            if return_lpd:
+                pv = s2 if add_noise else np.reshape(ys2.sum(1) / s_N + v, (-1, 1))
+                lpd = -0.5 * (y_star - mu) ** 2 / pv - 0.5 * np.log(2 * np.pi * pv)
+        return (mu, s2, lpd) if return_lpd else (mu, s2)
+
+    # ------------------------------------------------------------------ fit
+    def fit(self, X=None, y=None, s2=None, hyp0=None, options=None):
+        """Train the hyperparameters (gaussian_process.py:910-1232): space-filling design
+        (evaluated as ONE batch on the GPU), L-BFGS-B from the best ``opts_N`` starts, then
+        slice sampling; finally the posteriors of all kept samples are built in one batch."""
+        options = options or {}
+        opts_N = options.get("opts_N", 3)
+        init_N = options.get("init_N", 2 ** 10)
+        init_method = options.get("init_method", "sobol")
+        thin = options.get("thin", 5)
+        df_base = options.get("df_base", 7)
+        widths = options.get("widths", None)
+        tol_opt = options.get("tol_opt", 1e-5)
+        tol_opt_mcmc = options.get("tol_opt_mcmc", 1e-3)
+        sampler_name = options.get("sampler", "slicesample")
+        s_N = options.get("n_samples", 10)
+        burn_in = options.get("burn", thin * s_N)
+        lower_bounds = options.get("lower_bounds", "current")
+        upper_bounds = options.get("upper_bounds", "current")
+
+        X, y, s2 = self._convert_shapes(X, y, s2)
+        if X is not None:
+            self.X = X
+        if y is not None:
+            self.y = y
+        if s2 is not None:
+            self.s2 = s2
+        cov_n, noise_n, _ = self._counts()
+        info = [self.covariance.get_bounds_info(self.X, self.y),
+                self.noise.get_bounds_info(self.X, self.y),
+                self.mean.get_bounds_info(self.X, self.y)]
+        self.hyper_priors["df"][np.isnan(self.hyper_priors["df"])] = df_base
+
+        current = (isinstance(lower_bounds, str) and lower_bounds == "current"
+                   and isinstance(upper_bounds, str) and upper_bounds == "current")
+        if current and (np.any(np.isnan(self.lower_bounds)) or np.any(np.isnan(self.upper_bounds))):
+            self.set_bounds(self.get_recommended_bounds(self.lower_bounds, self.upper_bounds))
+        else:
+            self.set_bounds(self.get_recommended_bounds(lower_bounds, upper_bounds))
+        LB, UB = self.lower_bounds, self.upper_bounds
+        PLB = np.concatenate([i["PLB"] for i in info])
+        PUB = np.concatenate([i["PUB"] for i in info])
+        PLB = np.minimum(np.maximum(PLB, LB), UB)
+        PUB = np.maximum(np.minimum(PUB, UB), LB)
+
+        if hyp0 is None:
+            if self.posteriors is not None:
+                hyp0 = self.get_hyperparameters(as_array=True)
+            else:
+                hyp0 = np.reshape(np.minimum(np.maximum((PLB + PUB) / 2, LB), UB), (1, -1))
+        elif isinstance(hyp0, dict):
+            hyp0 = self.hyperparameters_from_dict(hyp0)
+        hyp0 = np.atleast_2d(hyp0)
+        use_prior = self.no_prior is not True
+
+        def design_objective(H):                     # whole design in one GPU batch
+            return self._nlz_batch(H, False, use_prior)
+        design_objective.batched = True
+
+        tol = tol_opt_mcmc if (s_N > 0 and sampler_name != "laplace") else tol_opt
+        if init_N > 0:
+            X0, y0 = f_min_fill(design_objective, hyp0, LB, UB, PLB, PUB, self.hyper_priors,
+                                init_N, init_method)
+            hyp = X0[0:np.maximum(opts_N, 1), :]
+            if noise_n > 0 and 1 < opts_N < init_N:
+                # second start: best point among the 20% lowest-noise design rows (:1112-1125)
+                rest, rest_y = X0[opts_N:, :], y0[opts_N:]
+                order = np.argsort(rest[:, cov_n])
+                rest, rest_y = rest[order, :], rest_y[order]
+                hyp[1, :] = rest[np.argmin(rest_y[0:math.ceil(0.2 * np.size(rest_y))]), :]
+            widths_default = np.std(X0, axis=0, ddof=1) if init_N > 1 else np.zeros(shape=PLB.shape)
+        else:
+            nll = design_objective(hyp0)
+            hyp = hyp0[np.argsort(nll), :]
+            widths_default = PUB - PLB
+        zero = widths_default == 0
+        if np.any(zero):
+            if np.shape(hyp)[0] > 1:
+                widths_default[zero] = np.std(hyp, axis=0, ddof=1)[zero]
+                zero = widths_default == 0
+            if np.any(zero):
+                widths_default[zero] = np.minimum(1, UB[zero] - LB[zero])
+
+        # keep the starts strictly inside the box (:1159-1166)
+        lo, hi = np.reshape(LB.copy(), (1, -1)), np.reshape(UB.copy(), (1, -1))
+        free = lo != hi
+        lo_i, hi_i = free & np.isfinite(lo), free & np.isfinite(hi)
+        lo[lo_i] = np.nextafter(lo[lo_i], np.inf)
+        hi[hi_i] = np.nextafter(hi[hi_i], -np.inf)
+        hyp = np.minimum(hi, np.maximum(lo, hyp))
+
+        def opt_objective(h):
+            return self.__gp_obj_fun(h, True, False)
+
+        nll = np.full((np.maximum(opts_N, 1),), np.inf)
+        results = []
+        opts_N = np.minimum(opts_N, hyp.shape[0])
+        for i in range(opts_N):
+            res = sp.optimize.minimize(fun=opt_objective, x0=hyp[i, :], jac=True,
+                                       bounds=list(zip(LB, UB)), tol=tol)
+            results.append(res)
+            hyp[i, :] = res.x
+            nll[i] = res.fun
+        if opts_N > 0:
+            optimize_result = results[np.argmin(nll)]
+            hyp_start = hyp[np.argmin(nll), :].copy()
+        else:
+            optimize_result = None
+            hyp_start = hyp[0, :].copy()
+        if s_N == 0:
+            hyp_start = np.reshape(hyp_start, (1, -1))
+            self.update(hyp=hyp_start)
+            return hyp_start, optimize_result, None
+
+        if sampler_name != "slicesample":
+            raise ValueError("Unknown sampler!")
+        widths = widths_default if widths is None else np.minimum(widths, widths_default)
+        slicer = SliceSampler(lambda h: self.__gp_obj_fun(h, False, True), hyp_start, widths, LB, UB,
+                              {"display": "off", "diagnostics": False})
+        sampling_result = slicer.sample(s_N * thin, burn=burn_in)
+        hyp = sampling_result["samples"][thin - 1::thin, :]
+        self.update(hyp=hyp)
+        return hyp, optimize_result, sampling_result
+
+    # ------------------------------------------------------------------ not in this round
+    def _not_built(self, name):
+        raise NotImplementedError(
+            f"GP.{name} is outside the hot path built so far (SURVEY.md 8f 'next' rows)")
+
+    def quad(self, *a, **k):
+        self._not_built("quad")
+
+    def predict_full(self, *a, **k):
+        self._not_built("predict_full")
+
+    def random_function(self, *a, **k):
+        self._not_built("random_function")
+
+    def plot(self, *a, **k):
+        self._not_built("plot")

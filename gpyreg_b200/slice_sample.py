@@ -1,0 +1,190 @@
+"""Coordinate-wise slice sampling with bounds and burn-in width adaptation, with the
+interface of the reference's ``SliceSampler`` (gpyreg/slice_sample.py).  One chain is
+strictly sequential (every proposal depends on the last accepted point), so this stays a
+host-side driver; each log-density evaluation is one B=1 call into the GPU path.
+
+The global NumPy RNG is consumed in the same order as the reference (one shuffle per
+sweep; per coordinate one draw for the slice level, one for the bracket position, one per
+shrink proposal), so a fixed ``np.random.seed`` gives the same chain whenever the
+log-density values agree.
+"""
+import logging
+
+import numpy as np
+
+
+class SliceSampler:
+    def __init__(self, log_f, x0, widths=None, LB=None, UB=None, options=None):
+        self.log_f = log_f
+        self.x0 = np.atleast_1d(np.asarray(x0, dtype=float)).copy() if np.ndim(x0) <= 1 else np.asarray(x0)
+        if np.ndim(self.x0) > 1:
+            raise ValueError("The initial point x0 needs to be a scalar or a 1D array")
+        D = self.x0.size
+
+        def as_bound(v, default):
+            if v is None:
+                return np.full((D,), default)
+            v = np.asarray(v, dtype=float)
+            return np.tile(v, D) if v.size == 1 else v.copy()
+
+        self.LB = as_bound(LB, -np.inf)
+        self.UB = as_bound(UB, np.inf)
+        self.LB_out = np.nextafter(self.LB, -np.inf)
+        self.UB_out = np.nextafter(self.UB, np.inf)
+        if widths is None:
+            self.widths = ((self.UB - self.LB) / 2).copy()
+            self.base_widths = None
+        else:
+            widths = np.asarray(widths, dtype=float)
+            self.widths = np.tile(widths, D) if widths.size == 1 else widths.copy()
+            self.base_widths = self.widths.copy()
+        self.widths[np.isinf(self.widths)] = 10
+        self.widths[self.LB == self.UB] = 1          # irrelevant for pinned coordinates
+        if np.shape(self.LB) != np.shape(self.x0) or np.shape(self.UB) != np.shape(self.x0):
+            raise ValueError("LB and UB need to be None, scalars, or 1D arrays of "
+                             "the same size as X0.")
+        if not np.all(self.UB >= self.LB):
+            raise ValueError("All upper bounds UB need to be equal or greater than "
+                             "lower bounds LB.")
+        if np.any(self.widths <= 0) or np.any(~np.isfinite(self.widths)) or np.any(~np.isreal(self.widths)):
+            raise ValueError("The widths vector needs to be all positive real numbers.")
+        if np.any(self.x0 < self.LB) or np.any(self.x0 > self.UB):
+            raise ValueError("The initial starting point X0 is outside the bounds.")
+        self.func_count = 0
+        options = options or {}
+        self.step_out = options.get("step_out", False)
+        self.display = options.get("display", "full")
+        self.adaptive = options.get("adaptive", True)
+        self.log_prior = options.get("log_prior", None)
+        self.diagnostics = options.get("diagnostics", True)
+        self.logger = logging.getLogger("SliceSampler")
+        self.logger.setLevel({"off": logging.WARN, "summary": logging.INFO}.get(self.display, logging.DEBUG))
+
+    # -- target density with bounds ------------------------------------------------
+    def _log_density(self, x):
+        """log p(x) (+ log prior), -inf outside the bounds or where p is NaN/-inf
+        (slice_sample.py:653-683)."""
+        if np.any(x < self.LB) or np.any(x > self.UB):
+            return -np.inf, np.nan, -np.inf
+        lp = 0.0
+        if self.log_prior is not None:
+            lp = self.log_prior(x)
+            if np.isnan(lp):
+                self.logger.warning("Prior density function returned NaN. Trying to continue.")
+                return -np.inf, np.nan, -np.inf
+            if not np.isfinite(lp):
+                return -np.inf, np.nan, -np.inf
+        f_val = self.log_f(x)
+        self.func_count += 1
+        f_sum = np.sum(f_val)
+        if np.any(np.isnan(f_val)):
+            self.logger.warning("Target density function returned NaN. Trying to continue.")
+            return -np.inf, f_val, lp
+        return f_sum + lp, f_val, lp
+
+    # -- sampling --------------------------------------------------------------------
+    def sample(self, N, thin=1, burn=None):
+        xx = self.x0.astype(float).copy()
+        D = xx.size
+        if burn is None:
+            burn = 0 if self.func_count > 0 else round(N / 3)
+        if not np.isscalar(thin) or thin <= 0:
+            raise ValueError("The thinning factor option needs to be a positive integer.")
+        if not np.isscalar(burn) or burn < 0:
+            raise ValueError("The burn-in samples option needs to be a non-negative integer.")
+        n_sweeps = N + (N - 1) * (thin - 1) + burn
+        samples = np.zeros((N, D))
+        log_Px, f_val, log_prior = self._log_density(xx)
+        if np.any(~np.isfinite(log_Px)):
+            raise ValueError("The initial starting point X0 needs to evaluate to a "
+                             "real number (not Inf or NaN).")
+        f_vals = np.zeros((N, np.size(f_val)))
+        log_priors = np.zeros((N,))
+        s1, s2 = np.zeros((D,)), np.zeros((D,))     # running moments over the 2nd half of burn-in
+        perm = np.arange(D)
+        for it in range(n_sweeps):
+            lo, hi, prop = xx.copy(), xx.copy(), xx.copy()
+            np.random.shuffle(perm)
+            for d in perm:
+                if self.LB[d] == self.UB[d]:
+                    continue
+                level = log_Px + np.log(np.random.rand())          # slice height
+                u = np.random.rand()                               # random bracket placement
+                lo[d] = np.fmax(lo[d] - u * self.widths[d], self.LB_out[d])
+                hi[d] = np.fmin(hi[d] + (1 - u) * self.widths[d], self.UB_out[d])
+                if self.step_out:
+                    while self._log_density(lo)[0] > level:
+                        lo[d] -= self.widths[d]
+                    while self._log_density(hi)[0] > level:
+                        hi[d] += self.widths[d]
+                n_shrink = 0
+                while True:                                        # shrink until accepted
+                    n_shrink += 1
+                    prop[d] = np.random.rand() * (hi[d] - lo[d]) + lo[d]
+                    log_Px, f_val, log_prior = self._log_density(prop)
+                    if log_Px > level:
+                        break
+                    if prop[d] > xx[d]:
+                        hi[d] = prop[d]
+                    elif prop[d] < xx[d]:
+                        lo[d] = prop[d]
+                    else:
+                        self.logger.warning("WARNING: Shrunk to current position and still "
+                                            " not acceptable!")
+                        break
+                if it < burn and self.adaptive:                    # width adaptation
+                    span = self.UB[d] - self.LB[d]
+                    if n_shrink > 3:
+                        floor = np.abs(np.spacing(span)) if np.isfinite(span) else np.spacing(1)
+                        self.widths[d] = np.maximum(self.widths[d] / 1.1, floor)
+                    elif n_shrink < 2:
+                        self.widths[d] = np.minimum(self.widths[d] * 1.2, span)
+                xx[d] = prop[d]
+                lo[d] = hi[d] = xx[d]
+            if it >= burn and (it - burn) % thin == 0:
+                k = (it - burn) // thin
+                samples[k, :] = xx
+                f_vals[k, :] = f_val
+                log_priors[k] = log_prior
+            if burn / 2 <= it < burn:
+                s1 += xx
+                s2 += xx ** 2
+                if it == burn - 1 and self.adaptive:
+                    n_stored = np.floor(burn / 2)
+                    new_w = np.fmin(5 * np.sqrt(np.maximum(s2 / n_stored - (s1 / n_stored) ** 2, 0)),
+                                    self.UB_out - self.LB_out)
+                    if self.base_widths is None:
+                        self.widths = new_w
+                    else:
+                        self.widths = np.maximum(new_w, np.sqrt(new_w * self.base_widths))
+        self.x0 = xx
+        R = eff_N = None
+        exit_flag = 0
+        if self.diagnostics:
+            exit_flag, R, eff_N = _diagnose(samples)
+        return {"samples": samples, "f_vals": f_vals, "exit_flag": exit_flag,
+                "log_priors": log_priors, "R": R, "eff_N": eff_N}
+
+
+def _diagnose(samples):
+    """Split-chain potential scale reduction and a crude effective sample size."""
+    N, D = samples.shape
+    if N < 8:
+        return 0, None, None
+    h = N // 2
+    a, b = samples[:h], samples[h:2 * h]
+    W = 0.5 * (a.var(0, ddof=1) + b.var(0, ddof=1))
+    Bv = h * np.var(np.stack([a.mean(0), b.mean(0)]), axis=0, ddof=1)
+    with np.errstate(all="ignore"):
+        R = np.sqrt(((h - 1) / h * W + Bv / h) / W)
+        x = samples - samples.mean(0)
+        rho1 = np.sum(x[1:] * x[:-1], 0) / np.sum(x * x, 0)
+        eff_N = N * (1 - rho1) / (1 + rho1)
+    flag = 1
+    if np.any(R > 1.5):
+        flag = -3
+    elif np.any(R > 1.1):
+        flag = -2
+    elif np.any(eff_N < N / 10.0):
+        flag = -1
+    return flag, R, eff_N

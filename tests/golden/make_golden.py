@@ -249,7 +249,152 @@ def gen_lownoise():
     print("lownoise.npz", len(out), "arrays")
 
 
+def gen_host():
+    """Host-side bookkeeping of the drivers around the path: recommended bounds, prior
+    normalisation, log priors + gradients, the f_min_fill design, a slice-sampling chain."""
+    from gpyreg.f_min_fill import f_min_fill, uuinv, smoothbox_cdf, smoothbox_ppf, \
+        smoothbox_student_t_cdf, smoothbox_student_t_ppf
+    from gpyreg.slice_sample import SliceSampler
+    out = {}
+    rng = np.random.default_rng(400)
+    N, D = 40, 3
+    X, y = synth(rng, N, D)
+    out["X"], out["y"] = X, y
+    for ci, cov in enumerate(COVS):
+        for k, v in cov[4]().get_bounds_info(X, y).items():
+            out[f"cov{ci}.{k}"] = v
+    for mk in (0, 1, 2):
+        for k, v in MEANS[mk]().get_bounds_info(X, y).items():
+            out[f"mean{mk}.{k}"] = v
+    for p in [(1, 0, 0), (1, 2, 0), (1, 1, 1), (0, 2, 1)]:
+        nobj = GaussianNoise(p[0] == 1, p[1] >= 1, p[1] == 2, p[2] == 1)
+        for k, v in nobj.get_bounds_info(X, y).items():
+            out["noise%d%d%d.%s" % (p + (k,))] = v
+    # a GP with every prior type on a single-element hyperparameter group
+    gp = make_gp(D, COVS[5], 1, (1, 2, 0))       # SE-iso: [ell, sf | noise, mult | m0]
+    gp.X, gp.y = X, y
+    gp.set_bounds(gp.get_recommended_bounds())
+    out["gp.LB"], out["gp.UB"] = gp.lower_bounds, gp.upper_bounds
+    priors = {
+        "covariance_log_lengthscale": ("gaussian", (0.2, 1.5)),
+        "covariance_log_outputscale": ("student_t", (0.0, 1.0, 4.0)),
+        "noise_log_scale": ("smoothbox", (-4.0, -1.0, 0.7)),
+        "noise_provided_log_multiplier": ("smoothbox_student_t", (-0.5, 0.5, 0.4, 3.0)),
+        "mean_const": None,
+    }
+    gp.set_priors(priors)
+    out["gp.norm"] = gp.normalization_constants
+    H = np.stack([rng.uniform(np.maximum(gp.lower_bounds, -6), np.minimum(gp.upper_bounds, 6))
+                  for _ in range(12)])
+    out["gp.H"] = H
+    lps, dlps = [], []
+    for h in H:
+        lp, dlp = gp._GP__compute_log_priors(h, True)
+        lps.append(lp)
+        dlps.append(dlp)
+    out["gp.lp"], out["gp.dlp"] = np.array(lps), np.array(dlps)
+    # f_min_fill design (objective = a cheap deterministic function)
+    np.random.seed(7)
+    hp = gp.hyper_priors
+    info = [gp.covariance.get_bounds_info(X, y), gp.noise.get_bounds_info(X, y),
+            gp.mean.get_bounds_info(X, y)]
+    PLB = np.concatenate([i["PLB"] for i in info])
+    PUB = np.concatenate([i["PUB"] for i in info])
+    LB, UB = gp.lower_bounds, gp.upper_bounds
+    PLB = np.minimum(np.maximum(PLB, LB), UB)
+    PUB = np.maximum(np.minimum(PUB, UB), LB)
+    x0 = np.reshape((PLB + PUB) / 2, (1, -1))
+    f = lambda h: float(np.sum((h - 0.3) ** 2))
+    X0, y0 = f_min_fill(f, x0, LB, UB, PLB, PUB, hp, 64, "sobol")
+    out["fmf.PLB"], out["fmf.PUB"], out["fmf.x0"] = PLB, PUB, x0
+    out["fmf.X"], out["fmf.y"] = X0, y0
+    for k in ("mu", "sigma", "df", "a", "b"):
+        out["fmf.hp." + k] = hp[k]
+    # same without any prior
+    gp2 = make_gp(D, COVS[3], 2, (1, 0, 0))
+    gp2.X, gp2.y = X, y
+    gp2.set_bounds(gp2.get_recommended_bounds())
+    np.random.seed(8)
+    info = [gp2.covariance.get_bounds_info(X, y), gp2.noise.get_bounds_info(X, y),
+            gp2.mean.get_bounds_info(X, y)]
+    PLB = np.concatenate([i["PLB"] for i in info])
+    PUB = np.concatenate([i["PUB"] for i in info])
+    LB, UB = gp2.lower_bounds, gp2.upper_bounds
+    PLB = np.minimum(np.maximum(PLB, LB), UB)
+    PUB = np.maximum(np.minimum(PUB, UB), LB)
+    x0 = np.reshape((PLB + PUB) / 2, (1, -1))
+    X0, y0 = f_min_fill(f, x0, LB, UB, PLB, PUB, gp2.hyper_priors, 32, "sobol")
+    out["fmf2.LB"], out["fmf2.UB"], out["fmf2.PLB"], out["fmf2.PUB"] = LB, UB, PLB, PUB
+    out["fmf2.X"], out["fmf2.y"] = X0, y0
+    # helper functions
+    q = np.linspace(0.01, 0.99, 9)
+    out["uuinv"] = uuinv(q, [-3.0, -1.0, 2.0, 5.0], 0.7)
+    out["sb"] = np.array([[smoothbox_cdf(v, 0.7, -1.0, 2.0), smoothbox_student_t_cdf(v, 3.0, 0.7, -1.0, 2.0)]
+                          for v in (-2.5, -1.0, 0.3, 2.0, 4.0)])
+    out["sbppf"] = np.array([[smoothbox_ppf(v, 0.7, -1.0, 2.0), smoothbox_student_t_ppf(v, 3.0, 0.7, -1.0, 2.0)]
+                             for v in q])
+    # slice sampler on a correlated Gaussian inside a box
+    np.random.seed(9)
+    logp = lambda x: float(-0.5 * (x[0] ** 2 + (x[1] - 0.5 * x[0]) ** 2 / 0.25 + x[2] ** 2 / 4))
+    ss = SliceSampler(logp, np.array([0.1, 0.2, -0.3]), np.array([1.0, 1.0, 2.0]),
+                      np.array([-3.0, -3.0, -5.0]), np.array([3.0, 3.0, 5.0]),
+                      {"display": "off", "diagnostics": False})
+    res = ss.sample(40, thin=2, burn=30)
+    out["ss.samples"], out["ss.f_vals"] = res["samples"], res["f_vals"]
+    out["ss.widths"], out["ss.func_count"] = ss.widths, np.array(ss.func_count)
+    np.savez_compressed(os.path.join(HERE, "host.npz"), **out)
+    print("host.npz", len(out), "arrays")
+
+
+def gen_fit():
+    """config 1: the two shipped examples (examples/example_1.py:6-23, example_2.py:5-40),
+    np.random.seed(0) right before fit, options n_samples=10, gp.plot() dropped."""
+    from scipy.stats import norm
+    out = {}
+    np.random.seed(1234)
+    N, D = 31, 1
+    X = -5 + np.random.rand(N, 1) * 10
+    s2 = 0.05 * np.exp(0.5 * X)
+    y = np.sin(X) + np.sqrt(s2) * norm.ppf(np.random.random_sample(X.shape))
+    y[y < 0] = -np.abs(3 * y[y < 0]) ** 2
+    gp = gpyreg.GP(D=D, covariance=Matern(degree=3), mean=NegativeQuadratic(),
+                   noise=GaussianNoise(constant_add=True, user_provided_add=True))
+    gp.set_priors({"covariance_log_lengthscale": None, "covariance_log_outputscale": None,
+                   "mean_const": None, "mean_location": None, "mean_log_scale": None,
+                   "noise_log_scale": ("student_t", (np.log(1e-3), 1.0, 7))})
+    np.random.seed(0)
+    hyp, opt, samp = gp.fit(X=X, y=y, s2=s2, options={"n_samples": 10})
+    xs = np.reshape(np.linspace(-15, 15, 200), (-1, 1))
+    fmu, fs2 = gp.predict(xs, add_noise=False)
+    out["ex1.X"], out["ex1.y"], out["ex1.s2"] = X, y, s2
+    out["ex1.hyp"], out["ex1.opt_x"], out["ex1.opt_fun"] = hyp, opt.x, np.array(opt.fun)
+    out["ex1.xs"], out["ex1.fmu"], out["ex1.fs2"] = xs, fmu, fs2
+    out["ex1.lpost"] = np.array([gp.log_posterior(h) for h in hyp])
+    np.random.seed(1235)
+    N, D = 20, 2
+    X = np.random.uniform(low=-3, high=3, size=(N, D))
+    y = np.reshape(np.sin(np.sum(X, 1)) + np.random.normal(scale=0.1, size=N), (-1, 1))
+    gp = gpyreg.GP(D=D, covariance=SquaredExponential(), mean=ConstantMean(),
+                   noise=GaussianNoise(constant_add=True))
+    gp.set_priors({"covariance_log_outputscale": ("student_t", (0, np.log(10), 3)),
+                   "covariance_log_lengthscale": ("gaussian", (np.log(np.std(X, ddof=1)), np.log(10))),
+                   "noise_log_scale": ("gaussian", (np.log(1e-3), 1.0)),
+                   "mean_const": ("smoothbox", (np.min(y), np.max(y), 1.0))})
+    np.random.seed(0)
+    hyp, opt, samp = gp.fit(X=X, y=y, options={"n_samples": 10})
+    xs = np.random.default_rng(5).uniform(-3, 3, (100, 2))
+    fmu, fs2 = gp.predict(xs, add_noise=True)
+    out["ex2.X"], out["ex2.y"] = X, y
+    out["ex2.hyp"], out["ex2.opt_x"], out["ex2.opt_fun"] = hyp, opt.x, np.array(opt.fun)
+    out["ex2.xs"], out["ex2.fmu"], out["ex2.fs2"] = xs, fmu, fs2
+    out["ex2.lpost"] = np.array([gp.log_posterior(h) for h in hyp])
+    np.savez_compressed(os.path.join(HERE, "fit.npz"), **out)
+    print("fit.npz", len(out), "arrays; ex1 opt fun", opt.fun)
+
+
 if __name__ == "__main__":
+    gen_fit()
+    gen_host()
     gen_plugins()
     gen_core()
     gen_lownoise()
