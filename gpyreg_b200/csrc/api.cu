@@ -106,6 +106,7 @@ static cudaError_t gemm_attr() {
 // `wide` forces the one-CTA-per-tile kernel (needed when the product is done in place).
 template <class Op>
 static void launch_gemm(gpb_ctx* ctx, const Op& op, dim3 grid, bool wide = false) {
+  if (Op::SLOT_MAJOR) grid = dim3(grid.y, grid.x);      // slot in x, tile in y (see gemm.cuh)
   if (wide || ctx->gemm_bn == 128) {
     gemm_nt_kernel<Op, 128><<<grid, GEMM_THREADS, gemm_smem<128>(), ctx->stream>>>(op);
   } else {
@@ -1203,7 +1204,7 @@ extern "C" int gpb_debug_gemm_nt(gpb_ctx* ctx, const double* A, const double* B,
   CKC(cudaMemcpyAsync(dA, A, sizeof(double) * M * K, cudaMemcpyHostToDevice, ctx->stream));
   CKC(cudaMemcpyAsync(dB, B, sizeof(double) * N * K, cudaMemcpyHostToDevice, ctx->stream));
   CKC(cudaMemcpyAsync(dC, C, sizeof(double) * M * N, cudaMemcpyHostToDevice, ctx->stream));
-  OpGeneric op{dA, dB, dC, M, N, M, K, alpha, beta};
+  OpGeneric op{dA, dB, dC, M, N, M, K, alpha, alpha != 0.0 ? beta / alpha : 0.0};
   launch_gemm(ctx, op, dim3(M / BM, N / BN));
   CKC(cudaMemcpyAsync(C, dC, sizeof(double) * M * N, cudaMemcpyDeviceToHost, ctx->stream));
   CKC(cudaStreamSynchronize(ctx->stream));
@@ -1228,7 +1229,7 @@ extern "C" int gpb_debug_gemm_bench(gpb_ctx* ctx, int M, int N, int K, int reps,
   fill_kernel<<<grid1d((long long)M * K), 256, 0, ctx->stream>>>(dA, 0.5, (long long)M * K);
   fill_kernel<<<grid1d((long long)N * K), 256, 0, ctx->stream>>>(dB, 0.25, (long long)N * K);
   fill_kernel<<<grid1d((long long)M * N), 256, 0, ctx->stream>>>(dC, 0.0, (long long)M * N);
-  OpGeneric op{dA, dB, dC, M, N, M, K, -1.0, 1.0};   // the trailing-update form
+  OpGeneric op{dA, dB, dC, M, N, M, K, -1.0, -1.0};   // the trailing-update form C - A B^T
   for (int i = 0; i < 3; ++i) launch_gemm(ctx, op, dim3(M / BM, N / BN));
   CKC(cudaEventRecord(ctx->ev[6], ctx->stream));
   for (int i = 0; i < reps; ++i) launch_gemm(ctx, op, dim3(M / BM, N / BN));

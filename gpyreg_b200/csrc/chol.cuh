@@ -6,12 +6,17 @@
 //   nlz_kernel        nlZ = z^T z/(2 sl) + sum log L_ii + N log(2 pi sl)/2
 // The dense O(N^3) work between these is the tile GEMM in gemm.cuh.
 #pragma once
+#include <utility>
+
 #include "common.cuh"
 
 namespace gpb {
 
 constexpr int DP_PITCH = T + 1;                                   // 129
-constexpr size_t DIAG_SMEM = (size_t)T * DP_PITCH * sizeof(double) + 5 * T * sizeof(double);
+constexpr int SB = 32;                                            // sub-block of the tile factorisation
+constexpr int IVP = 36;                                           // pitch of the 32x32 scratch blocks
+constexpr size_t DIAG_SMEM =
+    ((size_t)T * DP_PITCH + 5 * SB * IVP + 3 * T) * sizeof(double);
 
 struct DiagArgs {
   double* Abuf; double* Wbuf;      // Wbuf may be null (nlZ-only path)
@@ -25,70 +30,166 @@ struct DiagArgs {
   int* fail;                       // [nslots]  set to 1 on a pivot <= 0 or NaN
 };
 
-// S(r,c) lives at S[c*129 + r]: column-major, conflict-free along r.
+__device__ __forceinline__ void dmma_t(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+
+// --- 32x32 diagonal block in registers, one row per lane; every register index is a
+// compile-time constant (the steps are instantiated through a fold expression).
+template <int J>
+__device__ __forceinline__ void chol32_step(double (&arow)[SB], int lane, double* rsq_blk, int& failed) {
+  double piv = __shfl_sync(0xffffffffu, arow[J], J);
+  if (!(piv > 0.0)) { failed = 1; piv = 1.0; }       // LAPACK dpotrf: ajj <= 0 or NaN -> info > 0
+  const double rinv = rsqrt(piv);
+  if (lane == J) { arow[J] = piv * rinv; rsq_blk[J] = rinv; }
+  else if (lane > J) arow[J] *= rinv;
+#pragma unroll
+  for (int c = J + 1; c < SB; ++c) {
+    const double lcj = __shfl_sync(0xffffffffu, arow[J], c);
+    if (lane >= c) arow[c] -= arow[J] * lcj;
+  }
+}
+template <int... Js>
+__device__ __forceinline__ void chol32_all(double (&arow)[SB], int lane, double* rsq_blk, int& failed,
+                                           std::integer_sequence<int, Js...>) {
+  (chol32_step<Js>(arow, lane, rsq_blk, failed), ...);
+}
+// lane c owns column c of Inv = L^-1: inv[q] = Inv(q, c)
+template <int RR>
+__device__ __forceinline__ void inv32_step(const double (&arow)[SB], double (&inv)[SB], int lane,
+                                           const double* rsq_blk) {
+  if (RR == 0) return;
+  double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+  for (int q = 0; q < RR; ++q) {
+    const double lrq = __shfl_sync(0xffffffffu, arow[q], RR);     // L(RR, q), held by lane RR
+    if (q & 1) s1 += lrq * inv[q]; else s0 += lrq * inv[q];
+  }
+  const double drr = rsq_blk[RR];
+  if (lane < RR) inv[RR] = -(s0 + s1) * drr;
+}
+template <int... Rs>
+__device__ __forceinline__ void inv32_all(const double (&arow)[SB], double (&inv)[SB], int lane,
+                                          const double* rsq_blk, std::integer_sequence<int, Rs...>) {
+  (inv32_step<Rs>(arow, inv, lane, rsq_blk), ...);
+}
+
+// One CTA factors a 128x128 diagonal tile and inverts the factor.
+//   S(r,c) lives at S[c*129 + r] (column-major, conflict-free along r).
+//   The tile is processed in four 32-wide block columns.  Per block column:
+//     1. warp 0 holds the 32x32 diagonal block one row per lane IN REGISTERS, runs the
+//        right-looking Cholesky with warp shuffles (pivot check like LAPACK dpotrf: a pivot
+//        <= 0 or NaN marks the matrix as failed) and inverts the 32x32 factor the same way;
+//     2. all 8 warps: panel below  L21 = P * Inv^T  on the FP64 tensor pipe (DMMA);
+//     3. all 8 warps: trailing update  S -= L21 L21^T  on DMMA.
+//   Then D = L^-1 is assembled block by block (D_ij = -Inv_i * sum_k L_ik D_kj, DMMA); the
+//   off-diagonal blocks of D are kept transposed in the unused upper triangle of S.
 __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
   extern __shared__ double dsm[];
-  double* S = dsm;                       // [T][129]
-  double* dinv = dsm + T * DP_PITCH;     // 1 / L_jj
-  double* bsh = dinv + T;                // b_k
-  double* lg = bsh + T;                  // log L_jj
-  double* cj = lg + T;                   // scaled pivot column
-  double* dd = cj + T;                   // diagonal of L
+  double* S = dsm;                              // [T][129]
+  double* Iv = S + T * DP_PITCH;                // [4][32][36]  Inv_p(r,c) at Iv[p][c*36 + r]
+  double* Tm = Iv + 4 * SB * IVP;               // [32][36] scratch, T(m,n) at Tm[n*36 + m]
+  double* bsh = Tm + SB * IVP;                  // b_k
+  double* lg = bsh + T;                         // log L_jj
+  double* rsq = lg + T;                         // 1 / L_jj
+  __shared__ int s_failed;
   const int slot = a.sel[blockIdx.x];
   const int k = a.k, Np = a.Np;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, tq = lane & 3;
   double* A = a.Abuf + slot * a.smat + (long long)k * T + (long long)k * T * Np;
-  const int nact = min(T, a.N - k * T);  // rows/cols of this tile that hold data (rest: identity)
+  const int nact = min(T, a.N - k * T);         // rows/cols holding data (the rest is identity)
+  const int nact8 = (nact + 7) & ~7;
 
-  // load the lower triangle of the tile
   for (int e = tid; e < T * T; e += 256) {
     const int r = e & (T - 1), c = e >> 7;
     S[c * DP_PITCH + r] = (r >= c) ? A[(long long)c * Np + r] : 0.0;
   }
-  if (tid < T) bsh[tid] = a.bvec ? a.bvec[(long long)slot * Np + k * T + tid] : 0.0;
+  for (int e = tid; e < 4 * SB * IVP; e += 256) {     // diagonal-block inverses start as identity
+    const int within = e % (SB * IVP);
+    Iv[e] = (within / IVP == within % IVP) ? 1.0 : 0.0;
+  }
+  if (tid < T) {
+    bsh[tid] = a.bvec ? a.bvec[(long long)slot * Np + k * T + tid] : 0.0;
+    rsq[tid] = 1.0;
+  }
+  if (tid == 0) s_failed = 0;
   __syncthreads();
 
-  // ---- right-looking Cholesky of the active block, all 256 threads on the rank-1 update.
-  // The scaled pivot column lives in its own array (cj) so the update loop's loads do not
-  // alias its stores and can be software-pipelined; the diagonal goes to dd[].
-  int failed = 0;
-  const int r = tid & (T - 1), half = tid >> 7;
-  for (int j = 0; j < nact; ++j) {
-    double piv = S[j * DP_PITCH + j];
-    if (!(piv > 0.0)) { failed = 1; piv = 1.0; }     // LAPACK dpotrf: ajj <= 0 or NaN -> info > 0
-    const double d = sqrt(piv);
-    if (half == 0) {
-      if (r == j) dd[j] = d;
-      else if (r > j && r < nact) {
-        const double l = S[j * DP_PITCH + r] / d;
-        S[j * DP_PITCH + r] = l;
-        cj[r] = l;
+  for (int p = 0; p < T / SB; ++p) {
+    const int c0 = p * SB;
+    if (c0 >= nact) break;
+    double* Ivp = Iv + p * SB * IVP;
+    // ---- 1. diagonal block in registers (warp 0): lane r owns row r
+    if (warp == 0) {
+      double arow[SB];
+#pragma unroll
+      for (int c = 0; c < SB; ++c) arow[c] = (c <= lane) ? S[(c0 + c) * DP_PITCH + c0 + lane] : 0.0;
+      int failed = 0;
+      chol32_all(arow, lane, rsq + c0, failed, std::make_integer_sequence<int, SB>{});
+      if (failed && lane == 0) s_failed = 1;
+#pragma unroll
+      for (int c = 0; c < SB; ++c)
+        if (c <= lane) S[(c0 + c) * DP_PITCH + c0 + lane] = arow[c];
+      __syncwarp();
+      // inverse of the 32x32 factor: lane c owns column c; inv[q] = Inv(q, c)
+      double inv[SB];
+      {
+        const double dc = rsq[c0 + lane];
+#pragma unroll
+        for (int q = 0; q < SB; ++q) inv[q] = (q == lane) ? dc : 0.0;
+      }
+      inv32_all(arow, inv, lane, rsq + c0, std::make_integer_sequence<int, SB>{});
+#pragma unroll
+      for (int q = 0; q < SB; ++q) Ivp[lane * IVP + q] = inv[q];
+    }
+    __syncthreads();
+    // ---- 2. panel: rows below the block, L21 = P * Inv^T   (C(m,n) = sum_k P(m,k) Inv(n,k))
+    const int mblocks = max(0, (nact8 - c0 - SB) / 8);
+    for (int mb = warp; mb < mblocks; mb += 8) {
+      const int m0 = c0 + SB + mb * 8;
+      double af[8];
+#pragma unroll
+      for (int k4 = 0; k4 < 8; ++k4) af[k4] = S[(c0 + k4 * 4 + tq) * DP_PITCH + m0 + g];
+      double acc[4][2];
+#pragma unroll
+      for (int n8 = 0; n8 < 4; ++n8) {
+        acc[n8][0] = acc[n8][1] = 0.0;
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4)
+          dmma_t(acc[n8][0], acc[n8][1], af[k4], Ivp[(k4 * 4 + tq) * IVP + n8 * 8 + g]);
+      }
+#pragma unroll
+      for (int n8 = 0; n8 < 4; ++n8) {
+        S[(c0 + n8 * 8 + 2 * tq) * DP_PITCH + m0 + g] = acc[n8][0];
+        S[(c0 + n8 * 8 + 2 * tq + 1) * DP_PITCH + m0 + g] = acc[n8][1];
       }
     }
     __syncthreads();
-    if (r > j && r < nact) {
-      const double lrj = cj[r];
-      double* Sr = S + r;
-      int c = j + 1 + half;
-      for (; c + 6 <= r; c += 8) {
-        const double u0 = cj[c], u1 = cj[c + 2], u2 = cj[c + 4], u3 = cj[c + 6];
-        double s0 = Sr[c * DP_PITCH], s1 = Sr[(c + 2) * DP_PITCH], s2 = Sr[(c + 4) * DP_PITCH],
-               s3 = Sr[(c + 6) * DP_PITCH];
-        s0 -= lrj * u0; s1 -= lrj * u1; s2 -= lrj * u2; s3 -= lrj * u3;
-        Sr[c * DP_PITCH] = s0; Sr[(c + 2) * DP_PITCH] = s1; Sr[(c + 4) * DP_PITCH] = s2;
-        Sr[(c + 6) * DP_PITCH] = s3;
+    // ---- 3. trailing update of the lower 8x8 blocks: S -= L21 L21^T
+    const int nblk = mblocks * (mblocks + 1) / 2;
+    for (int idx = warp; idx < nblk; idx += 8) {
+      int bi, bj;
+      tri_decode(idx, bi, bj);
+      const int r0 = c0 + SB + bi * 8, q0 = c0 + SB + bj * 8;
+      double c0v = S[(q0 + 2 * tq) * DP_PITCH + r0 + g];
+      double c1v = S[(q0 + 2 * tq + 1) * DP_PITCH + r0 + g];
+#pragma unroll
+      for (int k4 = 0; k4 < 8; ++k4) {
+        const double av = -S[(c0 + k4 * 4 + tq) * DP_PITCH + r0 + g];
+        const double bv = S[(c0 + k4 * 4 + tq) * DP_PITCH + q0 + g];
+        dmma_t(c0v, c1v, av, bv);
       }
-      for (; c <= r; c += 2) Sr[c * DP_PITCH] -= lrj * cj[c];
+      S[(q0 + 2 * tq) * DP_PITCH + r0 + g] = c0v;
+      S[(q0 + 2 * tq + 1) * DP_PITCH + r0 + g] = c1v;
     }
     __syncthreads();
   }
-  if (tid < nact) S[tid * DP_PITCH + tid] = dd[tid];
-  __syncthreads();
-  if (tid < T) {
-    const double ljj = S[tid * DP_PITCH + tid];      // 1.0 in the padded part
-    dinv[tid] = 1.0 / ljj;
-    lg[tid] = (tid < nact) ? log(ljj) : 0.0;
-  }
+
+  if (tid < T) lg[tid] = (tid < nact) ? log(S[tid * DP_PITCH + tid]) : 0.0;
   __syncthreads();
   // write L_kk back (lower triangle)
   for (int e = tid; e < T * T; e += 256) {
@@ -99,59 +200,76 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
     double s = 0.0;
     for (int j = 0; j < nact; ++j) s += lg[j];       // fixed order
     a.logdet[(long long)slot * a.Nt + k] = s;
-    if (failed) a.fail[slot] = 1;
+    if (s_failed) a.fail[slot] = 1;
   }
 
-  // ---- D = L^-1 by forward substitution, one thread per column c; D(q,c), q > c, is kept
-  // transposed in the (free) strict upper triangle: S(c,q).  No barrier needed: a thread
-  // only reads L (final) and its own column.
-  // The loops run over (rr, q) uniformly so a warp reads L(rr,q) as a broadcast and
-  // D(q,c) from consecutive banks.
-  if (tid < T) {
-    const int c = tid;
-    for (int rr = 1; rr < nact; ++rr) {
-      if (c < rr) {
-        double acc0 = S[c * DP_PITCH + rr] * dinv[c];  // L(rr,c) * D(c,c)
-        double acc1 = 0.0;
-        int q = rr - 1;
-        for (; q - 1 > c; q -= 2) {
-          acc0 += S[q * DP_PITCH + rr] * S[q * DP_PITCH + c];
-          acc1 += S[(q - 1) * DP_PITCH + rr] * S[(q - 1) * DP_PITCH + c];
+  // ---- D = L^-1, 32x32 blocks: D_jj = Inv_j ; D_ij = -Inv_i * sum_{kb=j}^{i-1} L_i,kb D_kb,j
+  // D(R,C) for R in a later block than C is stored transposed at S[R*129 + C].
+  for (int j = 0; j < T / SB; ++j) {
+    if (j * SB >= nact) break;
+    for (int i = j + 1; i < T / SB; ++i) {
+      if (i * SB >= nact) break;
+      // pass A: Tm = sum_kb L_i,kb * D_kb,j     (16 output 8x8 blocks, two per warp)
+      for (int blk = warp; blk < 16; blk += 8) {
+        const int mi = blk >> 2, ni = blk & 3;
+        double t0 = 0.0, t1 = 0.0;
+        for (int kb = j; kb < i; ++kb) {
+#pragma unroll
+          for (int k4 = 0; k4 < 8; ++k4) {
+            const int q = k4 * 4 + tq;
+            const double av = S[(kb * SB + q) * DP_PITCH + i * SB + mi * 8 + g];
+            const double bv = (kb == j) ? Iv[j * SB * IVP + (ni * 8 + g) * IVP + q]
+                                        : S[(kb * SB + q) * DP_PITCH + j * SB + ni * 8 + g];
+            dmma_t(t0, t1, av, bv);
+          }
         }
-        if (q > c) acc0 += S[q * DP_PITCH + rr] * S[q * DP_PITCH + c];
-        S[rr * DP_PITCH + c] = -(acc0 + acc1) * dinv[rr];
+        Tm[(ni * 8 + 2 * tq) * IVP + mi * 8 + g] = t0;
+        Tm[(ni * 8 + 2 * tq + 1) * IVP + mi * 8 + g] = t1;
       }
+      __syncthreads();
+      // pass B: D_ij = -Inv_i * Tm
+      for (int blk = warp; blk < 16; blk += 8) {
+        const int mi = blk >> 2, ni = blk & 3;
+        double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) {
+          const int q = k4 * 4 + tq;
+          const double av = -Iv[i * SB * IVP + q * IVP + mi * 8 + g];
+          const double bv = Tm[(ni * 8 + g) * IVP + q];
+          dmma_t(d0, d1, av, bv);
+        }
+        const int R = i * SB + mi * 8 + g, C = j * SB + ni * 8 + 2 * tq;
+        S[R * DP_PITCH + C] = d0;
+        S[R * DP_PITCH + C + 1] = d1;
+      }
+      __syncthreads();
     }
   }
   __syncthreads();
+  // element (rr, c) of D, rr >= c
+  auto Dval = [&](int rr, int c) -> double {
+    if ((rr >> 5) == (c >> 5)) return Iv[(rr >> 5) * SB * IVP + (c & 31) * IVP + (rr & 31)];
+    return (rr < nact) ? S[rr * DP_PITCH + c] : 0.0;
+  };
   // ---- outputs: D_k (column-major, zeros above the diagonal), D_k^T, W diag tile, z_k
   double* Dk = a.Dbuf + ((long long)slot * a.Nt + k) * T * T;
   double* DTk = a.DTbuf + ((long long)slot * a.Nt + k) * T * T;
   double* Wd = a.Wbuf ? a.Wbuf + slot * a.smat + (long long)k * T + (long long)k * T * Np : nullptr;
   for (int e = tid; e < T * T; e += 256) {
     const int rr = e & (T - 1), c = e >> 7;          // element (rr, c) of D
-    double v;
-    if (rr == c) v = dinv[c];
-    else if (rr > c) v = (rr < nact) ? S[rr * DP_PITCH + c] : 0.0;
-    else v = 0.0;
+    const double v = (rr >= c) ? Dval(rr, c) : 0.0;
     Dk[c * T + rr] = v;
     if (Wd) Wd[(long long)c * Np + rr] = v;
   }
   for (int e = tid; e < T * T; e += 256) {
     const int rr = e & (T - 1), c = e >> 7;          // element (rr, c) of D^T = D(c, rr)
-    double v;
-    if (rr == c) v = dinv[c];
-    else if (c > rr) v = (c < nact) ? S[c * DP_PITCH + rr] : 0.0;
-    else v = 0.0;
-    DTk[c * T + rr] = v;
+    DTk[c * T + rr] = (c >= rr) ? Dval(c, rr) : 0.0;
   }
   if (a.zvec && tid < T) {
     const int rr = tid;
     double s = 0.0;
-    if (rr < nact) {
-      for (int c = 0; c < rr; ++c) s += S[rr * DP_PITCH + c] * bsh[c];
-      s += dinv[rr] * bsh[rr];
-    }
+    if (rr < nact)
+      for (int c = 0; c <= rr; ++c) s += Dval(rr, c) * bsh[c];
     a.zvec[(long long)slot * Np + k * T + rr] = s;
   }
 }

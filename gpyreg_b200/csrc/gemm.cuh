@@ -30,7 +30,7 @@ struct GemmTile {
   const double* E; long long lde;     // reduce mode: rowsum[m] = sum_n C(m,n)*E(m,n) (E null: C^2)
   double* rowsum; long long rs_half;  // rs_half: offset between the two column halves
   int K;
-  double alpha, beta;
+  double alpha, cscale;               // result = alpha * (cscale * C + A B^T); cscale = beta / alpha
   bool valid;
 };
 
@@ -73,8 +73,12 @@ gemm_nt_kernel(const __grid_constant__ Op op) {
   constexpr int WN = BN_ / 2;              // warp tile width
   constexpr int NI = WN / 8;
   constexpr int MODE = Op::MODE;
+  // default order: x = (tile, half), y = batch slot.  SLOT_MAJOR ops (tiles of unequal K) put
+  // the slot in x and the tile in y, so the block scheduler hands out the longest tiles of
+  // ALL matrices first (longest-processing-time order) instead of matrix after matrix.
   const int half = (NS > 1) ? (int)(blockIdx.x % NS) : 0;
-  GemmTile t = op.resolve((int)(blockIdx.x / NS));
+  const int bxq = (int)(blockIdx.x / NS);
+  GemmTile t = Op::SLOT_MAJOR ? op.resolve((int)blockIdx.y, bxq) : op.resolve(bxq, (int)blockIdx.y);
   if (!t.valid) return;
   if (NS > 1) {
     const long long off = (long long)half * BN_;
@@ -126,7 +130,7 @@ gemm_nt_kernel(const __grid_constant__ Op op) {
   if (MODE & GM_BETA) {
     // start from (beta/alpha) * C: the loads go straight into the accumulator registers and
     // overlap the pipeline fill, instead of a latency-bound read-modify-write epilogue
-    const double f = t.beta / t.alpha;
+    const double f = t.cscale;
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
@@ -242,35 +246,37 @@ __device__ __forceinline__ GemmTile empty_tile() {
   t.rs_half = 0;
   t.K = 0;
   t.alpha = 1.0;
-  t.beta = 0.0;
+  t.cscale = 0.0;
   t.valid = true;
   return t;
 }
 
 // debug / benchmark: plain C = alpha A B^T + beta C
 struct OpGeneric {
+  static constexpr bool SLOT_MAJOR = false;
   static constexpr int MODE = GM_BETA | GM_STORE;
   const double* A; const double* B; double* C;
   long long lda, ldb, ldc;
   int K;
-  double alpha, beta;
-  __device__ GemmTile resolve(int bx) const {
+  double alpha, cscale;
+  __device__ GemmTile resolve(int bx, int by) const {
     GemmTile t = empty_tile();
     t.A = A + (long long)bx * BM; t.lda = lda;
-    t.B = B + (long long)blockIdx.y * BN; t.ldb = ldb;
-    t.C = C + (long long)bx * BM + (long long)blockIdx.y * BN * ldc; t.ldc = ldc;
-    t.K = K; t.alpha = alpha; t.beta = beta;
+    t.B = B + (long long)by * BN; t.ldb = ldb;
+    t.C = C + (long long)bx * BM + (long long)by * BN * ldc; t.ldc = ldc;
+    t.K = K; t.alpha = alpha; t.cscale = cscale;
     return t;
   }
 };
 
 // potrf panel, step k:  L_ik = A_ik * D_k^T  (i > k), in place
 struct OpPanel {
+  static constexpr bool SLOT_MAJOR = false;
   static constexpr int MODE = GM_STORE;
   BatchBufs b; int k;
-  __device__ GemmTile resolve(int bx) const {
+  __device__ GemmTile resolve(int bx, int by) const {
     GemmTile t = empty_tile();
-    const int slot = b.sel[blockIdx.y];
+    const int slot = b.sel[by];
     const int i = k + 1 + bx;
     double* tile = b.Abuf + slot * b.smat + (long long)i * T + (long long)k * T * b.Np;
     t.A = tile; t.lda = b.Np;
@@ -283,11 +289,12 @@ struct OpPanel {
 
 // potrf trailing update, step k:  A_ij -= L_ik L_jk^T  (i >= j > k)
 struct OpSyrk {
+  static constexpr bool SLOT_MAJOR = false;
   static constexpr int MODE = GM_BETA | GM_STORE;
   BatchBufs b; int k;
-  __device__ GemmTile resolve(int bx) const {
+  __device__ GemmTile resolve(int bx, int by) const {
     GemmTile t = empty_tile();
-    const int slot = b.sel[blockIdx.y];
+    const int slot = b.sel[by];
     int a, c;
     tri_decode(bx, a, c);
     const int i = k + 1 + a, j = k + 1 + c;
@@ -295,18 +302,19 @@ struct OpSyrk {
     t.A = base + (long long)i * T + (long long)k * T * b.Np; t.lda = b.Np;
     t.B = base + (long long)j * T + (long long)k * T * b.Np; t.ldb = b.Np;
     t.C = base + (long long)i * T + (long long)j * T * b.Np; t.ldc = b.Np;
-    t.K = T; t.alpha = -1.0; t.beta = 1.0;
+    t.K = T; t.alpha = -1.0; t.cscale = -1.0;
     return t;
   }
 };
 
 // H pass:  upper tile (j,i) <- (L_ij * D_j)^T  for every i > j
 struct OpHpass {
+  static constexpr bool SLOT_MAJOR = false;
   static constexpr int MODE = GM_STORET;
   BatchBufs b;
-  __device__ GemmTile resolve(int bx) const {
+  __device__ GemmTile resolve(int bx, int by) const {
     GemmTile t = empty_tile();
-    const int slot = b.sel[blockIdx.y];
+    const int slot = b.sel[by];
     int a, c;
     tri_decode(bx, a, c);
     const int i = a + 1, j = c;
@@ -321,12 +329,13 @@ struct OpHpass {
 
 // triangular inverse, block column j (descending):  W_ij = - sum_{k=j+1..i} W_ik H_kj
 struct OpWrec {
+  static constexpr bool SLOT_MAJOR = true;
   static constexpr int MODE = GM_STORE | GM_STORET;
   BatchBufs b; int j; int dual;
-  __device__ GemmTile resolve(int bx) const {
+  __device__ GemmTile resolve(int bx, int by) const {
     GemmTile t = empty_tile();
-    const int slot = b.sel[blockIdx.y];
-    const int i = j + 1 + bx;
+    const int slot = b.sel[by];
+    const int i = b.Nt - 1 - bx;            // bx = 0 is the longest product (K = (i-j)*T)
     double* W = b.Wbuf + slot * b.smat;
     const double* H = b.Abuf + slot * b.smat;
     t.A = W + (long long)i * T + (long long)(j + 1) * T * b.Np; t.lda = b.Np;
@@ -340,11 +349,12 @@ struct OpWrec {
 
 // K^-1 = W^T W (lower tiles a >= c) written over the lower triangle of Abuf
 struct OpSyrk2 {
+  static constexpr bool SLOT_MAJOR = true;
   static constexpr int MODE = GM_STORE;
   BatchBufs b;
-  __device__ GemmTile resolve(int bx) const {
+  __device__ GemmTile resolve(int bx, int by) const {
     GemmTile t = empty_tile();
-    const int slot = b.sel[blockIdx.y];
+    const int slot = b.sel[by];
     int a, c;
     tri_decode(bx, a, c);
     const double* W = b.Wbuf + slot * b.smat;
@@ -363,15 +373,16 @@ struct OpSyrk2 {
 // predictive variance:  part[nt][j] = sum_{m in tile nt} ( sum_k Bt(j,k) Wm(m,k) )^2   (L_chol)
 //                    or sum_{m in tile nt} ( sum_k Bt(j,k) X(m,k) ) * Bt(j,m)            (low noise)
 struct OpPred {
+  static constexpr bool SLOT_MAJOR = false;
   static constexpr int MODE = GM_REDUCE;
   const double* Bt; long long ldbt;   // (Mcp x Np) column-major
   const double* Wm; long long ldw;    // (Np x Np) column-major
   double* part;                       // [Nt*ns][Mcp]
   int Mcp; int tri;                   // tri = 1: Wm lower triangular -> K = (nt+1)*T
   int Np; int ns;                     // ns = column halves per tile (BN / BN_)
-  __device__ GemmTile resolve(int bx) const {
+  __device__ GemmTile resolve(int bx, int by) const {
     GemmTile t = empty_tile();
-    const int jt = bx, nt = (int)gridDim.y - 1 - (int)blockIdx.y;   // longest K first
+    const int jt = bx, nt = (int)gridDim.y - 1 - by;   // longest K first
     t.A = Bt + (long long)jt * BM; t.lda = ldbt;
     t.B = Wm + (long long)nt * BN; t.ldb = ldw;
     t.K = tri ? (nt + 1) * T : Np;
