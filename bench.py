@@ -347,13 +347,17 @@ def run_b200(args, wl):
     cpu_t, cpu_units = cpu_eval_seconds(wl, hyp, X, y, reps)
     cpu = {"value": cpu_units / cpu_t, "unit": unit, "cores": blas_threads(), "kind": "port",
            "sample": f"{reps} hyperparameter row(s) of the same workload, {cpu_t:.1f} s"}
+    if wl["kind"] == "predict":
+        line_extra = {"samples": B, "test_points_per_step_per_gpu": wl["M"]}
+    else:
+        line_extra = {}
     line = {
         "metric": metric_name(wl), "value": value, "unit": unit, "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": wl["name"], "N": N, "D": spec.D, "P": P, "batch_per_gpu": B,
-                   "global_batch": B * world, "parallelism": f"hyp-batch x{world}",
+                   "global_batch": B * world, "parallelism": f"hyp-batch x{world}", **line_extra,
                    "l2": "working set (B x %.0f MB of matrices) far larger than the 126 MB L2"
                          % (2 * Np * Np * 8 / 1e6)},
         "clocks": clocks,

@@ -24,7 +24,8 @@ using namespace gpb;
 struct Bufs {              // device storage for `cap` batch slots
   int cap = 0;
   bool has_w = false;
-  int Np = 0, Nt = 0, D = 0, P = 0;
+  bool cap_is_max = false;   // cap is limited by device memory, not by the request
+  int Np = 0, Nt = 0, D = 0, P = 0, cov_n = 0;
   double *Abuf = nullptr, *Wbuf = nullptr, *Dbuf = nullptr, *DTbuf = nullptr;
   double *xs = nullptr, *resid = nullptr, *sn2v = nullptr, *bvec = nullptr, *zvec = nullptr,
          *alpha = nullptr, *logdet = nullptr, *mult = nullptr, *hyp = nullptr, *nlz = nullptr,
@@ -205,6 +206,7 @@ static void free_bufs(Bufs& b) {
   }
   b.cap = 0;
   b.has_w = false;
+  b.cap_is_max = false;
 }
 
 extern "C" void gpb_destroy(gpb_ctx* ctx) {
@@ -331,6 +333,7 @@ static int alloc_bufs(gpb_ctx* ctx, Bufs& b, int cap, bool with_w, int Np, int D
   b.Nt = Np / T;
   b.D = D;
   b.P = md.P;
+  b.cov_n = md.cov_n;
   const size_t smat = (size_t)Np * Np;
   const size_t nt = b.Nt;
   CK(cudaMalloc(&b.Abuf, smat * 8 * cap));
@@ -361,19 +364,24 @@ static int alloc_bufs(gpb_ctx* ctx, Bufs& b, int cap, bool with_w, int Np, int D
 static int ensure_ws(gpb_ctx* ctx, long long B, bool with_w) {
   Bufs& w = ctx->ws;
   const Model& md = ctx->md;
+  const bool shape_ok = w.cap > 0 && (w.has_w || !with_w) && w.Np == ctx->Np && w.D == ctx->D &&
+                        w.P == md.P && w.cov_n == md.cov_n;
+  // fast path (no cudaMemGetInfo): big enough, or already as big as memory allows
+  if (shape_ok && (w.cap >= B || w.cap_is_max)) return GPB_OK;
   size_t freeb = 0, totalb = 0;
   CK(cudaMemGetInfo(&freeb, &totalb));
   size_t have = 0;
-  if (w.cap) have = per_slot_bytes(w.Np, w.D, w.P, md.cov_n, w.has_w) * w.cap;
-  size_t limit = ctx->ws_limit ? ctx->ws_limit : (size_t)((freeb + have) * 0.70);
-  const size_t per = per_slot_bytes(ctx->Np, ctx->D, md.P, md.cov_n, with_w || w.has_w);
-  long long fit = (long long)(limit / per);
+  if (w.cap) have = per_slot_bytes(w.Np, w.D, w.P, w.cov_n, w.has_w) * w.cap;
+  const size_t limit = ctx->ws_limit ? ctx->ws_limit : (size_t)((freeb + have) * 0.70);
+  const bool keep_w = with_w || (w.has_w && w.Np == ctx->Np);
+  const size_t per = per_slot_bytes(ctx->Np, ctx->D, md.P, md.cov_n, keep_w);
+  const long long fit = (long long)(limit / per);
   if (fit < 1) FAIL(GPB_ENOMEM, "workspace for one matrix does not fit in device memory");
   const int want = (int)std::min<long long>(std::min<long long>(B, fit), 32768);
-  const bool ok = w.cap >= want && (w.has_w || !with_w) && w.Np == ctx->Np && w.D == ctx->D &&
-                  w.P == md.P;
-  if (ok) return GPB_OK;
-  return alloc_bufs(ctx, w, want, with_w || w.has_w, ctx->Np, ctx->D, md);
+  int rc = alloc_bufs(ctx, w, want, keep_w, ctx->Np, ctx->D, md);
+  if (rc != GPB_OK) return rc;
+  w.cap_is_max = (want == fit);
+  return GPB_OK;
 }
 
 // ---------------------------------------------------------------------------------
