@@ -46,6 +46,7 @@ struct gpb_ctx {
   double *dX = nullptr, *dy = nullptr, *ds2 = nullptr;
   size_t ws_limit = 0;
   int gemm_bn = 64;          // 64: two CTAs per SM (default); 128: one (env GPB_GEMM_BN)
+  long long* diag_dbg = nullptr;   // env GPB_DIAG_DBG: phase clock stamps of the diagonal kernel
   Bufs ws;
   double timings[6] = {0, 0, 0, 0, 0, 0};
   long long launches = 0;
@@ -179,6 +180,7 @@ extern "C" int gpb_create(int device, gpb_ctx** out) {
   }
   ctx->stream = ctx->own_stream;
   if (const char* bn = getenv("GPB_GEMM_BN")) ctx->gemm_bn = (atoi(bn) == 128) ? 128 : 64;
+  if (getenv("GPB_DIAG_DBG")) cudaMalloc(&ctx->diag_dbg, 40 * sizeof(long long));
   for (auto& ev : ctx->ev) cudaEventCreate(&ev);
   int rc = init_attrs(ctx);
   if (rc != GPB_OK) {
@@ -301,7 +303,7 @@ extern "C" int gpb_set_data(gpb_ctx* ctx, const double* X, const double* y, cons
     CK(cudaMemcpy(ctx->ds2, s2, sizeof(double) * N, cudaMemcpyHostToDevice));
   }
   const int Np = round_up(N, T);
-  if (Np != ctx->Np || D != ctx->D) free_bufs(ctx->ws);
+  if (Np != ctx->Np || D != ctx->D || N != ctx->N) free_bufs(ctx->ws);   // also re-zeroes the padding
   ctx->N = N;
   ctx->D = D;
   ctx->Np = Np;
@@ -337,7 +339,12 @@ static int alloc_bufs(gpb_ctx* ctx, Bufs& b, int cap, bool with_w, int Np, int D
   const size_t smat = (size_t)Np * Np;
   const size_t nt = b.Nt;
   CK(cudaMalloc(&b.Abuf, smat * 8 * cap));
-  if (with_w) CK(cudaMalloc(&b.Wbuf, smat * 8 * cap));
+  if (with_w) {
+    CK(cudaMalloc(&b.Wbuf, smat * 8 * cap));
+    // padded rows/columns of W are never written by the (padding-skipping) kernels: zero once
+    CK(cudaMemsetAsync(b.Wbuf, 0, smat * 8 * cap, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
   CK(cudaMalloc(&b.Dbuf, nt * T * T * 8 * cap));
   CK(cudaMalloc(&b.DTbuf, nt * T * T * 8 * cap));
   CK(cudaMalloc(&b.xs, (size_t)D * Np * 8 * cap));
@@ -387,7 +394,7 @@ static int ensure_ws(gpb_ctx* ctx, long long B, bool with_w) {
 // ---------------------------------------------------------------------------------
 // pipeline pieces (all asynchronous on ctx->stream)
 // ---------------------------------------------------------------------------------
-static BatchBufs batch_bufs(const Bufs& b, const int* sel) {
+static BatchBufs batch_bufs(const Bufs& b, const int* sel, long long N) {
   BatchBufs bb;
   bb.Abuf = b.Abuf;
   bb.Wbuf = b.Wbuf;
@@ -397,6 +404,7 @@ static BatchBufs batch_bufs(const Bufs& b, const int* sel) {
   bb.smat = b.smat();
   bb.Np = b.Np;
   bb.Nt = b.Nt;
+  bb.N = (int)N;
   return bb;
 }
 
@@ -456,7 +464,7 @@ static void run_prep_build(gpb_ctx* ctx, Bufs& b, const Model& md, long long N, 
 // substitution z = L^-1 (y - m) carried along.
 static void run_potrf(gpb_ctx* ctx, Bufs& b, long long N, const int* sel, int nsel, bool write_w,
                       bool with_rhs = true) {
-  const BatchBufs bb = batch_bufs(b, sel);
+  const BatchBufs bb = batch_bufs(b, sel, N);
   for (int k = 0; k < b.Nt; ++k) {
     DiagArgs da;
     da.Abuf = b.Abuf;
@@ -473,6 +481,7 @@ static void run_potrf(gpb_ctx* ctx, Bufs& b, long long N, const int* sel, int ns
     da.zvec = with_rhs ? b.zvec : nullptr;
     da.logdet = b.logdet;
     da.fail = b.fail;
+    da.dbg = (k == 0) ? ctx->diag_dbg : nullptr;
     diag_kernel<<<nsel, 256, DIAG_SMEM, ctx->stream>>>(da);
     LAUNCHED(ctx);
     const int n = b.Nt - k - 1;
@@ -523,8 +532,9 @@ static void run_bwd(gpb_ctx* ctx, Bufs& b, const int* sel, int nsel) {
 
 // W = L^-1 (lower tiles of Wbuf; dual: also W^T in the upper tiles); then optionally
 // Ainv = W^T W into the lower tiles of Abuf.
-static void run_inverse(gpb_ctx* ctx, Bufs& b, const int* sel, int nsel, bool dual, bool syrk2) {
-  const BatchBufs bb = batch_bufs(b, sel);
+static void run_inverse(gpb_ctx* ctx, Bufs& b, long long N, const int* sel, int nsel, bool dual,
+                        bool syrk2) {
+  const BatchBufs bb = batch_bufs(b, sel, N);
   const int Nt = b.Nt;
   if (Nt > 1) {
     launch_gemm(ctx, OpHpass{bb}, dim3((unsigned)(Nt * (Nt - 1) / 2), (unsigned)nsel));
@@ -675,7 +685,7 @@ static int nlz_batch_impl(gpb_ctx* ctx, const double* hyp, bool hyp_on_device, i
     if (want_grad) {
       run_bwd(ctx, b, b.sel, n);
       CK(cudaEventRecord(ctx->ev[3], ctx->stream));
-      run_inverse(ctx, b, b.sel, n, /*dual=*/true, /*syrk2=*/true);
+      run_inverse(ctx, b, ctx->N, b.sel, n, /*dual=*/true, /*syrk2=*/true);
       CK(cudaEventRecord(ctx->ev[4], ctx->stream));
       run_grad(ctx, b, md, ctx->N, b.sel, n);
     } else {
@@ -786,7 +796,7 @@ extern "C" int gpb_posterior_batch(gpb_ctx* ctx, const double* hyp, int64_t B, g
     e = cudaMemcpyAsync(b.sel2, low.data(), sizeof(int) * low.size(), cudaMemcpyHostToDevice,
                         ctx->stream);
     if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return bail(GPB_ECUDA); }
-    run_inverse(ctx, b, b.sel2, (int)low.size(), true, true);
+    run_inverse(ctx, b, ctx->N, b.sel2, (int)low.size(), true, true);
     for (int s : low) {
       symmetrize_kernel<<<grid1d(b.smat()), 256, 0, ctx->stream>>>(b.Abuf + s * b.smat(), b.Np);
       LAUNCHED(ctx);
@@ -864,7 +874,7 @@ static int ensure_w(gpb_ctx* ctx, gpb_post* post) {
     if (post->sp[s].lchol && !post->status[s]) high.push_back(s);
   if (!high.empty()) {
     CK(cudaMemcpyAsync(b.sel2, high.data(), sizeof(int) * high.size(), cudaMemcpyHostToDevice, ctx->stream));
-    run_inverse(ctx, b, b.sel2, (int)high.size(), false, false);
+    run_inverse(ctx, b, post->N, b.sel2, (int)high.size(), false, false);
     CK(cudaStreamSynchronize(ctx->stream));
   }
   post->w_ready = true;
@@ -965,6 +975,8 @@ static int predict_impl(gpb_ctx* ctx, const gpb_post* cpost, const double* Xs, c
       op.tri = p.lchol ? 1 : 0;
       op.Np = Np;
       op.ns = ctx->gemm_bn == 128 ? 1 : 2;
+      op.N = (int)post->N;
+      op.mc = mc;
       launch_gemm(ctx, op, dim3((unsigned)(Mcp / T), (unsigned)Nt));
       FinishArgs fa;
       fa.md = md;
@@ -1278,6 +1290,13 @@ extern "C" int gpb_debug_potrf(gpb_ctx* ctx, double* A, int n, int32_t* info) {
   if (e == cudaSuccess) e = cudaMemcpy(pad.data(), b.Abuf, sizeof(double) * pad.size(), cudaMemcpyDeviceToHost);
   int failh = 0;
   if (e == cudaSuccess) e = cudaMemcpy(&failh, b.fail, sizeof(int), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && ctx->diag_dbg) {
+    long long st[33];
+    cudaMemcpy(st, ctx->diag_dbg, sizeof st, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "diag_kernel phase cycles (n=%d):", n);
+    for (int i = 1; i < (int)st[0]; ++i) fprintf(stderr, " %lld", st[1 + i] - st[i]);
+    fprintf(stderr, "  total %lld\n", st[st[0]] - st[1]);
+  }
   free_bufs(b);
   if (e != cudaSuccess) FAIL(GPB_ECUDA, cudaGetErrorString(e));
   for (int c = 0; c < n; ++c)

@@ -28,6 +28,7 @@ struct DiagArgs {
   double* zvec;                    // [nslots][Np] z = L^-1 r
   double* logdet;                  // [nslots][Nt] partial sums of log L_ii
   int* fail;                       // [nslots]  set to 1 on a pivot <= 0 or NaN
+  long long* dbg;                  // optional: clock64() stamps of the phases (thread 0 of CTA 0)
 };
 
 __device__ __forceinline__ void dmma_t(double& d0, double& d1, double a, double b) {
@@ -40,11 +41,12 @@ __device__ __forceinline__ void dmma_t(double& d0, double& d1, double a, double 
 // --- 32x32 diagonal block in registers, one row per lane; every register index is a
 // compile-time constant (the steps are instantiated through a fold expression).
 template <int J>
-__device__ __forceinline__ void chol32_step(double (&arow)[SB], int lane, double* rsq_blk, int& failed) {
+__device__ __forceinline__ void chol32_step(double (&arow)[SB], int lane, double* rsq_blk, int& failed,
+                                            bool publish) {
   double piv = __shfl_sync(0xffffffffu, arow[J], J);
   if (!(piv > 0.0)) { failed = 1; piv = 1.0; }       // LAPACK dpotrf: ajj <= 0 or NaN -> info > 0
   const double rinv = rsqrt(piv);
-  if (lane == J) { arow[J] = piv * rinv; rsq_blk[J] = rinv; }
+  if (lane == J) { arow[J] = piv * rinv; if (publish) rsq_blk[J] = rinv; }
   else if (lane > J) arow[J] *= rinv;
 #pragma unroll
   for (int c = J + 1; c < SB; ++c) {
@@ -54,8 +56,8 @@ __device__ __forceinline__ void chol32_step(double (&arow)[SB], int lane, double
 }
 template <int... Js>
 __device__ __forceinline__ void chol32_all(double (&arow)[SB], int lane, double* rsq_blk, int& failed,
-                                           std::integer_sequence<int, Js...>) {
-  (chol32_step<Js>(arow, lane, rsq_blk, failed), ...);
+                                           bool publish, std::integer_sequence<int, Js...>) {
+  (chol32_step<Js>(arow, lane, rsq_blk, failed, publish), ...);
 }
 // lane c owns column c of Inv = L^-1: inv[q] = Inv(q, c)
 template <int RR>
@@ -96,6 +98,10 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
   double* lg = bsh + T;                         // log L_jj
   double* rsq = lg + T;                         // 1 / L_jj
   __shared__ int s_failed;
+  __shared__ long long stamps[32];
+  int nst = 0;
+#define STAMP() do { if (a.dbg && threadIdx.x == 0 && nst < 32) stamps[nst++] = clock64(); } while (0)
+  STAMP();
   const int slot = a.sel[blockIdx.x];
   const int k = a.k, Np = a.Np;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -118,23 +124,30 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
   }
   if (tid == 0) s_failed = 0;
   __syncthreads();
+  STAMP();
 
   for (int p = 0; p < T / SB; ++p) {
     const int c0 = p * SB;
     if (c0 >= nact) break;
     double* Ivp = Iv + p * SB * IVP;
-    // ---- 1. diagonal block in registers (warp 0): lane r owns row r
-    if (warp == 0) {
+    // ---- 1. diagonal block in registers: lane r owns row r.  Every warp runs the same
+    // factorisation redundantly (straight-line convergent code, no divergent region around
+    // the shuffles); only warp 0 publishes the results.
+    {
       double arow[SB];
 #pragma unroll
       for (int c = 0; c < SB; ++c) arow[c] = (c <= lane) ? S[(c0 + c) * DP_PITCH + c0 + lane] : 0.0;
       int failed = 0;
-      chol32_all(arow, lane, rsq + c0, failed, std::make_integer_sequence<int, SB>{});
-      if (failed && lane == 0) s_failed = 1;
+      const bool pub = (warp == 0);
+      chol32_all(arow, lane, rsq + c0, failed, pub, std::make_integer_sequence<int, SB>{});
+      if (failed && pub && lane == 0) s_failed = 1;
+      __syncthreads();                 // every warp has read the block; rsq[] is published
+      STAMP();
+      if (pub) {
 #pragma unroll
-      for (int c = 0; c < SB; ++c)
-        if (c <= lane) S[(c0 + c) * DP_PITCH + c0 + lane] = arow[c];
-      __syncwarp();
+        for (int c = 0; c < SB; ++c)
+          if (c <= lane) S[(c0 + c) * DP_PITCH + c0 + lane] = arow[c];
+      }
       // inverse of the 32x32 factor: lane c owns column c; inv[q] = Inv(q, c)
       double inv[SB];
       {
@@ -143,10 +156,13 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
         for (int q = 0; q < SB; ++q) inv[q] = (q == lane) ? dc : 0.0;
       }
       inv32_all(arow, inv, lane, rsq + c0, std::make_integer_sequence<int, SB>{});
+      if (pub) {
 #pragma unroll
-      for (int q = 0; q < SB; ++q) Ivp[lane * IVP + q] = inv[q];
+        for (int q = 0; q < SB; ++q) Ivp[lane * IVP + q] = inv[q];
+      }
     }
     __syncthreads();
+    STAMP();
     // ---- 2. panel: rows below the block, L21 = P * Inv^T   (C(m,n) = sum_k P(m,k) Inv(n,k))
     const int mblocks = max(0, (nact8 - c0 - SB) / 8);
     for (int mb = warp; mb < mblocks; mb += 8) {
@@ -169,6 +185,7 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
       }
     }
     __syncthreads();
+    STAMP();
     // ---- 3. trailing update of the lower 8x8 blocks: S -= L21 L21^T
     const int nblk = mblocks * (mblocks + 1) / 2;
     for (int idx = warp; idx < nblk; idx += 8) {
@@ -187,6 +204,7 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
       S[(q0 + 2 * tq + 1) * DP_PITCH + r0 + g] = c1v;
     }
     __syncthreads();
+    STAMP();
   }
 
   if (tid < T) lg[tid] = (tid < nact) ? log(S[tid * DP_PITCH + tid]) : 0.0;
@@ -203,6 +221,8 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
     if (s_failed) a.fail[slot] = 1;
   }
 
+  __syncthreads();
+  STAMP();
   // ---- D = L^-1, 32x32 blocks: D_jj = Inv_j ; D_ij = -Inv_i * sum_{kb=j}^{i-1} L_i,kb D_kb,j
   // D(R,C) for R in a later block than C is stored transposed at S[R*129 + C].
   for (int j = 0; j < T / SB; ++j) {
@@ -246,6 +266,7 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
     }
   }
   __syncthreads();
+  STAMP();
   // element (rr, c) of D, rr >= c
   auto Dval = [&](int rr, int c) -> double {
     if ((rr >> 5) == (c >> 5)) return Iv[(rr >> 5) * SB * IVP + (c & 31) * IVP + (rr & 31)];
@@ -272,6 +293,13 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
       for (int c = 0; c <= rr; ++c) s += Dval(rr, c) * bsh[c];
     a.zvec[(long long)slot * Np + k * T + rr] = s;
   }
+  __syncthreads();
+  STAMP();
+  if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) {
+    a.dbg[0] = nst;
+    for (int i = 0; i < nst; ++i) a.dbg[1 + i] = stamps[i];
+  }
+#undef STAMP
 }
 
 struct VecArgs {

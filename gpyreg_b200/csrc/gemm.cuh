@@ -30,6 +30,7 @@ struct GemmTile {
   const double* E; long long lde;     // reduce mode: rowsum[m] = sum_n C(m,n)*E(m,n) (E null: C^2)
   double* rowsum; long long rs_half;  // rs_half: offset between the two column halves
   int K;
+  int mvalid, nvalid;                 // rows / columns of the 128x128 tile that hold data (rest is padding)
   double alpha, cscale;               // result = alpha * (cscale * C + A B^T); cscale = beta / alpha
   bool valid;
 };
@@ -89,6 +90,11 @@ gemm_nt_kernel(const __grid_constant__ Op op) {
     if (t.E) t.E += off * t.lde;
     if (t.rowsum) t.rowsum += (long long)half * t.rs_half;
   }
+  // Padding: a CTA whose rows or columns are all padding has nothing to do; inside a CTA the
+  // warps whose 32 x WN sub-tile is all padding skip their loads, DMMAs and stores (the padded
+  // part of every operand is zero / identity, so the skipped results would be unchanged).
+  const int nv = t.nvalid - half * BN_;
+  if (!(MODE & GM_REDUCE) && (t.mvalid <= 0 || nv <= 0)) return;
 
   double* As = gsm;
   double* Bs = gsm + NSTAGE * BK * PITCH;
@@ -97,6 +103,7 @@ gemm_nt_kernel(const __grid_constant__ Op op) {
   const int g = lane >> 2, tq = lane & 3;
   const int wm = (warp & 3) * 32, wn = (warp >> 2) * WN;
   const int KT = t.K / BK;
+  const bool wact = (wm < t.mvalid) && (wn < nv);
 
   auto load_stage = [&](int kt, int stage) {
     const int k0 = kt * BK;
@@ -127,7 +134,7 @@ gemm_nt_kernel(const __grid_constant__ Op op) {
 
   // thread owns C(m = wm + mi*8 + g, n = wn + ni*8 + 2*tq + {0,1})
   double acc[4][NI][2];
-  if (MODE & GM_BETA) {
+  if ((MODE & GM_BETA) && wact) {
     // start from (beta/alpha) * C: the loads go straight into the accumulator registers and
     // overlap the pipeline fill, instead of a latency-bound read-modify-write epilogue
     const double f = t.cscale;
@@ -156,6 +163,7 @@ gemm_nt_kernel(const __grid_constant__ Op op) {
     }
     const double* as = As + (kt % NSTAGE) * BK * PITCH;
     const double* bs = Bs + (kt % NSTAGE) * BK * PB;
+    if (wact) {
 #pragma unroll
     for (int k4 = 0; k4 < BK / 4; ++k4) {
       double a[4], b[NI];
@@ -167,6 +175,7 @@ gemm_nt_kernel(const __grid_constant__ Op op) {
       for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
         for (int ni = 0; ni < NI; ++ni) dmma8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+    }
     }
   }
   cp_async_wait<0>();
@@ -197,6 +206,7 @@ gemm_nt_kernel(const __grid_constant__ Op op) {
     if (tid < BM) t.rowsum[tid] = red[tid] + red[BM + tid];
     return;
   }
+  if (!wact) return;
 #pragma unroll
   for (int mi = 0; mi < 4; ++mi) {
     const int m = wm + mi * 8 + g;
@@ -232,6 +242,8 @@ struct BatchBufs {
   const int* sel;
   long long smat;   // Np*Np
   int Np, Nt;
+  int N;            // rows that hold data; N16 = N rounded up to the K step
+  __device__ int n16() const { return (N + BK - 1) / BK * BK; }
 };
 
 __device__ __forceinline__ GemmTile empty_tile() {
@@ -245,6 +257,8 @@ __device__ __forceinline__ GemmTile empty_tile() {
   t.rowsum = nullptr;
   t.rs_half = 0;
   t.K = 0;
+  t.mvalid = BM;
+  t.nvalid = BN;
   t.alpha = 1.0;
   t.cscale = 0.0;
   t.valid = true;
@@ -283,6 +297,7 @@ struct OpPanel {
     t.B = b.Dbuf + ((long long)slot * b.Nt + k) * T * T; t.ldb = T;
     t.C = tile; t.ldc = b.Np;
     t.K = T;
+    t.mvalid = b.N - i * T;
     return t;
   }
 };
@@ -303,6 +318,8 @@ struct OpSyrk {
     t.B = base + (long long)j * T + (long long)k * T * b.Np; t.ldb = b.Np;
     t.C = base + (long long)i * T + (long long)j * T * b.Np; t.ldc = b.Np;
     t.K = T; t.alpha = -1.0; t.cscale = -1.0;
+    t.mvalid = b.N - i * T;
+    t.nvalid = b.N - j * T;
     return t;
   }
 };
@@ -342,7 +359,8 @@ struct OpWrec {
     t.B = H + (long long)j * T + (long long)(j + 1) * T * b.Np; t.ldb = b.Np;
     t.C = W + (long long)i * T + (long long)j * T * b.Np; t.ldc = b.Np;
     if (dual) { t.Ct = W + (long long)j * T + (long long)i * T * b.Np; t.ldct = b.Np; }
-    t.K = (i - j) * T; t.alpha = -1.0;
+    t.K = min((i - j) * T, b.n16() - (j + 1) * T); t.alpha = -1.0;
+    t.mvalid = b.N - i * T;
     return t;
   }
 };
@@ -365,7 +383,9 @@ struct OpSyrk2 {
     t.A0 = DTa; t.lda0 = T;
     if (a == c) { t.B0 = DTa; t.ldb0 = T; }
     t.C = b.Abuf + slot * b.smat + (long long)a * T + (long long)c * T * b.Np; t.ldc = b.Np;
-    t.K = (b.Nt - a) * T;
+    t.K = min((b.Nt - a) * T, b.n16() - a * T);
+    t.mvalid = b.N - a * T;
+    t.nvalid = b.N - c * T;
     return t;
   }
 };
@@ -380,12 +400,16 @@ struct OpPred {
   double* part;                       // [Nt*ns][Mcp]
   int Mcp; int tri;                   // tri = 1: Wm lower triangular -> K = (nt+1)*T
   int Np; int ns;                     // ns = column halves per tile (BN / BN_)
+  int N, mc;                          // training rows / test points that hold data
   __device__ GemmTile resolve(int bx, int by) const {
     GemmTile t = empty_tile();
     const int jt = bx, nt = (int)gridDim.y - 1 - by;   // longest K first
     t.A = Bt + (long long)jt * BM; t.lda = ldbt;
     t.B = Wm + (long long)nt * BN; t.ldb = ldw;
-    t.K = tri ? (nt + 1) * T : Np;
+    const int n16 = (N + BK - 1) / BK * BK;
+    t.K = tri ? min((nt + 1) * T, n16) : n16;
+    t.mvalid = mc - jt * BM;
+    t.nvalid = N - nt * BN;
     if (!tri) { t.E = Bt + (long long)jt * BM + (long long)nt * BN * ldbt; t.lde = ldbt; }
     t.rowsum = part + (long long)nt * ns * Mcp + (long long)jt * BM;
     t.rs_half = Mcp;

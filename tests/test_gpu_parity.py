@@ -219,3 +219,48 @@ def test_oracle_medium(eng, model):
         assert np.max(np.abs(mu - rmu)) <= TOL_PRED * (1 + np.max(np.abs(rmu)))
         assert np.max(np.abs(v - rv)) <= TOL_PRED * np.max(np.abs(rv))
     post.free()
+
+
+def test_large_rq_single_gp(eng):
+    """config 4 shape at a size the oracle finishes in seconds: one RationalQuadratic-ARD GP,
+    D=8, N not a multiple of the 128-tile (exercises the padding-aware tile kernels)."""
+    from bench import benign_hyp, synth_data
+    N, D = 2500, 8
+    spec = orc.ModelSpec(D=D, cov_kind=2, ard=True, mean_kind=1)
+    X, y = synth_data(N, D, seed=0)
+    hyp = benign_hyp(spec, 2, y, seed=1)
+    setup_engine(eng, spec, X, y, None)
+    nlz, dnlz, mult, status = eng.nlz_batch(hyp, want_grad=True)
+    ref_nlz, ref_dnlz = orc.nlz_batch(spec, hyp[:1], X, y, None, True)
+    assert not status.any() and np.all(mult == 1)
+    assert rel_err(nlz[:1], ref_nlz) <= TOL_NLZ
+    assert grad_err(dnlz[:1], ref_dnlz) <= TOL_GRAD
+    # size-independent property: nlZ is invariant under a permutation of the data rows
+    perm = np.random.default_rng(3).permutation(N)
+    setup_engine(eng, spec, X[perm], y[perm], None)
+    nlz_p, dnlz_p, _, _ = eng.nlz_batch(hyp, want_grad=True)
+    assert rel_err(nlz_p, nlz) <= 1e-11
+    assert grad_err(dnlz_p, dnlz) <= 1e-9
+
+
+@pytest.mark.parametrize("N", [1, 2, 127, 128, 129, 256])
+def test_tile_boundaries(eng, N):
+    """Sizes around the tile edge, including a single training point."""
+    rng = np.random.default_rng(N)
+    D = 2
+    X = rng.uniform(-2, 2, (N, D))
+    y = np.sin(X.sum(1)).reshape(-1, 1) + 0.05 * rng.standard_normal((N, 1))
+    spec = orc.ModelSpec(D=D, cov_kind=1, degree=3, ard=True, mean_kind=1)
+    hyp = np.array([[0.1, -0.2, 0.0, np.log(0.2), 0.1], [0.4, 0.3, 0.2, np.log(0.05), -0.1]])
+    setup_engine(eng, spec, X, y, None)
+    nlz, dnlz, mult, status = eng.nlz_batch(hyp, want_grad=True)
+    ref_nlz, ref_dnlz = orc.nlz_batch(spec, hyp, X, y, None, True)
+    assert rel_err(nlz, ref_nlz) <= TOL_NLZ and grad_err(dnlz, ref_dnlz) <= TOL_GRAD
+    post = eng.posterior_batch(hyp)
+    Xs = rng.uniform(-2, 2, (5, D))
+    mu, v = eng.predict(post, Xs, add_noise=True, separate=True)
+    rmu, rv = orc.predict(spec, orc.posterior_batch(spec, hyp, X, y, None), X, y, Xs, add_noise=True,
+                          separate_samples=True)
+    assert np.max(np.abs(mu - rmu)) <= TOL_PRED * (1 + np.max(np.abs(rmu)))
+    assert np.max(np.abs(v - rv)) <= TOL_PRED * np.max(np.abs(rv))
+    post.free()
