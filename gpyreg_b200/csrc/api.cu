@@ -46,6 +46,7 @@ struct gpb_ctx {
   double *dX = nullptr, *dy = nullptr, *ds2 = nullptr;
   size_t ws_limit = 0;
   int gemm_bn = 64;          // 64: two CTAs per SM (default); 128: one (env GPB_GEMM_BN)
+  int outer_block = 4;       // tile columns per outer block of the two-level Cholesky (env GPB_OUTER_BLOCK)
   long long* diag_dbg = nullptr;   // env GPB_DIAG_DBG: phase clock stamps of the diagonal kernel
   Bufs ws;
   double timings[6] = {0, 0, 0, 0, 0, 0};
@@ -180,6 +181,7 @@ extern "C" int gpb_create(int device, gpb_ctx** out) {
   }
   ctx->stream = ctx->own_stream;
   if (const char* bn = getenv("GPB_GEMM_BN")) ctx->gemm_bn = (atoi(bn) == 128) ? 128 : 64;
+  if (const char* ob = getenv("GPB_OUTER_BLOCK")) ctx->outer_block = std::max(1, atoi(ob));
   if (getenv("GPB_DIAG_DBG")) cudaMalloc(&ctx->diag_dbg, 40 * sizeof(long long));
   for (auto& ev : ctx->ev) cudaEventCreate(&ev);
   int rc = init_attrs(ctx);
@@ -465,7 +467,8 @@ static void run_prep_build(gpb_ctx* ctx, Bufs& b, const Model& md, long long N, 
 static void run_potrf(gpb_ctx* ctx, Bufs& b, long long N, const int* sel, int nsel, bool write_w,
                       bool with_rhs = true) {
   const BatchBufs bb = batch_bufs(b, sel, N);
-  for (int k = 0; k < b.Nt; ++k) {
+  const int Nt = b.Nt, OB = ctx->outer_block;          // outer block = OB tile columns
+  for (int k = 0; k < Nt; ++k) {
     DiagArgs da;
     da.Abuf = b.Abuf;
     da.Wbuf = write_w ? b.Wbuf : nullptr;
@@ -484,7 +487,7 @@ static void run_potrf(gpb_ctx* ctx, Bufs& b, long long N, const int* sel, int ns
     da.dbg = (k == 0) ? ctx->diag_dbg : nullptr;
     diag_kernel<<<nsel, 256, DIAG_SMEM, ctx->stream>>>(da);
     LAUNCHED(ctx);
-    const int n = b.Nt - k - 1;
+    const int n = Nt - k - 1;
     if (n <= 0) break;
     launch_gemm(ctx, OpPanel{bb, k}, dim3((unsigned)n, (unsigned)nsel), /*wide=*/true);
     if (with_rhs) {
@@ -503,7 +506,17 @@ static void run_potrf(gpb_ctx* ctx, Bufs& b, long long N, const int* sel, int ns
       fwd_update_kernel<<<dim3((unsigned)n, (unsigned)nsel), T, 0, ctx->stream>>>(va);
       LAUNCHED(ctx);
     }
-    launch_gemm(ctx, OpSyrk{bb, k}, dim3((unsigned)(n * (n + 1) / 2), (unsigned)nsel));
+    // two-level trailing update (see OpSyrk): inside the outer block only its own columns
+    const int ob0 = (k / OB) * OB;                     // first tile column of this outer block
+    const int obe = std::min(ob0 + OB, Nt);            // one past its last
+    if (k + 1 < obe) {
+      const int cnt = OpSyrk::count(Nt, k + 1, obe);
+      launch_gemm(ctx, OpSyrk{bb, k, 1, k + 1, obe}, dim3((unsigned)cnt, (unsigned)nsel));
+    }
+    if (k + 1 == obe && obe < Nt) {                    // outer block done: update the rest, long K
+      const int cnt = OpSyrk::count(Nt, obe, Nt);
+      launch_gemm(ctx, OpSyrk{bb, ob0, obe - ob0, obe, Nt}, dim3((unsigned)cnt, (unsigned)nsel));
+    }
   }
 }
 

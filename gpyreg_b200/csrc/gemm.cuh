@@ -302,22 +302,31 @@ struct OpPanel {
   }
 };
 
-// potrf trailing update, step k:  A_ij -= L_ik L_jk^T  (i >= j > k)
+// potrf trailing update:  A_ij -= sum_{k in [k0, k0+kw)} L_ik L_jk^T  for tile columns
+// j in [jlo, jhi), rows i >= j.  Two-level blocking: inside an outer block of `kw` tile columns
+// the update is restricted to that block's columns (K = 128 per step); once the outer block is
+// factored, ONE update with K = kw*128 brings the rest of the matrix up to date, so most of the
+// flops run with a long K loop and each C tile is read and written once per outer block.
 struct OpSyrk {
   static constexpr bool SLOT_MAJOR = false;
   static constexpr int MODE = GM_BETA | GM_STORE;
-  BatchBufs b; int k;
+  BatchBufs b; int k0, kw, jlo, jhi;
+  // tile enumeration: column-major over the trapezoid {(i,j): jlo <= j < jhi, j <= i < Nt}
+  __host__ __device__ static int count(int Nt, int jlo, int jhi) {
+    const int nc = jhi - jlo;
+    return nc * (Nt - jlo) - nc * (nc - 1) / 2;
+  }
   __device__ GemmTile resolve(int bx, int by) const {
     GemmTile t = empty_tile();
     const int slot = b.sel[by];
-    int a, c;
-    tri_decode(bx, a, c);
-    const int i = k + 1 + a, j = k + 1 + c;
+    int j = jlo, rem = bx;
+    while (rem >= b.Nt - j) { rem -= b.Nt - j; ++j; }      // at most jhi-jlo steps
+    const int i = j + rem;
     double* base = b.Abuf + slot * b.smat;
-    t.A = base + (long long)i * T + (long long)k * T * b.Np; t.lda = b.Np;
-    t.B = base + (long long)j * T + (long long)k * T * b.Np; t.ldb = b.Np;
+    t.A = base + (long long)i * T + (long long)k0 * T * b.Np; t.lda = b.Np;
+    t.B = base + (long long)j * T + (long long)k0 * T * b.Np; t.ldb = b.Np;
     t.C = base + (long long)i * T + (long long)j * T * b.Np; t.ldc = b.Np;
-    t.K = T; t.alpha = -1.0; t.cscale = -1.0;
+    t.K = kw * T; t.alpha = -1.0; t.cscale = -1.0;
     t.mvalid = b.N - i * T;
     t.nvalid = b.N - j * T;
     return t;
