@@ -12,7 +12,7 @@
 
 namespace gpb {
 
-constexpr int DP_PITCH = T + 1;                                   // 129
+constexpr int DP_PITCH = T + 4;                                   // 132: 16-byte rows, conflict-free DMMA fragments
 constexpr int SB = 32;                                            // sub-block of the tile factorisation
 constexpr int IVP = 36;                                           // pitch of the 32x32 scratch blocks
 constexpr size_t DIAG_SMEM =
@@ -45,14 +45,20 @@ __device__ __forceinline__ void chol32_step(double (&arow)[SB], int lane, double
                                             bool publish) {
   double piv = __shfl_sync(0xffffffffu, arow[J], J);
   if (!(piv > 0.0)) { failed = 1; piv = 1.0; }       // LAPACK dpotrf: ajj <= 0 or NaN -> info > 0
+  // branch-free: on lane J arow[J] IS the pivot, so one predicated multiply gives
+  // L_JJ = piv * rsqrt(piv) there and L_rJ = a_rJ * rsqrt(piv) below it (a divergent
+  // if/else here makes the compiler clone the rsqrt sequence into every branch)
   const double rinv = rsqrt(piv);
-  if (lane == J) { arow[J] = piv * rinv; if (publish) rsq_blk[J] = rinv; }
-  else if (lane > J) arow[J] *= rinv;
+  const double scaled = ((lane == J) ? piv : arow[J]) * rinv;
+  arow[J] = (lane >= J) ? scaled : arow[J];
+  // all broadcasts first, then the rank-1 update: the shuffles pipeline instead of each FMA
+  // waiting for its own shuffle
+  double l[SB];
 #pragma unroll
-  for (int c = J + 1; c < SB; ++c) {
-    const double lcj = __shfl_sync(0xffffffffu, arow[J], c);
-    if (lane >= c) arow[c] -= arow[J] * lcj;
-  }
+  for (int c = J + 1; c < SB; ++c) l[c] = __shfl_sync(0xffffffffu, arow[J], c);
+#pragma unroll
+  for (int c = J + 1; c < SB; ++c)
+    if (lane >= c) arow[c] -= arow[J] * l[c];
 }
 template <int... Js>
 __device__ __forceinline__ void chol32_all(double (&arow)[SB], int lane, double* rsq_blk, int& failed,
@@ -64,12 +70,19 @@ template <int RR>
 __device__ __forceinline__ void inv32_step(const double (&arow)[SB], double (&inv)[SB], int lane,
                                            const double* rsq_blk) {
   if (RR == 0) return;
-  double s0 = 0.0, s1 = 0.0;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  double lr[SB];
+#pragma unroll
+  for (int q = 0; q < RR; ++q) lr[q] = __shfl_sync(0xffffffffu, arow[q], RR);   // L(RR, q) from lane RR
 #pragma unroll
   for (int q = 0; q < RR; ++q) {
-    const double lrq = __shfl_sync(0xffffffffu, arow[q], RR);     // L(RR, q), held by lane RR
-    if (q & 1) s1 += lrq * inv[q]; else s0 += lrq * inv[q];
+    if ((q & 3) == 0) s0 += lr[q] * inv[q];
+    else if ((q & 3) == 1) s1 += lr[q] * inv[q];
+    else if ((q & 3) == 2) s2 += lr[q] * inv[q];
+    else s3 += lr[q] * inv[q];
   }
+  s0 += s2;
+  s1 += s3;
   const double drr = rsq_blk[RR];
   if (lane < RR) inv[RR] = -(s0 + s1) * drr;
 }
@@ -80,7 +93,7 @@ __device__ __forceinline__ void inv32_all(const double (&arow)[SB], double (&inv
 }
 
 // One CTA factors a 128x128 diagonal tile and inverts the factor.
-//   S(r,c) lives at S[c*129 + r] (column-major, conflict-free along r).
+//   S(r,c) lives at S[c*132 + r] (column-major, conflict-free along r, 16-byte aligned columns).
 //   The tile is processed in four 32-wide block columns.  Per block column:
 //     1. warp 0 holds the 32x32 diagonal block one row per lane IN REGISTERS, runs the
 //        right-looking Cholesky with warp shuffles (pivot check like LAPACK dpotrf: a pivot
@@ -90,7 +103,7 @@ __device__ __forceinline__ void inv32_all(const double (&arow)[SB], double (&inv
 //   Then D = L^-1 is assembled block by block (D_ij = -Inv_i * sum_k L_ik D_kj, DMMA); the
 //   off-diagonal blocks of D are kept transposed in the unused upper triangle of S.
 __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
-  extern __shared__ double dsm[];
+  extern __shared__ __align__(16) double dsm[];
   double* S = dsm;                              // [T][129]
   double* Iv = S + T * DP_PITCH;                // [4][32][36]  Inv_p(r,c) at Iv[p][c*36 + r]
   double* Tm = Iv + 4 * SB * IVP;               // [32][36] scratch, T(m,n) at Tm[n*36 + m]
@@ -110,10 +123,14 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
   const int nact = min(T, a.N - k * T);         // rows/cols holding data (the rest is identity)
   const int nact8 = (nact + 7) & ~7;
 
-  for (int e = tid; e < T * T; e += 256) {
-    const int r = e & (T - 1), c = e >> 7;
-    S[c * DP_PITCH + r] = (r >= c) ? A[(long long)c * Np + r] : 0.0;
+  // whole tile with 16-byte async copies (all in flight at once); the strict upper triangle
+  // holds the symmetric counterpart, which nothing reads before it is overwritten
+  for (int e = tid; e < T * T / 2; e += 256) {
+    const int r2 = (e & 63) * 2, c = e >> 6;
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(S + c * DP_PITCH + r2);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(A + (long long)c * Np + r2));
   }
+  asm volatile("cp.async.commit_group;\n" ::);
   for (int e = tid; e < 4 * SB * IVP; e += 256) {     // diagonal-block inverses start as identity
     const int within = e % (SB * IVP);
     Iv[e] = (within / IVP == within % IVP) ? 1.0 : 0.0;
@@ -123,6 +140,7 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
     rsq[tid] = 1.0;
   }
   if (tid == 0) s_failed = 0;
+  asm volatile("cp.async.wait_group 0;\n" ::);
   __syncthreads();
   STAMP();
 
@@ -130,10 +148,9 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
     const int c0 = p * SB;
     if (c0 >= nact) break;
     double* Ivp = Iv + p * SB * IVP;
-    // ---- 1. diagonal block in registers: lane r owns row r.  Every warp runs the same
-    // factorisation redundantly (straight-line convergent code, no divergent region around
-    // the shuffles); only warp 0 publishes the results.
-    {
+    // ---- 1. diagonal block in registers (warp 0 only: the SM's shuffle unit is shared, so
+    // redundant copies in the other warps would slow this one down): lane r owns row r
+    if (warp == 0) {
       double arow[SB];
 #pragma unroll
       for (int c = 0; c < SB; ++c) arow[c] = (c <= lane) ? S[(c0 + c) * DP_PITCH + c0 + lane] : 0.0;
@@ -141,7 +158,13 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
       const bool pub = (warp == 0);
       chol32_all(arow, lane, rsq + c0, failed, pub, std::make_integer_sequence<int, SB>{});
       if (failed && pub && lane == 0) s_failed = 1;
-      __syncthreads();                 // every warp has read the block; rsq[] is published
+      {                                // 1 / L_rr of the lane's own row (select chain: static indices)
+        double dl = 1.0;
+#pragma unroll
+        for (int c = 0; c < SB; ++c) dl = (c == lane) ? arow[c] : dl;
+        rsq[c0 + lane] = 1.0 / dl;
+      }
+      __syncwarp();                    // rsq[] is published
       STAMP();
       if (pub) {
 #pragma unroll
@@ -172,11 +195,14 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
       for (int k4 = 0; k4 < 8; ++k4) af[k4] = S[(c0 + k4 * 4 + tq) * DP_PITCH + m0 + g];
       double acc[4][2];
 #pragma unroll
-      for (int n8 = 0; n8 < 4; ++n8) {
-        acc[n8][0] = acc[n8][1] = 0.0;
+      for (int n8 = 0; n8 < 4; ++n8) acc[n8][0] = acc[n8][1] = 0.0;
 #pragma unroll
-        for (int k4 = 0; k4 < 8; ++k4)
-          dmma_t(acc[n8][0], acc[n8][1], af[k4], Ivp[(k4 * 4 + tq) * IVP + n8 * 8 + g]);
+      for (int k4 = 0; k4 < 8; ++k4) {
+        double bf[4];
+#pragma unroll
+        for (int n8 = 0; n8 < 4; ++n8) bf[n8] = Ivp[(k4 * 4 + tq) * IVP + n8 * 8 + g];
+#pragma unroll
+        for (int n8 = 0; n8 < 4; ++n8) dmma_t(acc[n8][0], acc[n8][1], af[k4], bf[n8]);   // 4 chains
       }
 #pragma unroll
       for (int n8 = 0; n8 < 4; ++n8) {
@@ -188,20 +214,36 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
     STAMP();
     // ---- 3. trailing update of the lower 8x8 blocks: S -= L21 L21^T
     const int nblk = mblocks * (mblocks + 1) / 2;
-    for (int idx = warp; idx < nblk; idx += 8) {
-      int bi, bj;
+    for (int idx = warp; idx < nblk; idx += 16) {         // two 8x8 blocks per pass, interleaved chains
+      const int idx2 = idx + 8;
+      const bool two = idx2 < nblk;
+      int bi, bj, bi2 = 0, bj2 = 0;
       tri_decode(idx, bi, bj);
+      if (two) tri_decode(idx2, bi2, bj2);
       const int r0 = c0 + SB + bi * 8, q0 = c0 + SB + bj * 8;
-      double c0v = S[(q0 + 2 * tq) * DP_PITCH + r0 + g];
-      double c1v = S[(q0 + 2 * tq + 1) * DP_PITCH + r0 + g];
+      const int r1 = c0 + SB + bi2 * 8, q1 = c0 + SB + bj2 * 8;
+      double av0[8], bv0[8], av1[8], bv1[8];
 #pragma unroll
       for (int k4 = 0; k4 < 8; ++k4) {
-        const double av = -S[(c0 + k4 * 4 + tq) * DP_PITCH + r0 + g];
-        const double bv = S[(c0 + k4 * 4 + tq) * DP_PITCH + q0 + g];
-        dmma_t(c0v, c1v, av, bv);
+        const int col = (c0 + k4 * 4 + tq) * DP_PITCH;
+        av0[k4] = -S[col + r0 + g];
+        bv0[k4] = S[col + q0 + g];
+        av1[k4] = -S[col + r1 + g];
+        bv1[k4] = S[col + q1 + g];
       }
-      S[(q0 + 2 * tq) * DP_PITCH + r0 + g] = c0v;
-      S[(q0 + 2 * tq + 1) * DP_PITCH + r0 + g] = c1v;
+      double x0 = S[(q0 + 2 * tq) * DP_PITCH + r0 + g], x1 = S[(q0 + 2 * tq + 1) * DP_PITCH + r0 + g];
+      double y0 = S[(q1 + 2 * tq) * DP_PITCH + r1 + g], y1 = S[(q1 + 2 * tq + 1) * DP_PITCH + r1 + g];
+#pragma unroll
+      for (int k4 = 0; k4 < 8; ++k4) {
+        dmma_t(x0, x1, av0[k4], bv0[k4]);
+        dmma_t(y0, y1, av1[k4], bv1[k4]);
+      }
+      S[(q0 + 2 * tq) * DP_PITCH + r0 + g] = x0;
+      S[(q0 + 2 * tq + 1) * DP_PITCH + r0 + g] = x1;
+      if (two) {
+        S[(q1 + 2 * tq) * DP_PITCH + r1 + g] = y0;
+        S[(q1 + 2 * tq + 1) * DP_PITCH + r1 + g] = y1;
+      }
     }
     __syncthreads();
     STAMP();
@@ -229,38 +271,56 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
     if (j * SB >= nact) break;
     for (int i = j + 1; i < T / SB; ++i) {
       if (i * SB >= nact) break;
-      // pass A: Tm = sum_kb L_i,kb * D_kb,j     (16 output 8x8 blocks, two per warp)
-      for (int blk = warp; blk < 16; blk += 8) {
-        const int mi = blk >> 2, ni = blk & 3;
-        double t0 = 0.0, t1 = 0.0;
+      // pass A: Tm = sum_kb L_i,kb * D_kb,j.  16 output 8x8 blocks: warp w owns (mi, ni) =
+      // (w>>2, w&3) and (w>>2 + 2, w&3): same B fragments, two interleaved DMMA chains.
+      {
+        const int mi = warp >> 2, ni = warp & 3;
+        double t0 = 0.0, t1 = 0.0, u0 = 0.0, u1 = 0.0;
         for (int kb = j; kb < i; ++kb) {
+          double a0[8], a1[8], bb[8];
 #pragma unroll
           for (int k4 = 0; k4 < 8; ++k4) {
             const int q = k4 * 4 + tq;
-            const double av = S[(kb * SB + q) * DP_PITCH + i * SB + mi * 8 + g];
-            const double bv = (kb == j) ? Iv[j * SB * IVP + (ni * 8 + g) * IVP + q]
-                                        : S[(kb * SB + q) * DP_PITCH + j * SB + ni * 8 + g];
-            dmma_t(t0, t1, av, bv);
+            a0[k4] = S[(kb * SB + q) * DP_PITCH + i * SB + mi * 8 + g];
+            a1[k4] = S[(kb * SB + q) * DP_PITCH + i * SB + (mi + 2) * 8 + g];
+            bb[k4] = (kb == j) ? Iv[j * SB * IVP + (ni * 8 + g) * IVP + q]
+                               : S[(kb * SB + q) * DP_PITCH + j * SB + ni * 8 + g];
+          }
+#pragma unroll
+          for (int k4 = 0; k4 < 8; ++k4) {
+            dmma_t(t0, t1, a0[k4], bb[k4]);
+            dmma_t(u0, u1, a1[k4], bb[k4]);
           }
         }
         Tm[(ni * 8 + 2 * tq) * IVP + mi * 8 + g] = t0;
         Tm[(ni * 8 + 2 * tq + 1) * IVP + mi * 8 + g] = t1;
+        Tm[(ni * 8 + 2 * tq) * IVP + (mi + 2) * 8 + g] = u0;
+        Tm[(ni * 8 + 2 * tq + 1) * IVP + (mi + 2) * 8 + g] = u1;
       }
       __syncthreads();
       // pass B: D_ij = -Inv_i * Tm
-      for (int blk = warp; blk < 16; blk += 8) {
-        const int mi = blk >> 2, ni = blk & 3;
-        double d0 = 0.0, d1 = 0.0;
+      {
+        const int mi = warp >> 2, ni = warp & 3;
+        double a0[8], a1[8], bb[8];
 #pragma unroll
         for (int k4 = 0; k4 < 8; ++k4) {
           const int q = k4 * 4 + tq;
-          const double av = -Iv[i * SB * IVP + q * IVP + mi * 8 + g];
-          const double bv = Tm[(ni * 8 + g) * IVP + q];
-          dmma_t(d0, d1, av, bv);
+          a0[k4] = -Iv[i * SB * IVP + q * IVP + mi * 8 + g];
+          a1[k4] = -Iv[i * SB * IVP + q * IVP + (mi + 2) * 8 + g];
+          bb[k4] = Tm[(ni * 8 + g) * IVP + q];
         }
-        const int R = i * SB + mi * 8 + g, C = j * SB + ni * 8 + 2 * tq;
-        S[R * DP_PITCH + C] = d0;
-        S[R * DP_PITCH + C + 1] = d1;
+        double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) {
+          dmma_t(d0, d1, a0[k4], bb[k4]);
+          dmma_t(e0, e1, a1[k4], bb[k4]);
+        }
+        const int C = j * SB + ni * 8 + 2 * tq;
+        const int R0 = i * SB + mi * 8 + g, R1 = i * SB + (mi + 2) * 8 + g;
+        S[R0 * DP_PITCH + C] = d0;
+        S[R0 * DP_PITCH + C + 1] = d1;
+        S[R1 * DP_PITCH + C] = e0;
+        S[R1 * DP_PITCH + C + 1] = e1;
       }
       __syncthreads();
     }
