@@ -22,10 +22,23 @@ import scipy.optimize
 import scipy.special
 import scipy.stats
 
+from .batched_drivers import MultiChainSliceSampler, minimize_lockstep
 from .engine import Engine
 from .f_min_fill import (f_min_fill, smoothbox_cdf, smoothbox_student_t_cdf)
 from .slice_sample import SliceSampler
 from .spec import ModelSpec
+
+
+def _scipy_at_least(major, minor):
+    try:
+        parts = sp.__version__.split(".")
+        return (int(parts[0]), int(parts[1])) >= (major, minor)
+    except (ValueError, IndexError):
+        return False
+
+
+# SciPy >= 1.15 ships L-BFGS-B as re-entrant C (the older Fortran kept state in SAVE variables)
+_SCIPY_LBFGSB_REENTRANT = _scipy_at_least(1, 15)
 
 
 class Posterior:
@@ -602,6 +615,9 @@ class GP:
         burn_in = options.get("burn", thin * s_N)
         lower_bounds = options.get("lower_bounds", "current")
         upper_bounds = options.get("upper_bounds", "current")
+        # extra, optional keys (defaults reproduce the reference's sequential drivers):
+        n_chains = int(options.get("n_chains", 1))           # slice-sampling chains in lock step
+        lockstep_opt = options.get("lockstep_opt", _SCIPY_LBFGSB_REENTRANT)   # batch the L-BFGS-B runs
 
         X, y, s2 = self._convert_shapes(X, y, s2)
         if X is not None:
@@ -680,12 +696,21 @@ class GP:
         nll = np.full((np.maximum(opts_N, 1),), np.inf)
         results = []
         opts_N = np.minimum(opts_N, hyp.shape[0])
-        for i in range(opts_N):
-            res = sp.optimize.minimize(fun=opt_objective, x0=hyp[i, :], jac=True,
-                                       bounds=list(zip(LB, UB)), tol=tol)
-            results.append(res)
-            hyp[i, :] = res.x
-            nll[i] = res.fun
+        if lockstep_opt and opts_N > 1:
+            # the opts_N runs are independent: advance them together, one batched nlZ+gradient
+            # evaluation per round (same iterates as running them one after another)
+            results = minimize_lockstep(lambda H: self._nlz_batch(H, True, use_prior), hyp[:opts_N, :],
+                                        list(zip(LB, UB)), tol)
+            for i, res in enumerate(results):
+                hyp[i, :] = res.x
+                nll[i] = res.fun
+        else:
+            for i in range(opts_N):
+                res = sp.optimize.minimize(fun=opt_objective, x0=hyp[i, :], jac=True,
+                                           bounds=list(zip(LB, UB)), tol=tol)
+                results.append(res)
+                hyp[i, :] = res.x
+                nll[i] = res.fun
         if opts_N > 0:
             optimize_result = results[np.argmin(nll)]
             hyp_start = hyp[np.argmin(nll), :].copy()
@@ -700,6 +725,16 @@ class GP:
         if sampler_name != "slicesample":
             raise ValueError("Unknown sampler!")
         widths = widths_default if widths is None else np.minimum(widths, widths_default)
+        if n_chains > 1:
+            # K independent chains from the optimum, advanced in lock step (batch of K per round)
+            per_chain = -(-s_N // n_chains)
+            mc = MultiChainSliceSampler(lambda H: -self._nlz_batch(H, False, use_prior), hyp_start, widths,
+                                        LB, UB, n_chains)
+            sampling_result = mc.sample(per_chain * thin, burn=burn_in)
+            kept = sampling_result["samples"][:, thin - 1::thin, :]            # (K, per_chain, P)
+            hyp = np.transpose(kept, (1, 0, 2)).reshape(-1, kept.shape[2])[:s_N]
+            self.update(hyp=hyp)
+            return hyp, optimize_result, sampling_result
         slicer = SliceSampler(lambda h: self.__gp_obj_fun(h, False, True), hyp_start, widths, LB, UB,
                               {"display": "off", "diagnostics": False})
         sampling_result = slicer.sample(s_N * thin, burn=burn_in)

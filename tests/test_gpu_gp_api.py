@@ -168,3 +168,43 @@ def test_plugin_errors_match_reference_messages():
     assert np.isscalar(sn2) and sn2 == pytest.approx(np.exp(1.0))
     m, dm = ZeroMean().compute(np.zeros(0), X, compute_grad=True)
     assert dm == [] and m.shape == (4,)
+
+
+def test_fit_multichain_and_lockstep(capsys):
+    """Batched drivers: lock-step L-BFGS-B gives the same optimum as the
+    sequential runs; 4 slice-sampling chains in lock step sample the same posterior."""
+    import time
+    gold = _load("fit.npz")
+    c = case(gold, "ex2")
+    X, y = c["X"], c["y"]
+
+    def make():
+        gp = g.GP(2, SquaredExponential(), ConstantMean(), GaussianNoise(constant_add=True))
+        gp.set_priors({"covariance_log_outputscale": ("student_t", (0, np.log(10), 3)),
+                       "covariance_log_lengthscale": ("gaussian", (np.log(np.std(X, ddof=1)), np.log(10))),
+                       "noise_log_scale": ("gaussian", (np.log(1e-3), 1.0)),
+                       "mean_const": ("smoothbox", (np.min(y), np.max(y), 1.0))})
+        return gp
+    np.random.seed(0)
+    gp_seq = make()
+    t0 = time.perf_counter()
+    hyp_seq, opt_seq, _ = gp_seq.fit(X=X, y=y, options={"n_samples": 10, "lockstep_opt": False})
+    t_seq = time.perf_counter() - t0
+    np.random.seed(0)
+    gp_lock = make()
+    hyp_lock, opt_lock, _ = gp_lock.fit(X=X, y=y, options={"n_samples": 10, "lockstep_opt": True})
+    np.testing.assert_array_equal(opt_lock.x, opt_seq.x)      # identical iterates
+    np.testing.assert_array_equal(hyp_lock, hyp_seq)
+    np.random.seed(0)
+    gp_mc = make()
+    t0 = time.perf_counter()
+    hyp_mc, _, res = gp_mc.fit(X=X, y=y, options={"n_samples": 40, "n_chains": 4})
+    t_mc = time.perf_counter() - t0
+    assert hyp_mc.shape == (40, 5) and gp_mc.posteriors.size == 40
+    lp_mc = np.array([gp_mc.log_posterior(h) for h in hyp_mc])
+    assert abs(lp_mc.mean() - c["lpost"].mean()) < 2.5
+    fmu, fs2 = gp_mc.predict(c["xs"], add_noise=True)
+    assert np.max(np.abs(fmu - c["fmu"])) <= 0.35 * (1 + np.max(np.abs(c["fmu"])))
+    with capsys.disabled():
+        print(f"\n[fit ex2] sequential fit {t_seq:.2f} s; 4-chain fit (40 samples) {t_mc:.2f} s, "
+              f"{res['func_count']} evals in {res['rounds']} rounds")
