@@ -34,6 +34,8 @@ SYMBOLS = {
     "gpb_predict": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_int,
                               _vp, _vp, _vp]),
     "gpb_predict_dev": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int, C.c_int, _vp, _vp]),
+    "gpb_predict_full": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int, _vp, _vp]),
+    "gpb_quad": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, C.c_int, C.c_int, _vp, _vp]),
     "gpb_cov": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int64, C.c_int, _vp,
                           C.c_int64, C.c_int, _vp, _vp]),
     "gpb_mean": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int64, C.c_int, _vp, _vp]),

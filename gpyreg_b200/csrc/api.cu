@@ -83,6 +83,17 @@ static std::string g_create_err;
     }                                                                                  \
   } while (0)
 
+// like CK, for functions that own temporaries released by a local `cleanup` lambda
+#define CKC(call)                                   \
+  do {                                              \
+    cudaError_t e_ = (call);                        \
+    if (e_ != cudaSuccess) {                        \
+      ctx->err = cudaGetErrorString(e_);            \
+      cleanup();                                    \
+      return GPB_ECUDA;                             \
+    }                                               \
+  } while (0)
+
 #define FAIL(code, msg) \
   do {                  \
     ctx->err = (msg);   \
@@ -140,6 +151,7 @@ static cudaError_t kind_attrs() {
 
 static int init_attrs(gpb_ctx* ctx) {
   CK(gemm_attr<OpGeneric>());
+  CK(gemm_attr<OpPlain>());
   CK(gemm_attr<OpPanel>());
   CK(gemm_attr<OpSyrk>());
   CK(gemm_attr<OpHpass>());
@@ -1064,8 +1076,254 @@ extern "C" int gpb_predict_dev(gpb_ctx* ctx, const gpb_post* post, const double*
 }
 
 // ---------------------------------------------------------------------------------
+// Bayesian quadrature (GP.quad)
+// ---------------------------------------------------------------------------------
+extern "C" int gpb_quad(gpb_ctx* ctx, const gpb_post* cpost, const double* mu, const double* sigma,
+                        int64_t M, int compute_var, int separate, double* F, double* F_var) {
+  if (!ctx || !cpost) return GPB_EINVAL;
+  gpb_post* post = const_cast<gpb_post*>(cpost);
+  if (!mu || !sigma || !F || M <= 0 || (compute_var && !F_var)) FAIL(GPB_EINVAL, "gpb_quad: bad arguments");
+  const Model md = post->md;
+  if (md.cov_kind != GPB_COV_SE || !md.ard)
+    FAIL(GPB_EINVAL, "Bayesian quadrature only supports the squared exponential kernel.");
+  if (md.nz0 != 1) FAIL(GPB_EINVAL, "gpb_quad: needs the constant noise term (hyp[cov_N] = log sigma)");
+  CK(cudaSetDevice(ctx->device));
+  for (int st : post->status)
+    if (st) FAIL(GPB_ESTATE, "gpb_quad: a posterior sample has no valid factorisation");
+  int rc = compute_var ? ensure_w(ctx, post) : GPB_OK;
+  if (rc != GPB_OK) return rc;
+  const Bufs& b = post->b;
+  const int Ns = b.cap, D = md.D, Np = b.Np, Nt = b.Nt;
+  const int Mc = (int)std::min<int64_t>(M, 8192);
+  const int McpMax = round_up(Mc, T);
+  const int ns = ctx->gemm_bn == 128 ? 1 : 2;
+  if ((rc = grow(ctx, &ctx->pXs, &ctx->pXs_n, (size_t)3 * McpMax * std::max(D, 1))) != GPB_OK) return rc;
+  if ((rc = grow(ctx, &ctx->pBt, &ctx->pBt_n, (size_t)McpMax * Np)) != GPB_OK) return rc;
+  if ((rc = grow(ctx, &ctx->pmu, &ctx->ppart_n, (size_t)3 * Nt * McpMax)) != GPB_OK) return rc;
+  if ((rc = grow(ctx, &ctx->psamp, &ctx->psamp_n, (size_t)4 * Ns * McpMax)) != GPB_OK) return rc;
+  if ((rc = grow(ctx, &ctx->pout, &ctx->pout_n, (size_t)3 * McpMax * (separate ? Ns : 1))) != GPB_OK) return rc;
+  double* dmu = ctx->pXs;
+  double* dsg = ctx->pXs + (size_t)McpMax * D;
+  double* mupart = ctx->pmu;
+  double* vpart = ctx->pmu + (size_t)Nt * McpMax;
+  const size_t smem = ((size_t)3 * D * T + 2 * T + 8 * T) * 8;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CK(cudaFuncSetAttribute(quad_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (3 * MAXD * T + 10 * T) * 8));
+    attr_done = true;
+  }
+  for (int64_t c0 = 0; c0 < M; c0 += Mc) {
+    const int mc = (int)std::min<int64_t>(Mc, M - c0);
+    const int Mcp = round_up(mc, T);
+    CK(cudaMemcpyAsync(dmu, mu + c0 * D, sizeof(double) * mc * D, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dsg, sigma + c0 * D, sizeof(double) * mc * D, cudaMemcpyHostToDevice, ctx->stream));
+    double* F_s = ctx->psamp;
+    double* V_s = F_s + (size_t)Ns * Mcp;
+    for (int s = 0; s < Ns; ++s) {
+      const SlotP& p = post->sp[s];
+      const double* hyp_s = b.hyp + (size_t)s * md.P;
+      const double sn2_eff = exp(2 * post->hyp[(size_t)s * md.P + md.cov_n]) * p.mult;   // :1919-1920
+      QuadArgs qa;
+      qa.md = md;
+      qa.N = (int)post->N;
+      qa.Np = Np;
+      qa.Nt = Nt;
+      qa.mc = mc;
+      qa.Mcp = Mcp;
+      qa.mu = dmu;
+      qa.sigma = dsg;
+      qa.X = ctx->dX;
+      qa.hyp = hyp_s;
+      qa.alpha = b.alpha + (size_t)s * Np;
+      qa.scale = p.lchol ? 1.0 / sqrt(sn2_eff) : 1.0;
+      qa.Bt = ctx->pBt;
+      qa.mupart = mupart;
+      quad_build_kernel<<<dim3((unsigned)(Mcp / T), (unsigned)Nt), 256, smem, ctx->stream>>>(qa);
+      LAUNCHED(ctx);
+      if (compute_var) {
+        OpPred op;
+        op.Bt = ctx->pBt;
+        op.ldbt = Mcp;
+        op.Wm = p.lchol ? b.Wbuf + (size_t)s * b.smat() : b.Abuf + (size_t)s * b.smat();
+        op.ldw = Np;
+        op.part = vpart;
+        op.Mcp = Mcp;
+        op.tri = p.lchol ? 1 : 0;
+        op.Np = Np;
+        op.ns = ns;
+        op.N = (int)post->N;
+        op.mc = mc;
+        launch_gemm(ctx, op, dim3((unsigned)(Mcp / T), (unsigned)Nt));
+      }
+      QuadFinishArgs fa;
+      fa.md = md;
+      fa.Nt = Nt;
+      fa.nv = Nt * ns;
+      fa.mc = mc;
+      fa.Mcp = Mcp;
+      fa.compute_var = compute_var;
+      fa.mu = dmu;
+      fa.sigma = dsg;
+      fa.hyp = hyp_s;
+      fa.mupart = mupart;
+      fa.vpart = vpart;
+      fa.F_s = F_s + (size_t)s * Mcp;
+      fa.V_s = V_s + (size_t)s * Mcp;
+      quad_finish_kernel<<<(unsigned)((mc + 255) / 256), 256, 0, ctx->stream>>>(fa);
+      LAUNCHED(ctx);
+    }
+    const size_t ocols = separate ? Ns : 1;
+    if (!compute_var) CK(cudaMemsetAsync(V_s, 0, sizeof(double) * Ns * Mcp, ctx->stream));
+    CombineArgs ca;
+    ca.Ns = Ns;
+    ca.mc = mc;
+    ca.Mcp = Mcp;
+    ca.add_noise = 0;
+    ca.separate = separate;
+    ca.want_lpd = 0;
+    ca.ys = nullptr;
+    ca.mu_s = F_s;
+    ca.s2_s = V_s;
+    ca.ys2_s = V_s;
+    ca.lpd_s = nullptr;
+    ca.mu = ctx->pout;
+    ca.s2 = ctx->pout + (size_t)McpMax * ocols;
+    ca.lpd = nullptr;
+    pred_combine_kernel<<<(unsigned)((mc + 255) / 256), 256, 0, ctx->stream>>>(ca);
+    LAUNCHED(ctx);
+    CK(cudaMemcpyAsync(F + c0 * ocols, ca.mu, sizeof(double) * mc * ocols, cudaMemcpyDeviceToHost, ctx->stream));
+    if (compute_var)
+      CK(cudaMemcpyAsync(F_var + c0 * ocols, ca.s2, sizeof(double) * mc * ocols, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  CK(cudaGetLastError());
+  return GPB_OK;
+}
+
+// ---------------------------------------------------------------------------------
 // plugin surface
 // ---------------------------------------------------------------------------------
+
+// ---------------------------------------------------------------------------------
+// full predictive covariance (GP.predict_full)
+// ---------------------------------------------------------------------------------
+template <int KIND>
+static void launch_full(gpb_ctx* ctx, const FullArgs& a) {
+  full_finish_kernel<KIND><<<grid1d((long long)a.M * a.M), 256, 0, ctx->stream>>>(a);
+  LAUNCHED(ctx);
+}
+
+extern "C" int gpb_predict_full(gpb_ctx* ctx, const gpb_post* cpost, const double* Xs, const double* ys,
+                                const double* s2s, int64_t M, int add_noise, double* mu, double* cov) {
+  if (!ctx || !cpost) return GPB_EINVAL;
+  gpb_post* post = const_cast<gpb_post*>(cpost);
+  if (!Xs || !mu || !cov || M <= 0) FAIL(GPB_EINVAL, "gpb_predict_full: bad arguments");
+  if (M > 8192) FAIL(GPB_EINVAL, "gpb_predict_full: M > 8192 (the M x M covariance per sample is the limit)");
+  CK(cudaSetDevice(ctx->device));
+  for (int st : post->status)
+    if (st) FAIL(GPB_ESTATE, "gpb_predict_full: a posterior sample has no valid factorisation");
+  int rc = ensure_w(ctx, post);
+  if (rc != GPB_OK) return rc;
+  const Bufs& b = post->b;
+  const Model md = post->md;
+  const int Ns = b.cap, D = md.D, Np = b.Np, Nt = b.Nt;
+  const int Mcp = round_up(M, T);
+  double *dXs = nullptr, *dys = nullptr, *ds2s = nullptr, *Bt = nullptr, *Vt = nullptr, *C2 = nullptr,
+         *mupart = nullptr, *dmu = nullptr, *dcov = nullptr;
+  auto cleanup = [&]() {
+    for (double* p : {dXs, dys, ds2s, Bt, Vt, C2, mupart, dmu, dcov})
+      if (p) cudaFree(p);
+  };
+  CKC(cudaMalloc(&dXs, sizeof(double) * M * D));
+  CKC(cudaMemcpyAsync(dXs, Xs, sizeof(double) * M * D, cudaMemcpyHostToDevice, ctx->stream));
+  if (ys) {
+    CKC(cudaMalloc(&dys, sizeof(double) * M));
+    CKC(cudaMemcpyAsync(dys, ys, sizeof(double) * M, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (s2s) {
+    CKC(cudaMalloc(&ds2s, sizeof(double) * M));
+    CKC(cudaMemcpyAsync(ds2s, s2s, sizeof(double) * M, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CKC(cudaMalloc(&Bt, sizeof(double) * Mcp * Np));
+  CKC(cudaMalloc(&Vt, sizeof(double) * Mcp * Np));
+  CKC(cudaMalloc(&C2, sizeof(double) * Mcp * Mcp));
+  CKC(cudaMalloc(&mupart, sizeof(double) * Nt * Mcp));
+  CKC(cudaMalloc(&dmu, sizeof(double) * M * Ns));
+  CKC(cudaMalloc(&dcov, sizeof(double) * M * M));
+  const int kc = kind_code(md.cov_kind, md.degree);
+  const size_t ks_smem = ((size_t)2 * D * T + T + 8 * T) * 8;
+  // the reference's noise is an (M,1) array as soon as a per-point term is active (noise_functions.py:258-278)
+  const int per_point = ((md.nz1 > 0 && s2s) || (md.nz2 == 1 && ys)) ? 1 : 0;
+  for (int s = 0; s < Ns; ++s) {
+    const SlotP& p = post->sp[s];
+    KsArgs ka;
+    ka.md = md;
+    ka.N = (int)post->N;
+    ka.Np = Np;
+    ka.Nt = Nt;
+    ka.mc = (int)M;
+    ka.Mcp = Mcp;
+    ka.Xs = dXs;
+    ka.hyp = b.hyp + (size_t)s * md.P;
+    ka.xs = b.xs + (size_t)s * D * Np;
+    ka.alpha = b.alpha + (size_t)s * Np;
+    ka.sp = p;
+    ka.scale = p.lchol ? 1.0 / sqrt(p.sn2_min * p.mult) : 1.0;
+    ka.Bt = Bt;
+    ka.mupart = mupart;
+    dim3 kgrid((unsigned)(Mcp / T), (unsigned)Nt);
+    switch (kc) {
+      case 0: launch_ks<0>(ctx, ka, kgrid, ks_smem); break;
+      case 1: launch_ks<1>(ctx, ka, kgrid, ks_smem); break;
+      case 3: launch_ks<3>(ctx, ka, kgrid, ks_smem); break;
+      case 5: launch_ks<5>(ctx, ka, kgrid, ks_smem); break;
+      default: launch_ks<2>(ctx, ka, kgrid, ks_smem); break;
+    }
+    if (p.lchol) {
+      // V^T = Bt W^T (Mcp x Np), then C2 = V^T V (Mcp x Mcp)
+      launch_gemm(ctx, OpPlain{Bt, b.Wbuf + (size_t)s * b.smat(), Vt, Mcp, Np, Mcp, Np},
+                  dim3((unsigned)(Mcp / T), (unsigned)Nt));
+      launch_gemm(ctx, OpPlain{Vt, Vt, C2, Mcp, Mcp, Mcp, Np}, dim3((unsigned)(Mcp / T), (unsigned)(Mcp / T)));
+    } else {
+      // T1 = Ks^T Ainv (Mcp x Np), then C2 = T1 Ks (Mcp x Mcp)
+      launch_gemm(ctx, OpPlain{Bt, b.Abuf + (size_t)s * b.smat(), Vt, Mcp, Np, Mcp, Np},
+                  dim3((unsigned)(Mcp / T), (unsigned)Nt));
+      launch_gemm(ctx, OpPlain{Vt, Bt, C2, Mcp, Mcp, Mcp, Np}, dim3((unsigned)(Mcp / T), (unsigned)(Mcp / T)));
+    }
+    FullArgs fa;
+    fa.md = md;
+    fa.Nt = Nt;
+    fa.M = (int)M;
+    fa.Mcp = Mcp;
+    fa.Xs = dXs;
+    fa.ys = dys;
+    fa.s2s = ds2s;
+    fa.hyp = b.hyp + (size_t)s * md.P;
+    fa.sp = p;
+    fa.mupart = mupart;
+    fa.C2 = C2;
+    fa.add_noise = add_noise;
+    fa.per_point = per_point;
+    fa.mu = dmu + s;
+    fa.Ns = Ns;
+    fa.cov = dcov;
+    switch (kc) {
+      case 0: launch_full<0>(ctx, fa); break;
+      case 1: launch_full<1>(ctx, fa); break;
+      case 3: launch_full<3>(ctx, fa); break;
+      case 5: launch_full<5>(ctx, fa); break;
+      default: launch_full<2>(ctx, fa); break;
+    }
+    CKC(cudaMemcpyAsync(cov + (size_t)s * M * M, dcov, sizeof(double) * M * M, cudaMemcpyDeviceToHost, ctx->stream));
+    CKC(cudaStreamSynchronize(ctx->stream));
+  }
+  CKC(cudaMemcpyAsync(mu, dmu, sizeof(double) * M * Ns, cudaMemcpyDeviceToHost, ctx->stream));
+  CKC(cudaStreamSynchronize(ctx->stream));
+  CKC(cudaGetLastError());
+  cleanup();
+  return GPB_OK;
+}
+
 template <int KIND>
 static void launch_cov(gpb_ctx* ctx, const CovArgs& a, long long total) {
   cov_plugin_kernel<KIND><<<grid1d(total), 256, 0, ctx->stream>>>(a);
@@ -1090,15 +1348,6 @@ extern "C" int gpb_cov(gpb_ctx* ctx, int cov_kind, int matern_degree, int ard, c
     for (double* p : {dh, dX, dXs, dKd, ddK})
       if (p) cudaFree(p);
   };
-#define CKC(call)                                   \
-  do {                                              \
-    cudaError_t e_ = (call);                        \
-    if (e_ != cudaSuccess) {                        \
-      ctx->err = cudaGetErrorString(e_);            \
-      cleanup();                                    \
-      return GPB_ECUDA;                             \
-    }                                               \
-  } while (0)
   CKC(cudaMalloc(&dh, sizeof(double) * md.cov_n));
   CKC(cudaMalloc(&dX, sizeof(double) * N * D));
   CKC(cudaMalloc(&dKd, sizeof(double) * total));

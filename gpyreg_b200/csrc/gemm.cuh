@@ -283,6 +283,23 @@ struct OpGeneric {
   }
 };
 
+// plain product C = A B^T (C is not read)
+struct OpPlain {
+  static constexpr bool SLOT_MAJOR = false;
+  static constexpr int MODE = GM_STORE;
+  const double* A; const double* B; double* C;
+  long long lda, ldb, ldc;
+  int K;
+  __device__ GemmTile resolve(int bx, int by) const {
+    GemmTile t = empty_tile();
+    t.A = A + (long long)bx * BM; t.lda = lda;
+    t.B = B + (long long)by * BN; t.ldb = ldb;
+    t.C = C + (long long)bx * BM + (long long)by * BN * ldc; t.ldc = ldc;
+    t.K = K;
+    return t;
+  }
+};
+
 // potrf panel, step k:  L_ik = A_ik * D_k^T  (i > k), in place
 struct OpPanel {
   static constexpr bool SLOT_MAJOR = false;

@@ -200,4 +200,193 @@ __global__ void __launch_bounds__(256) pred_combine_kernel(CombineArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------
+// Bayesian quadrature against Gaussian measures N(mu_j, diag(sigma_j^2)), SE-ARD kernel only
+// (reference: GP.quad, gaussian_process.py:1818-1981).  Same structure as predict with the
+// cross-covariance replaced by  z(j,i) = exp(lnnf_j - 1/2 sum_k ((mu_jk - x_ik)/tau_jk)^2),
+// tau_jk = sqrt(sigma_jk^2 + ell_k^2)  (:1925-1937).
+// ---------------------------------------------------------------------------------
+struct QuadArgs {
+  Model md;
+  int N, Np, Nt, mc, Mcp;
+  const double* mu;            // (mc, D) chunk
+  const double* sigma;         // (mc, D) chunk
+  const double* X;             // (N, D) training inputs, row-major
+  const double* hyp;
+  const double* alpha;         // [Np]
+  double scale;                // 1/sqrt(sn2_eff) (L_chol) or 1
+  double* Bt;                  // (Mcp, Np) column-major
+  double* mupart;              // [Nt][Mcp]
+};
+
+__global__ void __launch_bounds__(256) quad_build_kernel(QuadArgs a) {
+  extern __shared__ double bsm[];
+  const int D = a.md.D;
+  const int jt = blockIdx.x, kt = blockIdx.y;
+  double* mr = bsm;                 // [D][128] measure means
+  double* it = bsm + D * T;         // [D][128] 1 / tau
+  double* xc = bsm + 2 * D * T;     // [D][128] training inputs
+  double* lnnf = bsm + 3 * D * T;   // [128]
+  double* al = lnnf + T;            // [128]
+  double* red = al + T;             // [8][128]
+  for (int e = threadIdx.x; e < D * T; e += blockDim.x) {
+    const int k = e / T, i = e % T;
+    const int j = jt * T + i, gi = kt * T + i;
+    double m = 0.0, itau = 0.0;
+    if (j < a.mc) {
+      const double sg = a.sigma[(long long)j * D + k], ell = exp(a.hyp[k]);
+      m = a.mu[(long long)j * D + k];
+      itau = 1.0 / sqrt(sg * sg + ell * ell);
+    }
+    mr[e] = m;
+    it[e] = itau;
+    xc[e] = (gi < a.N) ? a.X[(long long)gi * D + k] : 0.0;
+  }
+  if (threadIdx.x < T) {
+    const int j = jt * T + threadIdx.x;
+    double v = 0.0;
+    if (j < a.mc) {
+      double sl = 0.0, st = 0.0;            // sum log ell, sum log tau
+      for (int k = 0; k < D; ++k) {
+        const double sg = a.sigma[(long long)j * D + k], ell = exp(a.hyp[k]);
+        sl += a.hyp[k];
+        st += log(sqrt(sg * sg + ell * ell));
+      }
+      v = 2 * a.hyp[D] + sl - st;          // :1925-1927
+    }
+    lnnf[threadIdx.x] = v;
+    al[threadIdx.x] = a.alpha[kt * T + threadIdx.x];
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  double fsum[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int b = 0; b < 16; ++b) {
+    const int il = ty * 16 + b, gi = kt * T + il;
+    double d2[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int k = 0; k < D; ++k) {
+      const double x = xc[k * T + il];
+#pragma unroll
+      for (int aa = 0; aa < 4; ++aa) {
+        const double q = (mr[k * T + tx + 32 * aa] - x) * it[k * T + tx + 32 * aa];
+        d2[aa] += q * q;
+      }
+    }
+#pragma unroll
+    for (int aa = 0; aa < 4; ++aa) {
+      const int jl = tx + 32 * aa, gj = jt * T + jl;
+      double z = 0.0;
+      if (gi < a.N && gj < a.mc) z = exp(lnnf[jl] - 0.5 * d2[aa]);     // :1937
+      a.Bt[(long long)gi * a.Mcp + gj] = a.scale * z;
+      fsum[aa] += z * al[il];
+    }
+  }
+#pragma unroll
+  for (int aa = 0; aa < 4; ++aa) red[ty * T + tx + 32 * aa] = fsum[aa];
+  __syncthreads();
+  if (threadIdx.x < T) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += red[w * T + threadIdx.x];
+    a.mupart[(long long)kt * a.Mcp + jt * T + threadIdx.x] = s;
+  }
+}
+
+struct QuadFinishArgs {
+  Model md;
+  int Nt, nv, mc, Mcp, compute_var;
+  const double* mu; const double* sigma; const double* hyp;
+  const double* mupart; const double* vpart;
+  double* F_s; double* V_s;      // this sample's rows, [Mcp]
+};
+
+__global__ void __launch_bounds__(256) quad_finish_kernel(QuadFinishArgs a) {
+  const Model& md = a.md;
+  const int D = md.D;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= a.mc) return;
+  const double* hm = a.hyp + md.cov_n + md.noise_n;
+  const double* mu = a.mu + (long long)j * D;
+  const double* sg = a.sigma + (long long)j * D;
+  double F = (md.mean_kind == 0) ? 0.0 : hm[0];                      // :1906-1909
+  for (int t = 0; t < a.Nt; ++t) F += a.mupart[(long long)t * a.Mcp + j];
+  if (md.mean_kind == 2) {                                           // :1939-1946
+    double nu = 0.0;
+    for (int k = 0; k < D; ++k) {
+      const double xm = hm[1 + k], om = exp(hm[1 + D + k]);
+      nu += 1.0 / (om * om) * (mu[k] * mu[k] + sg[k] * sg[k] - 2 * mu[k] * xm + xm * xm);
+    }
+    F += -0.5 * nu;
+  }
+  a.F_s[j] = F;
+  if (a.compute_var) {
+    double sl = 0.0, st = 0.0;
+    for (int k = 0; k < D; ++k) {
+      const double ell = exp(a.hyp[k]);
+      sl += a.hyp[k];
+      st += log(sqrt(2 * sg[k] * sg[k] + ell * ell));
+    }
+    const double nf_kk = exp(2 * a.hyp[D] + sl - st);                // :1949-1950
+    double v = 0.0;
+    for (int t = 0; t < a.nv; ++t) v += a.vpart[(long long)t * a.Mcp + j];
+    a.V_s[j] = fmax(2.220446049250313e-16, nf_kk - v);               // :1966-1969
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// Full predictive covariance (reference: GP.predict_full, gaussian_process.py:1561-1661):
+//   cov_s = K(x*,x*) - C2, C2 = V^T V (L_chol) or Ks^T Ainv Ks (low noise), symmetrised,
+//   plus the noise term of :1655-1659.
+// ---------------------------------------------------------------------------------
+struct FullArgs {
+  Model md;
+  int Nt, M, Mcp;
+  const double* Xs; const double* ys; const double* s2s;
+  const double* hyp;
+  SlotP sp;
+  const double* mupart;        // [Nt][Mcp]
+  const double* C2;            // (Mcp, Mcp) column-major
+  int add_noise, per_point;    // per_point: the reference's noise is an (M,1) array
+  double* mu;                  // this sample's column of (M, Ns): mu[j*Ns]
+  int Ns;
+  double* cov;                 // this sample's (M, M) row-major block
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(256) full_finish_kernel(FullArgs a) {
+  const Model& md = a.md;
+  const int D = md.D;
+  const long long total = (long long)a.M * a.M;
+  const double* hn = a.hyp + md.cov_n;
+  const double* hm = a.hyp + md.cov_n + md.noise_n;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e / a.M), j = (int)(e % a.M);
+    const double* xi = a.Xs + (long long)i * D;
+    const double* xj = a.Xs + (long long)j * D;
+    double r2 = 0.0;
+    for (int k = 0; k < D; ++k) {
+      const double ell = exp(a.hyp[md.ard ? k : 0]);
+      const double d = scale_coord(md.cov_kind, md.ard, md.degree, xi[k], ell) -
+                       scale_coord(md.cov_kind, md.ard, md.degree, xj[k], ell);
+      r2 = __dadd_rn(r2, __dmul_rn(d, d));
+    }
+    const double K = kern_value<KIND>(r2, a.sp.sf2, a.sp.rq_a);
+    const double cij = K - a.C2[(long long)j * a.Mcp + i];
+    const double cji = K - a.C2[(long long)i * a.Mcp + j];
+    double v = (cij + cji) / 2;                                     // :1645
+    if (a.add_noise) {
+      const double sn2 = noise_value(md.nz0, md.nz1, md.nz2, hn, a.ys != nullptr,
+                                     a.ys ? a.ys[i] : 0.0, a.s2s != nullptr, a.s2s ? a.s2s[i] : 0.0);
+      // np.dot(np.eye(M), sn2_star) * sn2_mult: a scalar sn2 lands on the diagonal, an (M,1)
+      // sn2 broadcasts over the whole row (:1655-1659)
+      if (a.per_point || i == j) v += sn2 * a.sp.mult;
+    }
+    a.cov[e] = v;
+    if (j == 0) {
+      double m = mean_value(md.mean_kind, D, hm, xi);
+      for (int t = 0; t < a.Nt; ++t) m += a.mupart[(long long)t * a.Mcp + i];
+      a.mu[(long long)i * a.Ns] = m;
+    }
+  }
+}
+
 }  // namespace gpb

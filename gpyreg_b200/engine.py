@@ -135,6 +135,28 @@ class Engine:
                                          int(separate), int(want_lpd), ptr(mu), ptr(s2), ptr(lpd)))
         return (mu, s2, lpd) if want_lpd else (mu, s2)
 
+    def predict_full(self, post, Xs, ys=None, s2s=None, add_noise=False):
+        """-> mu (M, Ns), cov (M, M, Ns) like GP.predict_full."""
+        Xs = f64(Xs)
+        M = Xs.shape[0]
+        ys = None if ys is None else f64(ys, (M,))
+        s2s = None if s2s is None else f64(s2s, (M,))
+        mu = np.empty((M, post.count))
+        cov = np.empty((post.count, M, M))
+        self._check(self.lib.gpb_predict_full(self._h, post._h, ptr(Xs), ptr(ys), ptr(s2s), M,
+                                              int(add_noise), ptr(mu), ptr(cov)))
+        return mu, cov.transpose(1, 2, 0)
+
+    def quad(self, post, mu, sigma, compute_var=False, separate=False):
+        mu, sigma = f64(mu), f64(sigma)
+        M = mu.shape[0]
+        cols = post.count if separate else 1
+        F = np.empty((M, cols))
+        Fv = np.empty((M, cols)) if compute_var else None
+        self._check(self.lib.gpb_quad(self._h, post._h, ptr(mu), ptr(sigma), M, int(compute_var),
+                                      int(separate), ptr(F), ptr(Fv)))
+        return (F, Fv) if compute_var else F
+
     def predict_dev(self, post, d_Xs, M, add_noise, separate, d_mu, d_s2):
         self._check(self.lib.gpb_predict_dev(self._h, post._h, d_Xs, M, int(add_noise), int(separate),
                                              d_mu, d_s2))

@@ -8,8 +8,7 @@ places where the reference loops over hyperparameter vectors one at a time are b
 the ``f_min_fill`` design (f_min_fill.py:174-176), the posterior rebuild in ``update``
 (gaussian_process.py:870-879) and the per-sample loop of ``predict`` (:1727).
 
-Not built in this round (SURVEY.md 8f "next" rows): ``quad``, ``predict_full``,
-``random_function``, ``plot``; a one-point ``update`` is done as a full (batched)
+Not built in this round: ``random_function``, ``plot``; a one-point ``update`` is done as a full (batched)
 recompute instead of the reference's rank-1 append -- same posterior, different cost.
 """
 import math
@@ -747,11 +746,37 @@ class GP:
         raise NotImplementedError(
             f"GP.{name} is outside the hot path built so far (SURVEY.md 8f 'next' rows)")
 
-    def quad(self, *a, **k):
-        self._not_built("quad")
+    def quad(self, mu, sigma, compute_var=False, separate_samples=False):
+        """Bayesian quadrature of the GP against Gaussian measures N(mu, diag(sigma^2))
+        (gaussian_process.py:1818-1981; squared-exponential kernel only): one GPU call for
+        all measures and all hyperparameter samples."""
+        from .covariance_functions import SquaredExponential
+        if not isinstance(self.covariance, SquaredExponential):
+            raise ValueError("Bayesian quadrature only supports the squared exponential kernel.")
+        if not self.covariance._ard:
+            raise ValueError("Bayesian quadrature needs the ARD squared exponential kernel "
+                             "(the reference reads D length scales, gaussian_process.py:1901)")
+        D = self.D
+        mu = np.tile(mu, (1, D)) if np.size(mu) == 1 else np.atleast_2d(np.asarray(mu, dtype=float))
+        sigma = np.tile(sigma, (1, D)) if np.size(sigma) == 1 else np.atleast_2d(np.asarray(sigma, dtype=float))
+        sigma = np.ascontiguousarray(np.broadcast_to(sigma, mu.shape))
+        batch = self._post_batch
+        if batch is None or batch._h is None:
+            raise RuntimeError("GP.quad: the posteriors hold no device factors; call "
+                               "update(compute_posterior=True) first")
+        return self.engine.quad(batch, mu, sigma, compute_var=compute_var, separate=separate_samples)
 
-    def predict_full(self, *a, **k):
-        self._not_built("predict_full")
+    def predict_full(self, x_star, y_star=None, s2_star=None, add_noise=False):
+        """Posterior mean (M, Ns) and full covariance (M, M, Ns) at x_star for every
+        hyperparameter sample (gaussian_process.py:1561-1661)."""
+        x_star, y_star, s2_star = self._convert_shapes(x_star, y_star, s2_star)
+        batch = self._post_batch
+        if self.y is None or batch is None or batch._h is None:
+            raise RuntimeError("GP.predict_full needs posteriors with device factors; call "
+                               "update(compute_posterior=True) on a GP with data first")
+        return self.engine.predict_full(batch, x_star, None if y_star is None else y_star.reshape(-1),
+                                        None if s2_star is None else s2_star.reshape(-1),
+                                        add_noise=add_noise)
 
     def random_function(self, *a, **k):
         self._not_built("random_function")

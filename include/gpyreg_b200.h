@@ -102,6 +102,19 @@ int gpb_predict(gpb_ctx* ctx, const gpb_post* post, const double* Xs, const doub
 int gpb_predict_dev(gpb_ctx* ctx, const gpb_post* post, const double* d_Xs, int64_t M,
                     int add_noise, int separate, double* d_mu, double* d_s2);
 
+/* GP.predict_full, gaussian_process.py:1561-1661: posterior mean and FULL covariance at M test
+ * points (M <= 8192), per hyperparameter sample.  mu (M,Ns) row-major; cov (Ns,M,M) C-order
+ * (the Python layer returns cov.transpose(1,2,0) like the reference, :1661). */
+int gpb_predict_full(gpb_ctx* ctx, const gpb_post* post, const double* Xs, const double* ys,
+                     const double* s2s, int64_t M, int add_noise, double* mu, double* cov);
+
+/* GP.quad, gaussian_process.py:1818-1981: Bayesian quadrature of the GP against M Gaussian
+ * measures N(mu_j, diag(sigma_j^2)) (squared-exponential ARD kernel only).
+ *   mu, sigma (M,D); F [, F_var]: (M) when separate == 0, else (M,Ns) row-major;
+ *   F_var may be NULL when compute_var == 0. */
+int gpb_quad(gpb_ctx* ctx, const gpb_post* post, const double* mu, const double* sigma, int64_t M,
+             int compute_var, int separate, double* F, double* F_var);
+
 /* Plugin surface -------------------------------------------------------------------
  * covariance.compute(hyp, X, X_star, compute_diag, compute_grad),
  * covariance_functions.py:135-186, :221-285, :301-367; isotropic_...py:104-161, :173-221.

@@ -392,7 +392,62 @@ def gen_fit():
     print("fit.npz", len(out), "arrays; ex1 opt fun", opt.fun)
 
 
+def gen_next():
+    """GP.quad (Bayesian quadrature) and GP.predict_full."""
+    out = {}
+    rng = np.random.default_rng(500)
+    for tag, mk, npar, use_s2, lownoise in [("zero", 0, (1, 0, 0), False, False),
+                                            ("const", 1, (1, 0, 0), False, False),
+                                            ("negquad", 2, (1, 1, 0), True, False),
+                                            ("lown", 1, (1, 0, 0), False, True)]:
+        N, D, B = 60, 3, 3
+        X, y = synth(rng, N, D)
+        s2 = rng.uniform(0.005, 0.05, (N, 1)) if use_s2 else None
+        gp = make_gp(D, COVS[0], mk, npar)
+        hyps = benign_hyp(rng, B, D, COVS[0], mk, npar, y)
+        if lownoise:
+            hyps[:, D + 1] = np.log(3e-4)           # noise variance 9e-8 < 1e-6: low-noise branch
+            hyps[:, :D] = np.log(0.6)
+        gp.update(X_new=X, y_new=y, s2_new=s2, hyp=hyps)
+        M = 9
+        mu = rng.uniform(-2, 2, (M, D))
+        sigma = rng.uniform(0.2, 1.5, (M, D))
+        out[f"{tag}.spec"] = np.array([D, 0, 0, 1, mk, *npar])
+        out[f"{tag}.X"], out[f"{tag}.y"], out[f"{tag}.hyp"] = X, y, hyps
+        if use_s2:
+            out[f"{tag}.s2"] = s2
+        out[f"{tag}.mu"], out[f"{tag}.sigma"] = mu, sigma
+        out[f"{tag}.L_chol"] = np.array([int(p.L_chol) for p in gp.posteriors])
+        for sep in (0, 1):
+            F, Fv = gp.quad(mu, sigma, compute_var=True, separate_samples=bool(sep))
+            out[f"{tag}.quad{sep}.F"], out[f"{tag}.quad{sep}.Fv"] = F, Fv
+        out[f"{tag}.quad_scalar.F"] = gp.quad(mu, 0.7, compute_var=False)
+        Xs = rng.uniform(-3, 3, (11, D))
+        ys = rng.standard_normal((11, 1))
+        s2s = rng.uniform(0.005, 0.05, (11, 1)) if use_s2 else None
+        out[f"{tag}.Xs"], out[f"{tag}.ys"] = Xs, ys
+        if use_s2:
+            out[f"{tag}.s2s"] = s2s
+        for an in (0, 1):
+            m, c = gp.predict_full(Xs, ys, s2s, add_noise=bool(an))
+            out[f"{tag}.full{an}.mu"], out[f"{tag}.full{an}.cov"] = m, np.ascontiguousarray(c)
+    # predict_full for a Matern-5 ARD + NegQuad GP too
+    N, D, B = 50, 4, 2
+    X, y = synth(rng, N, D)
+    gp = make_gp(D, COVS[3], 2, (1, 0, 0))
+    hyps = benign_hyp(rng, B, D, COVS[3], 2, (1, 0, 0), y)
+    gp.update(X_new=X, y_new=y, hyp=hyps)
+    Xs = rng.uniform(-3, 3, (8, D))
+    m, c = gp.predict_full(Xs, add_noise=True)
+    out["mat5.spec"] = np.array([D, 1, 5, 1, 2, 1, 0, 0])
+    out["mat5.X"], out["mat5.y"], out["mat5.hyp"], out["mat5.Xs"] = X, y, hyps, Xs
+    out["mat5.full1.mu"], out["mat5.full1.cov"] = m, np.ascontiguousarray(c)
+    np.savez_compressed(os.path.join(HERE, "next.npz"), **out)
+    print("next.npz", len(out), "arrays; low-noise L_chol", out["lown.L_chol"])
+
+
 if __name__ == "__main__":
+    gen_next()
     gen_fit()
     gen_host()
     gen_plugins()

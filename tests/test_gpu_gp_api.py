@@ -208,3 +208,43 @@ def test_fit_multichain_and_lockstep(capsys):
     with capsys.disabled():
         print(f"\n[fit ex2] sequential fit {t_seq:.2f} s; 4-chain fit (40 samples) {t_mc:.2f} s, "
               f"{res['func_count']} evals in {res['rounds']} rounds")
+
+
+@pytest.mark.parametrize("tag", ["zero", "const", "negquad", "lown"])
+def test_quad_and_predict_full(tag):
+    """GP.quad and GP.predict_full against the reference
+    (testing/test_gaussian_process.py:496-614 cross-checks the same two against each other)."""
+    gold = _load("next.npz")
+    c = case(gold, tag)
+    gp = build_gp(c["spec"])
+    gp.update(X_new=c["X"], y_new=c["y"], s2_new=c.get("s2"), hyp=c["hyp"])
+    assert [int(p.L_chol) for p in gp.posteriors] == list(c["L_chol"])
+    tol = 1e-8 if tag != "lown" else 1e-5            # the low-noise branch is ill-conditioned
+    for sep in (0, 1):
+        F, Fv = gp.quad(c["mu"], c["sigma"], compute_var=True, separate_samples=bool(sep))
+        assert F.shape == c[f"quad{sep}.F"].shape
+        assert np.max(np.abs(F - c[f"quad{sep}.F"])) <= tol * (1 + np.max(np.abs(c[f"quad{sep}.F"])))
+        assert np.max(np.abs(Fv - c[f"quad{sep}.Fv"])) <= tol * (np.max(np.abs(c[f"quad{sep}.Fv"])) + 1e-3)
+    F = gp.quad(c["mu"], 0.7)
+    assert np.max(np.abs(F - c["quad_scalar.F"])) <= tol * (1 + np.max(np.abs(c["quad_scalar.F"])))
+    for an in (0, 1):
+        m, cov = gp.predict_full(c["Xs"], c["ys"], c.get("s2s"), add_noise=bool(an))
+        assert m.shape == c[f"full{an}.mu"].shape and cov.shape == c[f"full{an}.cov"].shape
+        assert np.max(np.abs(m - c[f"full{an}.mu"])) <= tol * (1 + np.max(np.abs(c[f"full{an}.mu"])))
+        assert np.max(np.abs(cov - c[f"full{an}.cov"])) <= tol * np.max(np.abs(c[f"full{an}.cov"]))
+    # predict() is the diagonal of predict_full()
+    mu_d, s2_d = gp.predict(c["Xs"], separate_samples=True)
+    m, cov = gp.predict_full(c["Xs"])
+    assert np.allclose(np.einsum("iis->is", cov), s2_d, rtol=1e-7, atol=1e-9 if tag != "lown" else 1e-5)
+
+
+def test_predict_full_matern_and_quad_errors():
+    gold = _load("next.npz")
+    c = case(gold, "mat5")
+    gp = build_gp(c["spec"])
+    gp.update(X_new=c["X"], y_new=c["y"], hyp=c["hyp"])
+    m, cov = gp.predict_full(c["Xs"], add_noise=True)
+    assert np.max(np.abs(m - c["full1.mu"])) <= 1e-8 * (1 + np.max(np.abs(c["full1.mu"])))
+    assert np.max(np.abs(cov - c["full1.cov"])) <= 1e-8 * np.max(np.abs(c["full1.cov"]))
+    with pytest.raises(ValueError, match="Bayesian quadrature only supports the squared exponential"):
+        gp.quad(np.zeros((1, 4)), 1.0)
