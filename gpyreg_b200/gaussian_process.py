@@ -8,7 +8,7 @@ places where the reference loops over hyperparameter vectors one at a time are b
 the ``f_min_fill`` design (f_min_fill.py:174-176), the posterior rebuild in ``update``
 (gaussian_process.py:870-879) and the per-sample loop of ``predict`` (:1727).
 
-Not built in this round: ``random_function``, ``plot``; a one-point ``update`` is done as a full (batched)
+Not built: ``plot`` (matplotlib); a one-point ``update`` is done as a full (batched)
 recompute instead of the reference's rank-1 append -- same posterior, different cost.
 """
 import math
@@ -38,6 +38,21 @@ def _scipy_at_least(major, minor):
 
 # SciPy >= 1.15 ships L-BFGS-B as re-entrant C (the older Fortran kept state in SAVE variables)
 _SCIPY_LBFGSB_REENTRANT = _scipy_at_least(1, 15)
+
+
+def _robust_cholesky(sigma):
+    """Upper factor T with T^T T = sigma; falls back to an eigen-decomposition when sigma is
+    only positive semi-definite (gaussian_process.py:2331-2355)."""
+    try:
+        return sp.linalg.cholesky(sigma, check_finite=False)
+    except sp.linalg.LinAlgError:
+        w, U = sp.linalg.eigh((sigma + sigma.T) / 2)
+        keep = np.abs(w) > np.abs(np.spacing(np.max(w))) * w.shape[0]
+        w, U = w[keep], U[:, keep]
+        if np.any(w < 0):
+            return np.zeros(sigma.shape)
+        U = U * np.where(U[np.argmax(np.abs(U), axis=0), np.arange(U.shape[1])] < 0, -1.0, 1.0)
+        return np.dot(np.diag(np.sqrt(w)), U.T)
 
 
 class Posterior:
@@ -778,8 +793,31 @@ class GP:
                                         None if s2_star is None else s2_star.reshape(-1),
                                         add_noise=add_noise)
 
-    def random_function(self, *a, **k):
-        self._not_built("random_function")
+    def random_function(self, X_star, add_noise=False):
+        """Draw one function from the GP (prior if there is no data, else posterior) at
+        X_star (gaussian_process.py:2241-2329).  The mean and covariance come from the GPU
+        path; the (M, M) factorisation for the draw is a small host operation.  Consumes the
+        global NumPy RNG in the reference's order."""
+        X_star = np.atleast_2d(np.asarray(X_star, dtype=float))
+        M = X_star.shape[0]
+        cov_n, noise_n, mean_n = self._counts()
+        s = np.random.randint(0, np.size(self.posteriors))
+        hyp = np.asarray(self.posteriors[s].hyp, dtype=float)
+        if self.y is None:
+            f_mu = np.reshape(self.mean.compute(hyp[cov_n + noise_n:cov_n + noise_n + mean_n], X_star), (-1, 1))
+            C = self.covariance.compute(hyp[:cov_n], X_star) + np.spacing(1) * np.eye(M)
+        else:
+            mu, cov = self.predict_full(X_star)
+            f_mu, C = mu[:, s:s + 1], cov[:, :, s]
+        C = (C + C.T) / 2
+        Tm = _robust_cholesky(C)
+        f_star = np.dot(Tm.T, np.random.standard_normal((Tm.shape[0], 1))) + f_mu
+        if not add_noise:
+            return f_star
+        sn2 = self.noise.compute(hyp[cov_n:cov_n + noise_n], X_star, None, None)
+        mult = self.posteriors[s].sn2_mult
+        mult = 1 if mult is None else mult
+        return f_star + np.sqrt(sn2 * mult) * np.random.standard_normal(size=f_mu.shape)
 
     def plot(self, *a, **k):
         self._not_built("plot")

@@ -442,6 +442,14 @@ def gen_next():
     out["mat5.spec"] = np.array([D, 1, 5, 1, 2, 1, 0, 0])
     out["mat5.X"], out["mat5.y"], out["mat5.hyp"], out["mat5.Xs"] = X, y, hyps, Xs
     out["mat5.full1.mu"], out["mat5.full1.cov"] = m, np.ascontiguousarray(c)
+    # random_function: one seeded posterior draw and one prior draw
+    np.random.seed(11)
+    out["mat5.draw"] = gp.random_function(Xs, add_noise=True)
+    gp0 = make_gp(D, COVS[0], 1, (1, 0, 0))
+    gp0.update(hyp=hyps[:, :D + 3], compute_posterior=False)
+    np.random.seed(12)
+    out["mat5.prior_hyp"] = hyps[:, :D + 3]
+    out["mat5.prior_draw"] = gp0.random_function(Xs, add_noise=False)
     np.savez_compressed(os.path.join(HERE, "next.npz"), **out)
     print("next.npz", len(out), "arrays; low-noise L_chol", out["lown.L_chol"])
 

@@ -248,3 +248,19 @@ def test_predict_full_matern_and_quad_errors():
     assert np.max(np.abs(cov - c["full1.cov"])) <= 1e-8 * np.max(np.abs(c["full1.cov"]))
     with pytest.raises(ValueError, match="Bayesian quadrature only supports the squared exponential"):
         gp.quad(np.zeros((1, 4)), 1.0)
+
+
+def test_random_function_matches_reference_draws():
+    gold = _load("next.npz")
+    c = case(gold, "mat5")
+    gp = build_gp(c["spec"])
+    gp.update(X_new=c["X"], y_new=c["y"], hyp=c["hyp"])
+    np.random.seed(11)
+    draw = gp.random_function(c["Xs"], add_noise=True)
+    assert draw.shape == c["draw"].shape
+    assert np.max(np.abs(draw - c["draw"])) <= 1e-6 * (1 + np.max(np.abs(c["draw"])))
+    gp0 = g.GP(4, SquaredExponential(), ConstantMean(), GaussianNoise(constant_add=True))
+    gp0.update(hyp=c["prior_hyp"], compute_posterior=False)
+    np.random.seed(12)
+    pdraw = gp0.random_function(c["Xs"])
+    assert np.max(np.abs(pdraw - c["prior_draw"])) <= 1e-6 * (1 + np.max(np.abs(c["prior_draw"])))
