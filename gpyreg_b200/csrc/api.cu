@@ -46,6 +46,8 @@ struct gpb_ctx {
   double *dX = nullptr, *dy = nullptr, *ds2 = nullptr;
   size_t ws_limit = 0;
   int gemm_bn = 64;          // 64: two CTAs per SM (default); 128: one (env GPB_GEMM_BN)
+  int loader = 2;            // 0: cp.async (LDGSTS); 1: TMA bulk copies + mbarriers; 2: TMA for launches that
+                             // fill the GPU, cp.async for small ones (env GPB_LOADER=cpasync|tma|auto)
   int outer_block = 4;       // tile columns per outer block of the two-level Cholesky (env GPB_OUTER_BLOCK)
   long long* diag_dbg = nullptr;   // env GPB_DIAG_DBG: phase clock stamps of the diagonal kernel
   Bufs ws;
@@ -109,23 +111,32 @@ static inline unsigned grid1d(long long n, int block = 256) {
 
 template <class Op>
 static cudaError_t gemm_attr() {
-  cudaError_t e = cudaFuncSetAttribute(gemm_nt_kernel<Op, 128>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)gemm_smem<128>());
+  cudaError_t e;
+  e = cudaFuncSetAttribute(gemm_nt_kernel<Op, 128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<128>());
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(gemm_nt_kernel<Op, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)gemm_smem<64>());
+  e = cudaFuncSetAttribute(gemm_nt_kernel<Op, 64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<64>());
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(gemm_nt_kernel<Op, 128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<128>());
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(gemm_nt_kernel<Op, 64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<64>());
 }
 // grid.x counts logical 128x128 tiles; the BN_=64 variant launches two CTAs per tile.
 // `wide` forces the one-CTA-per-tile kernel (needed when the product is done in place).
 template <class Op>
 static void launch_gemm(gpb_ctx* ctx, const Op& op, dim3 grid, bool wide = false) {
   if (Op::SLOT_MAJOR) grid = dim3(grid.y, grid.x);      // slot in x, tile in y (see gemm.cuh)
-  if (wide || ctx->gemm_bn == 128) {
-    gemm_nt_kernel<Op, 128><<<grid, GEMM_THREADS, gemm_smem<128>(), ctx->stream>>>(op);
+  // TMA bulk copies win when the launch fills the machine (>= 2 CTAs per SM); a lone CTA on an
+  // SM hides latency better with per-thread cp.async (measured: B=1 triangular inverse)
+  const bool two = !(wide || ctx->gemm_bn == 128);
+  const long long ctas = (long long)grid.x * grid.y * grid.z * (two ? 2 : 1);
+  const bool tma = ctx->loader == 1 || (ctx->loader == 2 && ctas >= 2 * 148);
+  if (!two) {
+    if (tma) gemm_nt_kernel<Op, 128, 1><<<grid, GEMM_THREADS, gemm_smem<128>(), ctx->stream>>>(op);
+    else gemm_nt_kernel<Op, 128, 0><<<grid, GEMM_THREADS, gemm_smem<128>(), ctx->stream>>>(op);
   } else {
     grid.x *= 2;
-    gemm_nt_kernel<Op, 64><<<grid, GEMM_THREADS, gemm_smem<64>(), ctx->stream>>>(op);
+    if (tma) gemm_nt_kernel<Op, 64, 1><<<grid, GEMM_THREADS, gemm_smem<64>(), ctx->stream>>>(op);
+    else gemm_nt_kernel<Op, 64, 0><<<grid, GEMM_THREADS, gemm_smem<64>(), ctx->stream>>>(op);
   }
   LAUNCHED(ctx);
 }
@@ -193,6 +204,8 @@ extern "C" int gpb_create(int device, gpb_ctx** out) {
   }
   ctx->stream = ctx->own_stream;
   if (const char* bn = getenv("GPB_GEMM_BN")) ctx->gemm_bn = (atoi(bn) == 128) ? 128 : 64;
+  if (const char* ld = getenv("GPB_LOADER"))
+    ctx->loader = (strcmp(ld, "tma") == 0) ? 1 : (strcmp(ld, "cpasync") == 0 ? 0 : 2);
   if (const char* ob = getenv("GPB_OUTER_BLOCK")) ctx->outer_block = std::max(1, atoi(ob));
   if (getenv("GPB_DIAG_DBG")) cudaMalloc(&ctx->diag_dbg, 40 * sizeof(long long));
   for (auto& ev : ctx->ev) cudaEventCreate(&ev);

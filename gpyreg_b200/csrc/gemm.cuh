@@ -50,6 +50,36 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
 
+// ---- TMA bulk-copy + mbarrier helpers (cp.async.bulk -> SASS UBLKCP) ---------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// one contiguous run of `bytes` (multiple of 16) global -> shared, completion counted on `bar`
+__device__ __forceinline__ void bulk_g2s(double* dst, const double* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // MODE bits
 constexpr int GM_BETA = 1;     // C enters the product: accumulators start at (beta/alpha) * C
 constexpr int GM_STORE = 2;    // normal store
@@ -58,14 +88,18 @@ constexpr int GM_REDUCE = 8;   // row-sum epilogue (no store)
 
 template <int BN_>
 constexpr size_t gemm_smem() {
-  return (size_t)NSTAGE * BK * (PITCH + BN_ + 4) * sizeof(double);
+  return (size_t)NSTAGE * BK * (PITCH + BN_ + 4) * sizeof(double) + 2 * NSTAGE * sizeof(unsigned long long);
 }
 
 // BN_ = 128: one CTA per SM, 32x64 warp tiles.  BN_ = 64: the logical 128x128 tile is split
 // into two column halves (blockIdx.x = 2*tile + half), 32x32 warp tiles, <= 128 registers and
 // 100 KB of shared memory so TWO CTAs share an SM and one CTA's prologue/epilogue (C tile
 // read/write, pipeline fill) overlaps the other's DMMA main loop.
-template <class Op, int BN_>
+// LOADER = 0: every thread streams its share of the operand tiles with 16-byte cp.async
+// (LDGSTS).  LOADER = 1: warp 0 issues TMA bulk copies (cp.async.bulk, one lane per 1 KB /
+// 512 B tile column: 32 copies per stage) and the ring is synchronised with full/empty
+// mbarriers, so the other 7 warps issue no load instructions at all.
+template <class Op, int BN_, int LOADER>
 __global__ void __launch_bounds__(GEMM_THREADS, (BN_ == 64 ? 2 : 1))
 gemm_nt_kernel(const __grid_constant__ Op op) {
   extern __shared__ __align__(16) double gsm[];
@@ -126,12 +160,47 @@ gemm_nt_kernel(const __grid_constant__ Op op) {
     }
   };
 
+  unsigned long long* full_bar = reinterpret_cast<unsigned long long*>(gsm + NSTAGE * BK * (PITCH + PB));
+  unsigned long long* empty_bar = full_bar + NSTAGE;
+  constexpr unsigned STAGE_BYTES = BK * (BM + BN_) * sizeof(double);
+  // called by all 32 lanes of warp 0: lane l copies tile column (l & 15) of A (l < 16) or B
+  auto bulk_stage = [&](int kt, int stage) {
+    const int k0 = kt * BK;
+    const bool alt = (k0 < T);
+    const double* Ap = (alt && t.A0) ? t.A0 : t.A;
+    const long long la = (alt && t.A0) ? t.lda0 : t.lda;
+    const double* Bp = (alt && t.B0) ? t.B0 : t.B;
+    const long long lb = (alt && t.B0) ? t.ldb0 : t.ldb;
+    if (lane == 0) mbar_expect_tx(full_bar + stage, STAGE_BYTES);
+    __syncwarp();
+    const int kk = lane & (BK - 1);
+    if (lane < BK)
+      bulk_g2s(As + (stage * BK + kk) * PITCH, Ap + (long long)(k0 + kk) * la, BM * 8, full_bar + stage);
+    else
+      bulk_g2s(Bs + (stage * BK + kk) * PB, Bp + (long long)(k0 + kk) * lb, BN_ * 8, full_bar + stage);
+  };
+  if (LOADER == 1) {
+    if (tid == 0) {
 #pragma unroll
-  for (int s = 0; s < NSTAGE - 1; ++s) {
-    if (s < KT) load_stage(s, s);
-    cp_async_commit();
+      for (int s = 0; s < NSTAGE; ++s) {
+        mbar_init(full_bar + s, 1);
+        mbar_init(empty_bar + s, GEMM_THREADS / 32);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 0) {
+      for (int s = 0; s < NSTAGE - 1; ++s)
+        if (s < KT) bulk_stage(s, s);
+    }
+  } else {
+#pragma unroll
+    for (int s = 0; s < NSTAGE - 1; ++s) {
+      if (s < KT) load_stage(s, s);
+      cp_async_commit();
+    }
   }
-
   // thread owns C(m = wm + mi*8 + g, n = wn + ni*8 + 2*tq + {0,1})
   double acc[4][NI][2];
   if ((MODE & GM_BETA) && wact) {
@@ -154,9 +223,18 @@ gemm_nt_kernel(const __grid_constant__ Op op) {
   }
 
   for (int kt = 0; kt < KT; ++kt) {
-    cp_async_wait<NSTAGE - 2>();
-    __syncthreads();
-    {
+    if (LOADER == 1) {
+      const int nk = kt + NSTAGE - 1;
+      if (warp == 0 && nk < KT) {
+        const int ns = nk % NSTAGE;
+        // the slot was last read in iteration kt-1: wait until all 8 warps have released it
+        if (nk >= NSTAGE) mbar_wait(empty_bar + ns, ((nk / NSTAGE) - 1) & 1);
+        bulk_stage(nk, ns);
+      }
+      mbar_wait(full_bar + (kt % NSTAGE), (kt / NSTAGE) & 1);
+    } else {
+      cp_async_wait<NSTAGE - 2>();
+      __syncthreads();
       const int nk = kt + NSTAGE - 1;
       if (nk < KT) load_stage(nk, nk % NSTAGE);
       cp_async_commit();
@@ -177,8 +255,12 @@ gemm_nt_kernel(const __grid_constant__ Op op) {
         for (int ni = 0; ni < NI; ++ni) dmma8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
     }
     }
+    if (LOADER == 1) {                       // this warp is done with the slot
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_bar + (kt % NSTAGE));
+    }
   }
-  cp_async_wait<0>();
+  if (LOADER == 0) cp_async_wait<0>();
 
   // ---- epilogue
   if (MODE & GM_REDUCE) {
