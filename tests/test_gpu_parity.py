@@ -264,3 +264,70 @@ def test_tile_boundaries(eng, N):
     assert np.max(np.abs(mu - rmu)) <= TOL_PRED * (1 + np.max(np.abs(rmu)))
     assert np.max(np.abs(v - rv)) <= TOL_PRED * np.max(np.abs(rv))
     post.free()
+
+
+def test_batch_chunking_and_workspace_limit(eng):
+    """A workspace cap smaller than the batch forces several chunks: same results, bit for bit."""
+    from bench import benign_hyp, synth_data
+    N, D, B = 300, 3, 13
+    spec = orc.ModelSpec(D=D, cov_kind=0, ard=True, mean_kind=1)
+    X, y = synth_data(N, D, seed=0)
+    hyp = benign_hyp(spec, B, y, seed=1)
+    setup_engine(eng, spec, X, y, None)
+    full = eng.nlz_batch(hyp, want_grad=True)
+    from gpyreg_b200 import Engine
+    e2 = Engine(0)
+    e2.set_workspace_limit(4 * 2 * 384 * 384 * 8 + (1 << 20))        # room for ~4 slots
+    e2.set_model(spec.cov_kind, spec.degree, spec.ard, spec.mean_kind, spec.noise_params)
+    e2.set_data(X, y, None)
+    part = e2.nlz_batch(hyp, want_grad=True)
+    np.testing.assert_array_equal(part[0], full[0])
+    np.testing.assert_array_equal(part[1], full[1])
+    e2.close()
+
+
+def test_predict_many_points_and_wide_inputs(eng):
+    """More test points than one chunk (8192) and the widest supported input (D = 32)."""
+    rng = np.random.default_rng(9)
+    N, D = 150, 32
+    X = rng.uniform(-1, 1, (N, D))
+    y = np.sin(X[:, :3].sum(1)).reshape(-1, 1)
+    spec = orc.ModelSpec(D=D, cov_kind=0, ard=True, mean_kind=2)
+    hyp = np.concatenate([np.log(2.0) + 0.1 * rng.standard_normal((2, D)), np.zeros((2, 1)),
+                          np.full((2, 1), np.log(0.1)), np.zeros((2, 1)), 0.1 * rng.standard_normal((2, D)),
+                          np.full((2, D), np.log(3.0))], axis=1)
+    setup_engine(eng, spec, X, y, None)
+    nlz, dnlz, _, status = eng.nlz_batch(hyp, want_grad=True)
+    ref_nlz, ref_dnlz = orc.nlz_batch(spec, hyp, X, y, None, True)
+    assert not status.any() and rel_err(nlz, ref_nlz) <= TOL_NLZ and grad_err(dnlz, ref_dnlz) <= TOL_GRAD
+    post = eng.posterior_batch(hyp)
+    Xs = rng.uniform(-1, 1, (20000, D))
+    mu, v = eng.predict(post, Xs)
+    rmu, rv = orc.predict(spec, orc.posterior_batch(spec, hyp, X, y, None), X, y, Xs)
+    assert np.max(np.abs(mu - rmu)) <= TOL_PRED * (1 + np.max(np.abs(rmu)))
+    assert np.max(np.abs(v - rv)) <= TOL_PRED * np.max(np.abs(rv))
+    post.free()
+    with pytest.raises(Exception, match="D > 32"):
+        eng.set_data(np.zeros((4, 33)), np.zeros(4), None)
+
+
+def test_runs_on_a_torch_stream(eng):
+    """gpb_set_stream: work is enqueued on the caller's stream (what bench.py times)."""
+    import torch
+    from bench import benign_hyp, synth_data
+    spec = orc.ModelSpec(D=2, cov_kind=0, ard=True, mean_kind=0)
+    X, y = synth_data(200, 2, seed=0)
+    hyp = benign_hyp(spec, 3, y, seed=1)
+    setup_engine(eng, spec, X, y, None)
+    ref = eng.nlz_batch(hyp, want_grad=True)
+    s = torch.cuda.Stream()
+    eng.set_stream(s.cuda_stream)
+    d_hyp = torch.from_numpy(hyp).cuda()
+    d_nlz = torch.empty(3, dtype=torch.float64, device="cuda")
+    d_dnlz = torch.empty((3, hyp.shape[1]), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    eng.nlz_batch_dev(d_hyp.data_ptr(), 3, True, d_nlz.data_ptr(), d_dnlz.data_ptr())
+    s.synchronize()
+    np.testing.assert_array_equal(d_nlz.cpu().numpy(), ref[0])
+    np.testing.assert_array_equal(d_dnlz.cpu().numpy(), ref[1])
+    eng.set_stream(0)
