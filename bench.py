@@ -192,7 +192,9 @@ def run_reference(args, wl):
 
 
 def metric_name(wl):
-    return "nlZ+grad evals/s" if wl["kind"] == "nlz" else "predict test points/s"
+    if wl["kind"] == "predict":
+        return "predict pts/s (N=%d, D=%d, FP64)" % (wl["N"], wl["spec"].D)
+    return "nlZ+grad evals/s @N=%d,D=%d FP64" % (wl["N"], wl["spec"].D)
 
 
 # ----------------------------------------------------------------------------- GPU arm
