@@ -229,8 +229,9 @@ def run_b200(args, wl):
         raise SystemExit("bench.py: no CUDA device; gpyreg_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
+    # NCCL prints its version banner on stdout when NCCL_DEBUG is set in the environment:
+    # divert it so stdout carries only the one JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_debug.%h.%p.log")
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     spec, N, B = wl["spec"], wl["N"], (args.batch or wl["B"])
