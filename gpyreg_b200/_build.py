@@ -19,11 +19,22 @@ def _sources():
     return out
 
 
+def _source_hash():
+    import hashlib
+    h = hashlib.sha256()
+    for path in _sources():
+        with open(path, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def is_stale():
-    if not os.path.exists(LIB):
+    """The library is stale when the sources it was built from changed (content hash kept
+    next to the .so; file times do not survive the copy to the GPU box)."""
+    if not os.path.exists(LIB) or not os.path.exists(LIB + ".srchash"):
         return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(s) > t for s in _sources())
+    with open(LIB + ".srchash") as f:
+        return f.read().strip() != _source_hash()
 
 
 def build_library(force=False, verbose=False):
@@ -40,6 +51,8 @@ def build_library(force=False, verbose=False):
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
     os.replace(LIB + ".tmp", LIB)
+    with open(LIB + ".srchash", "w") as f:
+        f.write(_source_hash() + "\n")
     return LIB
 
 

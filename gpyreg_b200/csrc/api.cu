@@ -109,36 +109,53 @@ static inline unsigned grid1d(long long n, int block = 256) {
   return (unsigned)std::min<long long>((n + block - 1) / block, 148LL * 16);
 }
 
+// CTA shapes of the tile GEMM (see gemm.cuh)
+enum Shape { SHAPE_SPLIT_N = 0, SHAPE_SPLIT_M = 1, SHAPE_WIDE = 2 };
+
+template <class Op, int BM_, int BN_>
+static cudaError_t gemm_attr_shape() {
+  cudaError_t e = cudaFuncSetAttribute(gemm_nt_kernel<Op, BM_, BN_, 0>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)gemm_smem<BM_, BN_>());
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(gemm_nt_kernel<Op, BM_, BN_, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)gemm_smem<BM_, BN_>());
+}
 template <class Op>
 static cudaError_t gemm_attr() {
-  cudaError_t e;
-  e = cudaFuncSetAttribute(gemm_nt_kernel<Op, 128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<128>());
+  cudaError_t e = gemm_attr_shape<Op, 128, 128>();
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(gemm_nt_kernel<Op, 64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<64>());
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(gemm_nt_kernel<Op, 128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<128>());
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(gemm_nt_kernel<Op, 64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<64>());
+  return gemm_attr_shape<Op, 128, 64>();
 }
-// grid.x counts logical 128x128 tiles; the BN_=64 variant launches two CTAs per tile.
-// `wide` forces the one-CTA-per-tile kernel (needed when the product is done in place).
+
+template <class Op, int BM_, int BN_>
+static void launch_shape(gpb_ctx* ctx, const Op& op, dim3 grid, bool tma) {
+  grid.x *= (BM / BM_) * (BN / BN_);
+  if (tma) gemm_nt_kernel<Op, BM_, BN_, 1><<<grid, GEMM_THREADS, gemm_smem<BM_, BN_>(), ctx->stream>>>(op);
+  else gemm_nt_kernel<Op, BM_, BN_, 0><<<grid, GEMM_THREADS, gemm_smem<BM_, BN_>(), ctx->stream>>>(op);
+  LAUNCHED(ctx);
+}
+
+// grid.x counts logical 128x128 tiles; the split shapes launch two CTAs per tile.
 template <class Op>
-static void launch_gemm(gpb_ctx* ctx, const Op& op, dim3 grid, bool wide = false) {
+static void launch_gemm(gpb_ctx* ctx, const Op& op, dim3 grid) {
   if (Op::SLOT_MAJOR) grid = dim3(grid.y, grid.x);      // slot in x, tile in y (see gemm.cuh)
+  const bool two = ctx->gemm_bn != 128;
   // TMA bulk copies win when the launch fills the machine (>= 2 CTAs per SM); a lone CTA on an
   // SM hides latency better with per-thread cp.async (measured: B=1 triangular inverse)
-  const bool two = !(wide || ctx->gemm_bn == 128);
   const long long ctas = (long long)grid.x * grid.y * grid.z * (two ? 2 : 1);
   const bool tma = ctx->loader == 1 || (ctx->loader == 2 && ctas >= 2 * 148);
-  if (!two) {
-    if (tma) gemm_nt_kernel<Op, 128, 1><<<grid, GEMM_THREADS, gemm_smem<128>(), ctx->stream>>>(op);
-    else gemm_nt_kernel<Op, 128, 0><<<grid, GEMM_THREADS, gemm_smem<128>(), ctx->stream>>>(op);
-  } else {
-    grid.x *= 2;
-    if (tma) gemm_nt_kernel<Op, 64, 1><<<grid, GEMM_THREADS, gemm_smem<64>(), ctx->stream>>>(op);
-    else gemm_nt_kernel<Op, 64, 0><<<grid, GEMM_THREADS, gemm_smem<64>(), ctx->stream>>>(op);
-  }
-  LAUNCHED(ctx);
+  if (two) launch_shape<Op, 128, 64>(ctx, op, grid, tma);
+  else launch_shape<Op, 128, 128>(ctx, op, grid, tma);
+}
+
+// the in-place potrf panel: row halves (64x128) keep it race-free with two CTAs per SM
+static void launch_panel(gpb_ctx* ctx, const OpPanel& op, dim3 grid) {
+  const bool two = ctx->gemm_bn != 128;
+  const long long ctas = (long long)grid.x * grid.y * (two ? 2 : 1);
+  const bool tma = ctx->loader == 1 || (ctx->loader == 2 && ctas >= 2 * 148);
+  if (two) launch_shape<OpPanel, 64, 128>(ctx, op, grid, tma);
+  else launch_shape<OpPanel, 128, 128>(ctx, op, grid, tma);
 }
 
 constexpr int COV_SMEM_MAX = (2 * MAXD * T + 2 * T + 8 * (MAXD + 2) + 8 * T) * 8;
@@ -164,12 +181,14 @@ static int init_attrs(gpb_ctx* ctx) {
   CK(gemm_attr<OpGeneric>());
   CK(gemm_attr<OpPlain>());
   CK(gemm_attr<OpPanel>());
+  CK((gemm_attr_shape<OpPanel, 64, 128>()));
   CK(gemm_attr<OpSyrk>());
   CK(gemm_attr<OpHpass>());
   CK(gemm_attr<OpWrec>());
   CK(gemm_attr<OpSyrk2>());
   CK(gemm_attr<OpPred>());
   CK(cudaFuncSetAttribute(diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
+  CK(cudaFuncSetAttribute(quad_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (3 * MAXD * T + 10 * T) * 8));
   CK(kind_attrs<0>());
   CK(kind_attrs<1>());
   CK(kind_attrs<3>());
@@ -514,23 +533,9 @@ static void run_potrf(gpb_ctx* ctx, Bufs& b, long long N, const int* sel, int ns
     LAUNCHED(ctx);
     const int n = Nt - k - 1;
     if (n <= 0) break;
-    launch_gemm(ctx, OpPanel{bb, k}, dim3((unsigned)n, (unsigned)nsel), /*wide=*/true);
-    if (with_rhs) {
-      VecArgs va;
-      va.Abuf = b.Abuf;
-      va.DTbuf = b.DTbuf;
-      va.sel = sel;
-      va.smat = b.smat();
-      va.Np = b.Np;
-      va.Nt = b.Nt;
-      va.k = k;
-      va.bvec = b.bvec;
-      va.zvec = b.zvec;
-      va.alpha = b.alpha;
-      va.sp = b.sp;
-      fwd_update_kernel<<<dim3((unsigned)n, (unsigned)nsel), T, 0, ctx->stream>>>(va);
-      LAUNCHED(ctx);
-    }
+    // panel  L_ik = A_ik D_k^T  with the forward-substitution update  b_i -= L_ik z_k  fused in
+    launch_panel(ctx, OpPanel{bb, k, with_rhs ? b.zvec : nullptr, with_rhs ? b.bvec : nullptr},
+                 dim3((unsigned)n, (unsigned)nsel));
     // two-level trailing update (see OpSyrk): inside the outer block only its own columns
     const int ob0 = (k / OB) * OB;                     // first tile column of this outer block
     const int obe = std::min(ob0 + OB, Nt);            // one past its last
@@ -1120,11 +1125,6 @@ extern "C" int gpb_quad(gpb_ctx* ctx, const gpb_post* cpost, const double* mu, c
   double* mupart = ctx->pmu;
   double* vpart = ctx->pmu + (size_t)Nt * McpMax;
   const size_t smem = ((size_t)3 * D * T + 2 * T + 8 * T) * 8;
-  static bool attr_done = false;
-  if (!attr_done) {
-    CK(cudaFuncSetAttribute(quad_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (3 * MAXD * T + 10 * T) * 8));
-    attr_done = true;
-  }
   for (int64_t c0 = 0; c0 < M; c0 += Mc) {
     const int mc = (int)std::min<int64_t>(Mc, M - c0);
     const int Mcp = round_up(mc, T);

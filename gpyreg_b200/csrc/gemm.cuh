@@ -29,6 +29,7 @@ struct GemmTile {
   double* Ct; long long ldct;         // also/only store C(m,n) at Ct[n + m*ldct]
   const double* E; long long lde;     // reduce mode: rowsum[m] = sum_n C(m,n)*E(m,n) (E null: C^2)
   double* rowsum; long long rs_half;  // rs_half: offset between the two column halves
+  const double* vdot; double* vdst;   // GM_ROWDOT: vdst[m] -= sum_n C(m,n) * vdot[n]
   int K;
   int mvalid, nvalid;                 // rows / columns of the 128x128 tile that hold data (rest is padding)
   double alpha, cscale;               // result = alpha * (cscale * C + A B^T); cscale = beta / alpha
@@ -86,58 +87,76 @@ constexpr int GM_STORE = 2;    // normal store
 constexpr int GM_STORET = 4;   // transposed store
 constexpr int GM_REDUCE = 8;   // row-sum epilogue (no store)
 
-template <int BN_>
+constexpr int GM_ROWDOT = 16;  // after the store: vdst[m] -= sum_n C(m,n) * vdot[n]   (fused forward solve)
+
+template <int BM_, int BN_>
 constexpr size_t gemm_smem() {
-  return (size_t)NSTAGE * BK * (PITCH + BN_ + 4) * sizeof(double) + 2 * NSTAGE * sizeof(unsigned long long);
+  return (size_t)NSTAGE * BK * (BM_ + 4 + BN_ + 4) * sizeof(double) + 2 * NSTAGE * sizeof(unsigned long long);
 }
 
-// BN_ = 128: one CTA per SM, 32x64 warp tiles.  BN_ = 64: the logical 128x128 tile is split
-// into two column halves (blockIdx.x = 2*tile + half), 32x32 warp tiles, <= 128 registers and
-// 100 KB of shared memory so TWO CTAs share an SM and one CTA's prologue/epilogue (C tile
-// read/write, pipeline fill) overlaps the other's DMMA main loop.
+// CTA shapes (rows x columns of the logical 128x128 tile handled by one CTA):
+//   128x128  one CTA per SM, 32x64 warp tiles (only where nothing else fits);
+//   128x64   the tile is split into two column halves, 32x32 warp tiles, <= 128 registers and
+//            100 KB of shared memory, so TWO CTAs share an SM and one CTA's prologue/epilogue
+//            (C tile read/write, pipeline fill) overlaps the other's DMMA main loop;
+//    64x128  split into two row halves instead: each CTA reads and writes only its own rows,
+//            which keeps an IN-PLACE product (potrf panel: C aliases A) race-free.
+// blockIdx.x = tile * parts + part.
 // LOADER = 0: every thread streams its share of the operand tiles with 16-byte cp.async
-// (LDGSTS).  LOADER = 1: warp 0 issues TMA bulk copies (cp.async.bulk, one lane per 1 KB /
-// 512 B tile column: 32 copies per stage) and the ring is synchronised with full/empty
-// mbarriers, so the other 7 warps issue no load instructions at all.
-template <class Op, int BN_, int LOADER>
-__global__ void __launch_bounds__(GEMM_THREADS, (BN_ == 64 ? 2 : 1))
+// (LDGSTS).  LOADER = 1: warp 0 issues TMA bulk copies (cp.async.bulk, one lane per tile
+// column: 32 copies per stage) and the ring is synchronised with full/empty mbarriers, so the
+// other 7 warps issue no load instructions at all.
+template <class Op, int BM_, int BN_, int LOADER>
+__global__ void __launch_bounds__(GEMM_THREADS, ((BM_ * BN_ < BM * BN) ? 2 : 1))
 gemm_nt_kernel(const __grid_constant__ Op op) {
   extern __shared__ __align__(16) double gsm[];
-  constexpr int NS = BN / BN_;             // column halves per logical tile
-  constexpr int PB = BN_ + 4;              // pitch of the B tile
-  constexpr int WN = BN_ / 2;              // warp tile width
-  constexpr int NI = WN / 8;
+  constexpr int NSN = BN / BN_, NSM = BM / BM_;       // column / row parts per logical tile
+  constexpr int PA = BM_ + 4, PB = BN_ + 4;           // pitches: fragment loads hit 16 distinct banks
+  constexpr int MW = BM_ / 32, NW = 8 / MW;           // warp grid
+  constexpr int WN = BN_ / NW, NI = WN / 8;           // warp tile 32 x WN
   constexpr int MODE = Op::MODE;
-  // default order: x = (tile, half), y = batch slot.  SLOT_MAJOR ops (tiles of unequal K) put
+  // default order: x = (tile, part), y = batch slot.  SLOT_MAJOR ops (tiles of unequal K) put
   // the slot in x and the tile in y, so the block scheduler hands out the longest tiles of
   // ALL matrices first (longest-processing-time order) instead of matrix after matrix.
-  const int half = (NS > 1) ? (int)(blockIdx.x % NS) : 0;
-  const int bxq = (int)(blockIdx.x / NS);
+  const int part = (int)(blockIdx.x % (NSN * NSM));
+  const int hn = part % NSN, hm = part / NSN;
+  const int bxq = (int)(blockIdx.x / (NSN * NSM));
   GemmTile t = Op::SLOT_MAJOR ? op.resolve((int)blockIdx.y, bxq) : op.resolve(bxq, (int)blockIdx.y);
   if (!t.valid) return;
-  if (NS > 1) {
-    const long long off = (long long)half * BN_;
+  if (NSN > 1) {
+    const long long off = (long long)hn * BN_;
     t.B += off;
     if (t.B0) t.B0 += off;
     if (t.C) t.C += off * t.ldc;
     if (t.Ct) t.Ct += off;
     if (t.E) t.E += off * t.lde;
-    if (t.rowsum) t.rowsum += (long long)half * t.rs_half;
+    if (t.rowsum) t.rowsum += (long long)hn * t.rs_half;
+  }
+  if (NSM > 1) {
+    const long long off = (long long)hm * BM_;
+    t.A += off;
+    if (t.A0) t.A0 += off;
+    if (t.C) t.C += off;
+    if (t.Ct) t.Ct += off * t.ldct;
+    if (t.E) t.E += off;
+    if (t.rowsum) t.rowsum += off;
+    if (t.vdst) t.vdst += off;
   }
   // Padding: a CTA whose rows or columns are all padding has nothing to do; inside a CTA the
   // warps whose 32 x WN sub-tile is all padding skip their loads, DMMAs and stores (the padded
   // part of every operand is zero / identity, so the skipped results would be unchanged).
-  const int nv = t.nvalid - half * BN_;
-  if (!(MODE & GM_REDUCE) && (t.mvalid <= 0 || nv <= 0)) return;
+  const int nv = t.nvalid - hn * BN_;
+  const int mv = t.mvalid - hm * BM_;
+  if (!(MODE & GM_REDUCE) && (mv <= 0 || nv <= 0)) return;
 
   double* As = gsm;
-  double* Bs = gsm + NSTAGE * BK * PITCH;
+  double* Bs = gsm + NSTAGE * BK * PA;
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, tq = lane & 3;
-  const int wm = (warp & 3) * 32, wn = (warp >> 2) * WN;
+  const int wm = (warp % MW) * 32, wn = (warp / MW) * WN;
   const int KT = t.K / BK;
-  const bool wact = (wm < t.mvalid) && (wn < nv);
+  const bool wact = (wm < mv) && (wn < nv);
 
   auto load_stage = [&](int kt, int stage) {
     const int k0 = kt * BK;
@@ -147,22 +166,22 @@ gemm_nt_kernel(const __grid_constant__ Op op) {
     const double* Bp = (alt && t.B0) ? t.B0 : t.B;
     const long long lb = (alt && t.B0) ? t.ldb0 : t.ldb;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < BM_ / 32; ++i) {
       const int c = tid + GEMM_THREADS * i;
-      const int kk = c >> 6, mc = (c & 63) * 2;
-      cp_async16(As + (stage * BK + kk) * PITCH + mc, Ap + (long long)(k0 + kk) * la + mc);
+      const int kk = c / (BM_ / 2), mc = (c % (BM_ / 2)) * 2;
+      cp_async16(As + (stage * BK + kk) * PA + mc, Ap + (long long)(k0 + kk) * la + mc);
     }
 #pragma unroll
-    for (int i = 0; i < 4 / NS; ++i) {
+    for (int i = 0; i < BN_ / 32; ++i) {
       const int c = tid + GEMM_THREADS * i;
       const int kk = c / (BN_ / 2), nc = (c % (BN_ / 2)) * 2;
       cp_async16(Bs + (stage * BK + kk) * PB + nc, Bp + (long long)(k0 + kk) * lb + nc);
     }
   };
 
-  unsigned long long* full_bar = reinterpret_cast<unsigned long long*>(gsm + NSTAGE * BK * (PITCH + PB));
+  unsigned long long* full_bar = reinterpret_cast<unsigned long long*>(gsm + NSTAGE * BK * (PA + PB));
   unsigned long long* empty_bar = full_bar + NSTAGE;
-  constexpr unsigned STAGE_BYTES = BK * (BM + BN_) * sizeof(double);
+  constexpr unsigned STAGE_BYTES = BK * (BM_ + BN_) * sizeof(double);
   // called by all 32 lanes of warp 0: lane l copies tile column (l & 15) of A (l < 16) or B
   auto bulk_stage = [&](int kt, int stage) {
     const int k0 = kt * BK;
@@ -175,7 +194,7 @@ gemm_nt_kernel(const __grid_constant__ Op op) {
     __syncwarp();
     const int kk = lane & (BK - 1);
     if (lane < BK)
-      bulk_g2s(As + (stage * BK + kk) * PITCH, Ap + (long long)(k0 + kk) * la, BM * 8, full_bar + stage);
+      bulk_g2s(As + (stage * BK + kk) * PA, Ap + (long long)(k0 + kk) * la, BM_ * 8, full_bar + stage);
     else
       bulk_g2s(Bs + (stage * BK + kk) * PB, Bp + (long long)(k0 + kk) * lb, BN_ * 8, full_bar + stage);
   };
@@ -201,11 +220,12 @@ gemm_nt_kernel(const __grid_constant__ Op op) {
       cp_async_commit();
     }
   }
+
   // thread owns C(m = wm + mi*8 + g, n = wn + ni*8 + 2*tq + {0,1})
   double acc[4][NI][2];
   if ((MODE & GM_BETA) && wact) {
-    // start from (beta/alpha) * C: the loads go straight into the accumulator registers and
-    // overlap the pipeline fill, instead of a latency-bound read-modify-write epilogue
+    // start from cscale * C: the loads go straight into the accumulator registers and overlap
+    // the pipeline fill, instead of a latency-bound read-modify-write epilogue
     const double f = t.cscale;
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
@@ -239,21 +259,21 @@ gemm_nt_kernel(const __grid_constant__ Op op) {
       if (nk < KT) load_stage(nk, nk % NSTAGE);
       cp_async_commit();
     }
-    const double* as = As + (kt % NSTAGE) * BK * PITCH;
+    const double* as = As + (kt % NSTAGE) * BK * PA;
     const double* bs = Bs + (kt % NSTAGE) * BK * PB;
     if (wact) {
 #pragma unroll
-    for (int k4 = 0; k4 < BK / 4; ++k4) {
-      double a[4], b[NI];
+      for (int k4 = 0; k4 < BK / 4; ++k4) {
+        double a[4], b[NI];
 #pragma unroll
-      for (int mi = 0; mi < 4; ++mi) a[mi] = as[(k4 * 4 + tq) * PITCH + wm + mi * 8 + g];
+        for (int mi = 0; mi < 4; ++mi) a[mi] = as[(k4 * 4 + tq) * PA + wm + mi * 8 + g];
 #pragma unroll
-      for (int ni = 0; ni < NI; ++ni) b[ni] = bs[(k4 * 4 + tq) * PB + wn + ni * 8 + g];
+        for (int ni = 0; ni < NI; ++ni) b[ni] = bs[(k4 * 4 + tq) * PB + wn + ni * 8 + g];
 #pragma unroll
-      for (int mi = 0; mi < 4; ++mi)
+        for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < NI; ++ni) dmma8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
-    }
+          for (int ni = 0; ni < NI; ++ni) dmma8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+      }
     }
     if (LOADER == 1) {                       // this warp is done with the slot
       __syncwarp();
@@ -265,7 +285,7 @@ gemm_nt_kernel(const __grid_constant__ Op op) {
   // ---- epilogue
   if (MODE & GM_REDUCE) {
     __syncthreads();            // all warps done with the ring; reuse it for the N-direction reduce
-    double* red = gsm;          // [2][BM]
+    double* red = gsm;          // [NW][BM_]
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi) {
       const int m = wm + mi * 8 + g;
@@ -282,31 +302,66 @@ gemm_nt_kernel(const __grid_constant__ Op op) {
       }
       s += __shfl_xor_sync(0xffffffffu, s, 1);
       s += __shfl_xor_sync(0xffffffffu, s, 2);
-      if (tq == 0) red[(warp >> 2) * BM + m] = s;
+      if (tq == 0) red[(warp / MW) * BM_ + m] = s;
     }
     __syncthreads();
-    if (tid < BM) t.rowsum[tid] = red[tid] + red[BM + tid];
+    if (tid < BM_) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) s += red[w * BM_ + tid];
+      t.rowsum[tid] = s;
+    }
     return;
   }
-  if (!wact) return;
+  if (wact) {
 #pragma unroll
-  for (int mi = 0; mi < 4; ++mi) {
-    const int m = wm + mi * 8 + g;
+    for (int mi = 0; mi < 4; ++mi) {
+      const int m = wm + mi * 8 + g;
 #pragma unroll
-    for (int ni = 0; ni < NI; ++ni) {
-      const int n = wn + ni * 8 + 2 * tq;
-      const double c0 = t.alpha * acc[mi][ni][0];
-      const double c1 = t.alpha * acc[mi][ni][1];
-      if (MODE & GM_STORE) {
-        t.C[m + (long long)n * t.ldc] = c0;
-        t.C[m + (long long)(n + 1) * t.ldc] = c1;
-      }
-      if (MODE & GM_STORET) {
-        if (t.Ct) {
-          double2 v = make_double2(c0, c1);
-          *reinterpret_cast<double2*>(t.Ct + n + (long long)m * t.ldct) = v;
+      for (int ni = 0; ni < NI; ++ni) {
+        const int n = wn + ni * 8 + 2 * tq;
+        const double c0 = t.alpha * acc[mi][ni][0];
+        const double c1 = t.alpha * acc[mi][ni][1];
+        if (MODE & GM_STORE) {
+          t.C[m + (long long)n * t.ldc] = c0;
+          t.C[m + (long long)(n + 1) * t.ldc] = c1;
+        }
+        if (MODE & GM_STORET) {
+          if (t.Ct) {
+            double2 v = make_double2(c0, c1);
+            *reinterpret_cast<double2*>(t.Ct + n + (long long)m * t.ldct) = v;
+          }
         }
       }
+    }
+  }
+  if (MODE & GM_ROWDOT) {
+    // fused forward substitution: vdst[m] -= sum_n C(m,n) * vdot[n]  (needs all columns of the
+    // tile in this CTA: BN_ == BN), reduced in a fixed order
+    if (t.vdot == nullptr) return;
+    __syncthreads();
+    double* red = gsm;          // [NW][BM_]
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+      const int m = wm + mi * 8 + g;
+      double s = 0.0;
+      if (wact) {
+#pragma unroll
+        for (int ni = 0; ni < NI; ++ni) {
+          const int n = wn + ni * 8 + 2 * tq;
+          s += (t.alpha * acc[mi][ni][0]) * t.vdot[n] + (t.alpha * acc[mi][ni][1]) * t.vdot[n + 1];
+        }
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (tq == 0) red[(warp / MW) * BM_ + m] = s;
+    }
+    __syncthreads();
+    if (tid < BM_ && tid < mv) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) s += red[w * BM_ + tid];
+      t.vdst[tid] -= s;
     }
   }
 }
@@ -338,6 +393,8 @@ __device__ __forceinline__ GemmTile empty_tile() {
   t.lde = 0;
   t.rowsum = nullptr;
   t.rs_half = 0;
+  t.vdot = nullptr;
+  t.vdst = nullptr;
   t.K = 0;
   t.mvalid = BM;
   t.nvalid = BN;
@@ -382,11 +439,13 @@ struct OpPlain {
   }
 };
 
-// potrf panel, step k:  L_ik = A_ik * D_k^T  (i > k), in place
+// potrf panel, step k:  L_ik = A_ik * D_k^T  (i > k), in place; with a right-hand side the
+// forward-substitution update  b_i -= L_ik z_k  rides in the epilogue
 struct OpPanel {
   static constexpr bool SLOT_MAJOR = false;
-  static constexpr int MODE = GM_STORE;
+  static constexpr int MODE = GM_STORE | GM_ROWDOT;
   BatchBufs b; int k;
+  const double* zvec; double* bvec;      // [nslots][Np] or null
   __device__ GemmTile resolve(int bx, int by) const {
     GemmTile t = empty_tile();
     const int slot = b.sel[by];
@@ -397,6 +456,10 @@ struct OpPanel {
     t.C = tile; t.ldc = b.Np;
     t.K = T;
     t.mvalid = b.N - i * T;
+    if (zvec) {
+      t.vdot = zvec + (long long)slot * b.Np + (long long)k * T;
+      t.vdst = bvec + (long long)slot * b.Np + (long long)i * T;
+    }
     return t;
   }
 };
