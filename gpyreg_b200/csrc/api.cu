@@ -568,7 +568,7 @@ static void run_bwd(gpb_ctx* ctx, Bufs& b, const int* sel, int nsel) {
     va.zvec = b.zvec;
     va.alpha = b.alpha;
     va.sp = b.sp;
-    bwd_step_kernel<<<dim3((unsigned)std::max(i, 1), (unsigned)nsel), T, 0, ctx->stream>>>(va);
+    bwd_step_kernel<<<dim3((unsigned)std::max(i, 1), (unsigned)nsel), 256, 0, ctx->stream>>>(va);
     LAUNCHED(ctx);
   }
 }

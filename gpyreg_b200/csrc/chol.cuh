@@ -388,32 +388,58 @@ __global__ void __launch_bounds__(T) fwd_update_kernel(VecArgs a) {
 
 // backward substitution, block row i = a.k (descending): every CTA recomputes
 // w_i = D_i^T b_i; CTA j < i applies b_j -= L_ij^T w_i; CTA 0 stores alpha_i = w_i / sl.
-__global__ void __launch_bounds__(T) bwd_step_kernel(VecArgs a) {
+// 256 threads; loads are issued in batches so many are in flight (the kernel is pure latency).
+__global__ void __launch_bounds__(256) bwd_step_kernel(VecArgs a) {
   __shared__ double w[T];
   __shared__ double bi[T];
+  __shared__ double part[2][T];
   const int slot = a.sel[blockIdx.y];
   const int i = a.k, j = blockIdx.x;
   const int tid = threadIdx.x;
-  bi[tid] = a.bvec[(long long)slot * a.Np + i * T + tid];
+  if (tid < T) bi[tid] = a.bvec[(long long)slot * a.Np + i * T + tid];
   __syncthreads();
-  const double* DT = a.DTbuf + ((long long)slot * a.Nt + i) * T * T;
-  double s = 0.0;
-#pragma unroll 8
-  for (int m = 0; m < T; ++m) s += DT[m * T + tid] * bi[m];       // (D^T b)(n) = sum_m DT(n,m) b(m)
-  w[tid] = s;
-  if (j == 0) a.alpha[(long long)slot * a.Np + i * T + tid] = s / a.sp[slot].sl;   // :2455-2465
+  {
+    // (D^T b)(n) = sum_m DT(n,m) b(m): thread (n, h) sums the m of parity h
+    const double* DT = a.DTbuf + ((long long)slot * a.Nt + i) * T * T;
+    const int n = tid & (T - 1), h = tid >> 7;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll 4
+    for (int m = h; m < T; m += 8) {
+      s0 += DT[m * T + n] * bi[m];
+      s1 += DT[(m + 2) * T + n] * bi[m + 2];
+      s2 += DT[(m + 4) * T + n] * bi[m + 4];
+      s3 += DT[(m + 6) * T + n] * bi[m + 6];
+    }
+    part[h][n] = (s0 + s1) + (s2 + s3);
+  }
+  __syncthreads();
+  if (tid < T) {
+    const double s = part[0][tid] + part[1][tid];
+    w[tid] = s;
+    if (j == 0) a.alpha[(long long)slot * a.Np + i * T + tid] = s / a.sp[slot].sl;   // :2455-2465
+  }
   __syncthreads();
   if (j >= i) return;
-  // (L_ij^T w)(n) = sum_m L(iT+m, jT+n) w(m): one warp per group of columns, lanes over m
+  // (L_ij^T w)(n) = sum_m L(iT+m, jT+n) w(m): 8 warps x 16 columns, lanes over m, 4 columns per pass
   const double* L = a.Abuf + slot * a.smat + (long long)i * T + (long long)j * T * a.Np;
   const int lane = tid & 31, warp = tid >> 5;
-  for (int n = warp; n < T; n += 4) {
-    const double* col = L + (long long)n * a.Np;
-    double v = col[lane] * w[lane] + col[lane + 32] * w[lane + 32] + col[lane + 64] * w[lane + 64] +
-               col[lane + 96] * w[lane + 96];
+  const double w0 = w[lane], w1 = w[lane + 32], w2 = w[lane + 64], w3 = w[lane + 96];
+  for (int n0 = warp * 16; n0 < warp * 16 + 16; n0 += 4) {
+    double v[4];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) a.bvec[(long long)slot * a.Np + j * T + n] -= v;
+    for (int c = 0; c < 4; ++c) {
+      const double* col = L + (long long)(n0 + c) * a.Np;
+      v[c] = col[lane] * w0 + col[lane + 32] * w1 + col[lane + 64] * w2 + col[lane + 96] * w3;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v[c] += __shfl_xor_sync(0xffffffffu, v[c], o);
+    }
+    if (lane < 4) {
+      const double r = (lane == 0) ? v[0] : (lane == 1 ? v[1] : (lane == 2 ? v[2] : v[3]));
+      a.bvec[(long long)slot * a.Np + j * T + n0 + lane] -= r;
+    }
   }
 }
 
