@@ -331,3 +331,43 @@ def test_runs_on_a_torch_stream(eng):
     np.testing.assert_array_equal(d_nlz.cpu().numpy(), ref[0])
     np.testing.assert_array_equal(d_dnlz.cpu().numpy(), ref[1])
     eng.set_stream(0)
+
+
+def test_full_size_properties(eng):
+    """BASELINE.json's headline shape (Matern-5 ARD + NegativeQuadratic, N=5000, D=10), where
+    the CPU oracle needs ~6 s per row: size-independent properties instead of a point-wise oracle.
+      * nlZ and its gradient do not depend on the order of the data rows;
+      * the gradient is the derivative of nlZ (central difference along a random direction);
+      * a row's result does not depend on what else is in the batch;
+      * predictive variances lie in [0, sf^2] and the across-sample average follows :1793-1798."""
+    from bench import benign_hyp, synth_data
+    N, D = 5000, 10
+    spec = orc.ModelSpec(D=D, cov_kind=1, degree=5, ard=True, mean_kind=2)
+    X, y = synth_data(N, D, seed=0)
+    hyp = benign_hyp(spec, 3, y, seed=1)
+    setup_engine(eng, spec, X, y, None)
+    nlz, dnlz, mult, status = eng.nlz_batch(hyp, want_grad=True)
+    assert not status.any() and np.all(mult == 1) and np.all(np.isfinite(dnlz))
+    rng = np.random.default_rng(4)
+    v = rng.standard_normal(hyp.shape[1])
+    v /= np.linalg.norm(v)
+    eps = 1e-5
+    pm = eng.nlz_batch(np.stack([hyp[0] + eps * v, hyp[0] - eps * v]), want_grad=False)[0]
+    fd = (pm[0] - pm[1]) / (2 * eps)
+    assert abs(fd - dnlz[0] @ v) <= 1e-6 * max(1.0, abs(fd))
+    one = eng.nlz_batch(hyp[2:3], want_grad=True)
+    assert one[0][0] == nlz[2] and np.array_equal(one[1][0], dnlz[2])
+    post = eng.posterior_batch(hyp)
+    Xs = rng.uniform(-3, 3, (1000, D))
+    mu_s, s2_s = eng.predict(post, Xs, separate=True)
+    mu_a, s2_a = eng.predict(post, Xs, separate=False)
+    sf2 = np.exp(2 * hyp[:, D])
+    assert np.all(s2_s >= 0) and np.all(s2_s <= sf2[None, :] * (1 + 1e-12))
+    mbar = mu_s.mean(1, keepdims=True)
+    np.testing.assert_allclose(mu_a, mbar, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(s2_a[:, 0], s2_s.mean(1) + ((mu_s - mbar) ** 2).sum(1) / 2, rtol=1e-10)
+    post.free()
+    perm = rng.permutation(N)
+    setup_engine(eng, spec, X[perm], y[perm], None)
+    nlz_p, dnlz_p, _, _ = eng.nlz_batch(hyp[:1], want_grad=True)
+    assert rel_err(nlz_p, nlz[:1]) <= 1e-11 and grad_err(dnlz_p, dnlz[:1]) <= 1e-9

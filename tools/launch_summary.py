@@ -12,8 +12,11 @@ for r in rows:
     if r.get("Metric Name") != "gpu__time_duration.sum":
         continue
     kn = r["Kernel Name"]
-    m = re.search(r"gemm_nt_kernel<(?:gpb::)?(\w+), *(\d+)", kn)
-    name = "gemm_nt_kernel<%s,%s>" % (m.group(1), m.group(2)) if m else re.sub(r"\(.*", "", kn).replace("void ", "")
+    m = re.search(r"gemm_nt_kernel<(?:gpb::)?(\w+), *(?:\(int\))?(\d+), *(?:\(int\))?(\d+), *(?:\(int\))?(\d+)", kn)
+    if m:
+        name = "gemm_nt_kernel<%s,%sx%s,%s>" % (m.group(1), m.group(2), m.group(3), "tma" if m.group(4) == "1" else "cp.async")
+    else:
+        name = re.sub(r"\(.*", "", kn).replace("void ", "")
     agg[name][0] += 1
     agg[name][1] += float(r["Metric Value"]) / 1e3
 tot = sum(v[1] for v in agg.values())
