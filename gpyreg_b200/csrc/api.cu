@@ -69,6 +69,7 @@ struct gpb_post {
   std::vector<int> status;  // 1 = Cholesky failed
   std::vector<double> hyp;  // host copy (B,P)
   bool w_ready = false;
+  double* X = nullptr;      // device copy of the training inputs the factors belong to (N, D)
 };
 
 static std::string g_create_err;
@@ -798,7 +799,14 @@ extern "C" int gpb_posterior_batch(gpb_ctx* ctx, const double* hyp, int64_t B, g
   const Model md = ctx->md;
   size_t freeb = 0, totalb = 0;
   CK(cudaMemGetInfo(&freeb, &totalb));
-  if (per_slot_bytes(ctx->Np, ctx->D, md.P, md.cov_n, true) * (size_t)B > freeb * 0.95)
+  const size_t need = per_slot_bytes(ctx->Np, ctx->D, md.P, md.cov_n, true) * (size_t)B;
+  if (need > freeb * 0.95 && ctx->ws.cap > 0) {
+    // the evaluation workspace is a cache: give it back before giving up
+    CK(cudaStreamSynchronize(ctx->stream));
+    free_bufs(ctx->ws);
+    CK(cudaMemGetInfo(&freeb, &totalb));
+  }
+  if (need > freeb * 0.95)
     FAIL(GPB_ENOMEM, "gpb_posterior_batch: the posterior factors do not fit in device memory");
   gpb_post* post = new gpb_post();
   post->ctx = ctx;
@@ -814,9 +822,16 @@ extern "C" int gpb_posterior_batch(gpb_ctx* ctx, const double* hyp, int64_t B, g
   post->hyp.assign(hyp, hyp + B * md.P);
   auto bail = [&](int code) {
     free_bufs(post->b);
+    if (post->X) cudaFree(post->X);
     delete post;
     return code;
   };
+  {
+    cudaError_t e = cudaMalloc(&post->X, sizeof(double) * ctx->N * ctx->D);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(post->X, ctx->dX, sizeof(double) * ctx->N * ctx->D, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return bail(GPB_ECUDA); }
+  }
   if (md.P > 0) {
     cudaError_t e = cudaMemcpyAsync(b.hyp, hyp, sizeof(double) * B * md.P, cudaMemcpyHostToDevice,
                                     ctx->stream);
@@ -858,6 +873,7 @@ extern "C" void gpb_posterior_free(gpb_post* post) {
   cudaSetDevice(post->ctx->device);
   cudaStreamSynchronize(post->ctx->stream);
   free_bufs(post->b);
+  if (post->X) cudaFree(post->X);
   delete post;
 }
 
@@ -1145,7 +1161,7 @@ extern "C" int gpb_quad(gpb_ctx* ctx, const gpb_post* cpost, const double* mu, c
       qa.Mcp = Mcp;
       qa.mu = dmu;
       qa.sigma = dsg;
-      qa.X = ctx->dX;
+      qa.X = post->X;
       qa.hyp = hyp_s;
       qa.alpha = b.alpha + (size_t)s * Np;
       qa.scale = p.lchol ? 1.0 / sqrt(sn2_eff) : 1.0;
