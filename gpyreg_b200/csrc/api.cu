@@ -172,6 +172,8 @@ static cudaError_t kind_attrs() {
   if (e) return e;
   e = cudaFuncSetAttribute(grad_kernel<KIND, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, COV_SMEM_MAX);
   if (e) return e;
+  e = cudaFuncSetAttribute(grad_kernel<KIND, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, COV_SMEM_MAX);
+  if (e) return e;
   e = cudaFuncSetAttribute(grad_kernel<KIND, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, COV_SMEM_MAX);
   if (e) return e;
   e = cudaFuncSetAttribute(grad_kernel<KIND, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, COV_SMEM_MAX);
@@ -590,11 +592,12 @@ static void run_inverse(gpb_ctx* ctx, Bufs& b, long long N, const int* sel, int 
 
 template <int KIND>
 static void launch_grad(gpb_ctx* ctx, const GradArgs& a, dim3 grid, int ard, int D) {
-  const int dp = !ard ? 0 : (D <= 8 ? 8 : (D <= 16 ? 16 : 32));
+  const int dp = !ard ? 0 : (D <= 8 ? 8 : (D <= 12 ? 12 : (D <= 16 ? 16 : 32)));
   const size_t smem = ((size_t)2 * D * T + 2 * T + 8 * (size_t)((dp ? dp : 1) + 2)) * 8;
   switch (dp) {
     case 0: grad_kernel<KIND, 0><<<grid, 256, smem, ctx->stream>>>(a); break;
     case 8: grad_kernel<KIND, 8><<<grid, 256, smem, ctx->stream>>>(a); break;
+    case 12: grad_kernel<KIND, 12><<<grid, 256, smem, ctx->stream>>>(a); break;
     case 16: grad_kernel<KIND, 16><<<grid, 256, smem, ctx->stream>>>(a); break;
     default: grad_kernel<KIND, 32><<<grid, 256, smem, ctx->stream>>>(a); break;
   }

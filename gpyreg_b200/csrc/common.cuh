@@ -64,7 +64,7 @@ __device__ __forceinline__ double kern_value(double r2, double sf2, double a_rq)
     return sf2 * pow(Mq, -a_rq);                     // :339
   } else {
     double r = sqrt(r2);
-    double f = (KIND == 1) ? 1.0 : (KIND == 3 ? 1 + r : 1 + r * (1 + r / 3));   // :210-218
+    double f = (KIND == 1) ? 1.0 : (KIND == 3 ? 1 + r : 1 + r * (1 + r * (1.0 / 3)));   // :210-218
     return sf2 * f * exp(-r);                        // :259
   }
 }
@@ -85,8 +85,8 @@ __device__ __forceinline__ void kern_value_grad(double r2, double sf2, double a_
   } else {
     double r = sqrt(r2);
     double e = exp(-r);
-    double f = (KIND == 1) ? 1.0 : (KIND == 3 ? 1 + r : 1 + r * (1 + r / 3));
-    double df = (KIND == 1) ? 1.0 / r : (KIND == 3 ? 1.0 : (1 + r) / 3);   // :210-218
+    double f = (KIND == 1) ? 1.0 : (KIND == 3 ? 1 + r : 1 + r * (1 + r * (1.0 / 3)));
+    double df = (KIND == 1) ? 1.0 / r : (KIND == 3 ? 1.0 : (1 + r) * (1.0 / 3));   // :210-218
     K = sf2 * f * e;
     c = sf2 * (df * e);                              // :280 (inf*0 -> NaN for Matern-1 at r=0)
   }

@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(256) build_kernel(BuildArgs a) {
   }
   __syncthreads();
   const SlotP p = a.sp[slot];
+  const double inv_sl = 1.0 / p.sl;      // one reciprocal per CTA instead of a division per element
   const double* sn2v = a.sn2v + (long long)slot * Np;
   double* A = a.Abuf + slot * a.smat;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -206,7 +207,7 @@ __global__ void __launch_bounds__(256) build_kernel(BuildArgs a) {
         } else {
           const double K = kern_value<KIND>(r2[aa][bb], p.sf2, p.rq_a);
           if (p.lchol) {
-            v = K / p.sl;                                            // gaussian_process.py:2416
+            v = K * inv_sl;                                          // gaussian_process.py:2416
             if (gi == gj) v += sn2v[gi] / p.sn2_min;                 // :2409-2412
           } else {
             v = K;                                                   // :2433
@@ -238,7 +239,7 @@ struct GradArgs {
 };
 
 template <int KIND, int DP>
-__global__ void __launch_bounds__(256) grad_kernel(GradArgs a) {
+__global__ void __launch_bounds__(256, (DP <= 16 ? 3 : 2)) grad_kernel(GradArgs a) {
   extern __shared__ double bsm[];
   constexpr int NACC = (DP > 0 ? DP : 1) + 2;      // length scales | sf | rq shape
   const int slot = a.sel[blockIdx.y];
@@ -263,6 +264,7 @@ __global__ void __launch_bounds__(256) grad_kernel(GradArgs a) {
   }
   __syncthreads();
   const SlotP p = a.sp[slot];
+  const double inv_sl = 1.0 / p.sl;      // one reciprocal per CTA instead of a division per element
   const double* Ainv = a.Abuf + slot * a.smat;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
 
@@ -291,7 +293,7 @@ __global__ void __launch_bounds__(256) grad_kernel(GradArgs a) {
       cw[aa] = 0.0;
       if (gi >= N || gi < gj) continue;
       const double w = (gi == gj) ? 0.5 : 1.0;
-      const double Q = w * (Ainv[(long long)gj * Np + gi] / p.sl - al_r[il] * al_c[jl]);   // :2477-2484
+      const double Q = w * (Ainv[(long long)gj * Np + gi] * inv_sl - al_r[il] * al_c[jl]);   // :2477-2484
       double K, c, dshape;
       kern_value_grad<KIND>(r2[aa], p.sf2, p.rq_a, K, c, dshape);
       acc[NACC - 2] += Q * (2 * K);                  // dK/dlog(sf) = 2K
