@@ -46,6 +46,7 @@ SYMBOLS = {
     "gpb_debug_gemm_bench": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     "gpb_last_timings": (C.c_int, [_vp, _vp]),
     "gpb_launch_count": (C.c_int64, [_vp]),
+    "gpb_cache_stats": (C.c_int, [_vp, _vp, _vp]),
 }
 
 _lib = None

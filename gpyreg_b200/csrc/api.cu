@@ -31,7 +31,7 @@ struct Bufs {              // device storage for `cap` batch slots
          *alpha = nullptr, *logdet = nullptr, *mult = nullptr, *hyp = nullptr, *nlz = nullptr,
          *dnlz = nullptr, *gpart = nullptr;
   SlotP* sp = nullptr;
-  int *fail = nullptr, *sel = nullptr, *sel2 = nullptr;
+  int *fail = nullptr, *sel = nullptr, *sel2 = nullptr, *sel3 = nullptr, *sel4 = nullptr;
   long long smat() const { return (long long)Np * Np; }
 };
 
@@ -51,6 +51,17 @@ struct gpb_ctx {
   int outer_block = 4;       // tile columns per outer block of the two-level Cholesky (env GPB_OUTER_BLOCK)
   long long* diag_dbg = nullptr;   // env GPB_DIAG_DBG: phase clock stamps of the diagonal kernel
   Bufs ws;
+  // Factor cache of the last single-chunk nlZ-only call: slot s still holds the Cholesky factor of
+  // hyperparameter row s.  A later row that differs only in its MEAN hyperparameters re-uses it and
+  // replays the O(N^2) forward solve (a slice sampler moves one coordinate at a time).
+  struct {
+    bool valid = false;
+    int n = 0;
+    std::vector<double> key;     // n x (cov_N + noise_N)
+    std::vector<char> ok;
+    long long hits = 0, misses = 0;
+  } cache;
+  bool cache_enabled = true;    // env GPB_NLZ_CACHE=0 disables
   double timings[6] = {0, 0, 0, 0, 0, 0};
   long long launches = 0;
   cudaEvent_t ev[8] = {};
@@ -184,6 +195,8 @@ static int init_attrs(gpb_ctx* ctx) {
   CK(gemm_attr<OpGeneric>());
   CK(gemm_attr<OpPlain>());
   CK(gemm_attr<OpPanel>());
+  CK((gemm_attr_shape<OpFwd, 64, 128>()));
+  CK((gemm_attr_shape<OpFwd, 128, 128>()));
   CK((gemm_attr_shape<OpPanel, 64, 128>()));
   CK(gemm_attr<OpSyrk>());
   CK(gemm_attr<OpHpass>());
@@ -229,6 +242,7 @@ extern "C" int gpb_create(int device, gpb_ctx** out) {
   if (const char* ld = getenv("GPB_LOADER"))
     ctx->loader = (strcmp(ld, "tma") == 0) ? 1 : (strcmp(ld, "cpasync") == 0 ? 0 : 2);
   if (const char* ob = getenv("GPB_OUTER_BLOCK")) ctx->outer_block = std::max(1, atoi(ob));
+  if (const char* nc = getenv("GPB_NLZ_CACHE")) ctx->cache_enabled = atoi(nc) != 0;
   if (getenv("GPB_DIAG_DBG")) cudaMalloc(&ctx->diag_dbg, 40 * sizeof(long long));
   for (auto& ev : ctx->ev) cudaEventCreate(&ev);
   int rc = init_attrs(ctx);
@@ -250,7 +264,7 @@ static void free_bufs(Bufs& b) {
   }
   if (b.sp) cudaFree(b.sp);
   b.sp = nullptr;
-  int** ip[] = {&b.fail, &b.sel, &b.sel2};
+  int** ip[] = {&b.fail, &b.sel, &b.sel2, &b.sel3, &b.sel4};
   for (auto p : ip) {
     if (*p) cudaFree(*p);
     *p = nullptr;
@@ -293,6 +307,13 @@ extern "C" int gpb_set_workspace_limit(gpb_ctx* ctx, uint64_t bytes) {
 
 extern "C" int64_t gpb_launch_count(const gpb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+extern "C" int gpb_cache_stats(const gpb_ctx* ctx, int64_t* hits, int64_t* misses) {
+  if (!ctx || !hits || !misses) return GPB_EINVAL;
+  *hits = ctx->cache.hits;
+  *misses = ctx->cache.misses;
+  return GPB_OK;
+}
+
 extern "C" int gpb_last_timings(const gpb_ctx* ctx, double out[6]) {
   if (!ctx || !out) return GPB_EINVAL;
   for (int i = 0; i < 6; ++i) out[i] = ctx->timings[i];
@@ -329,6 +350,7 @@ extern "C" int gpb_set_model(gpb_ctx* ctx, int cov_kind, int matern_degree, int 
     FAIL(GPB_EINVAL, "gpb_set_model: unsupported model descriptor");
   ctx->md = md;
   ctx->has_model = true;
+  ctx->cache.valid = false;
   return GPB_OK;
 }
 
@@ -353,6 +375,7 @@ extern "C" int gpb_set_data(gpb_ctx* ctx, const double* X, const double* y, cons
   }
   const int Np = round_up(N, T);
   if (Np != ctx->Np || D != ctx->D || N != ctx->N) free_bufs(ctx->ws);   // also re-zeroes the padding
+  ctx->cache.valid = false;
   ctx->N = N;
   ctx->D = D;
   ctx->Np = Np;
@@ -412,6 +435,8 @@ static int alloc_bufs(gpb_ctx* ctx, Bufs& b, int cap, bool with_w, int Np, int D
   CK(cudaMalloc(&b.fail, sizeof(int) * cap));
   CK(cudaMalloc(&b.sel, sizeof(int) * cap));
   CK(cudaMalloc(&b.sel2, sizeof(int) * cap));
+  CK(cudaMalloc(&b.sel3, sizeof(int) * cap));
+  CK(cudaMalloc(&b.sel4, sizeof(int) * cap));
   b.cap = cap;
   b.has_w = with_w;
   return GPB_OK;
@@ -434,6 +459,7 @@ static int ensure_ws(gpb_ctx* ctx, long long B, bool with_w) {
   const long long fit = (long long)(limit / per);
   if (fit < 1) FAIL(GPB_ENOMEM, "workspace for one matrix does not fit in device memory");
   const int want = (int)std::min<long long>(std::min<long long>(B, fit), 32768);
+  ctx->cache.valid = false;
   int rc = alloc_bufs(ctx, w, want, keep_w, ctx->Np, ctx->D, md);
   if (rc != GPB_OK) return rc;
   w.cap_is_max = (want == fit);
@@ -649,22 +675,23 @@ static void run_grad(gpb_ctx* ctx, Bufs& b, const Model& md, long long N, const 
 // Factor `n` slots (hyp already in b.hyp): build + potrf with the reference's x10 jitter
 // retry per element (gaussian_process.py:2413-2421, :2430-2438).  On return b.sel holds the
 // identity list, status_h[s] = 1 for slots that failed all 10 attempts.
-static int factor_with_retry(gpb_ctx* ctx, Bufs& b, const Model& md, long long N, int n, bool write_w,
-                             std::vector<int>& status_h) {
-  std::vector<int> ident(n), failh(n);
-  for (int i = 0; i < n; ++i) ident[i] = i;
-  CK(cudaMemcpyAsync(b.sel, ident.data(), sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
-  fill_kernel<<<grid1d(b.cap), 256, 0, ctx->stream>>>(b.mult, 1.0, b.cap);
+static int factor_with_retry(gpb_ctx* ctx, Bufs& b, const Model& md, long long N,
+                             const std::vector<int>& slots, bool write_w, std::vector<int>& status_h) {
+  if (slots.empty()) return GPB_OK;
+  const int maxslot = *std::max_element(slots.begin(), slots.end()) + 1;
+  std::vector<int> failh(maxslot);
+  CK(cudaMemcpyAsync(b.sel3, slots.data(), sizeof(int) * slots.size(), cudaMemcpyHostToDevice, ctx->stream));
+  set_mult_kernel<<<(unsigned)((slots.size() + 255) / 256), 256, 0, ctx->stream>>>(b.mult, b.fail, b.sel3,
+                                                                                 (int)slots.size(), 1.0);
   LAUNCHED(ctx);
-  CK(cudaMemsetAsync(b.fail, 0, sizeof(int) * b.cap, ctx->stream));
-  status_h.assign(n, 0);
-  const int* sel = b.sel;
-  int nsel = n;
-  std::vector<int> cur = ident;
+  for (int s : slots) status_h[s] = 0;
+  const int* sel = b.sel3;
+  int nsel = (int)slots.size();
+  std::vector<int> cur = slots;
   for (int attempt = 0; attempt < 10; ++attempt) {
     run_prep_build(ctx, b, md, N, sel, nsel);
     run_potrf(ctx, b, N, sel, nsel, write_w);
-    CK(cudaMemcpyAsync(failh.data(), b.fail, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(failh.data(), b.fail, sizeof(int) * maxslot, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     std::vector<int> next;
     for (int s : cur)
@@ -686,6 +713,50 @@ static int factor_with_retry(gpb_ctx* ctx, Bufs& b, const Model& md, long long N
     nsel = (int)next.size();
   }
   return GPB_OK;
+}
+
+// Replay only the forward solve z = L^-1 (y - m) on slots whose factor is cached (their
+// covariance and noise hyperparameters are unchanged): O(N^2) instead of O(N^3).
+static void run_solve_only(gpb_ctx* ctx, Bufs& b, const Model& md, long long N, const int* sel, int nsel) {
+  PrepArgs pa;
+  pa.md = md;
+  pa.N = (int)N;
+  pa.Np = b.Np;
+  pa.X = ctx->dX;
+  pa.y = ctx->dy;
+  pa.s2 = ctx->ds2;
+  pa.hyp = b.hyp;
+  pa.sel = sel;
+  pa.mult = b.mult;
+  pa.xs = b.xs;
+  pa.resid = b.resid;
+  pa.sn2v = b.sn2v;
+  pa.sp = b.sp;
+  prep_kernel<<<nsel, 256, 0, ctx->stream>>>(pa);
+  LAUNCHED(ctx);
+  copy_kernel<<<grid1d((long long)b.Np * b.cap), 256, 0, ctx->stream>>>(b.bvec, b.resid, (long long)b.Np * b.cap);
+  LAUNCHED(ctx);
+  const BatchBufs bb = batch_bufs(b, sel, N);
+  for (int k = 0; k < b.Nt; ++k) {
+    DiagSolveArgs da;
+    da.Dbuf = b.Dbuf;
+    da.sel = sel;
+    da.Np = b.Np;
+    da.Nt = b.Nt;
+    da.N = (int)N;
+    da.k = k;
+    da.bvec = b.bvec;
+    da.zvec = b.zvec;
+    diag_solve_kernel<<<nsel, T, 0, ctx->stream>>>(da);
+    LAUNCHED(ctx);
+    const int n = b.Nt - k - 1;
+    if (n <= 0) break;
+    // same CTA shape as the fused panel, so the reduction order (and every bit) is the same
+    dim3 grid((unsigned)n, (unsigned)nsel);
+    const OpFwd op{bb, k, b.zvec, b.bvec};
+    if (ctx->gemm_bn != 128) launch_shape<OpFwd, 64, 128>(ctx, op, grid, false);
+    else launch_shape<OpFwd, 128, 128>(ctx, op, grid, false);
+  }
 }
 
 // ---------------------------------------------------------------------------------
@@ -714,8 +785,40 @@ static int nlz_batch_impl(gpb_ctx* ctx, const double* hyp, bool hyp_on_device, i
     const int n = (int)std::min<int64_t>(b.cap, B - row0);
     if (P > 0) CK(cudaMemcpyAsync(b.hyp, hyp + row0 * P, sizeof(double) * n * P, kin, ctx->stream));
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-    rc = factor_with_retry(ctx, b, md, ctx->N, n, want_grad != 0, status_h);
-    if (rc != GPB_OK) return rc;
+    {
+      std::vector<int> ident(n);
+      for (int i = 0; i < n; ++i) ident[i] = i;
+      CK(cudaMemcpyAsync(b.sel, ident.data(), sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
+      status_h.assign(n, 0);
+      // which rows can re-use the factor still sitting in their slot?
+      const int kn = md.cov_n + md.noise_n;
+      const bool cacheable = ctx->cache_enabled && !hyp_on_device && !want_grad && B <= b.cap;
+      std::vector<int> miss, hit;
+      for (int sidx = 0; sidx < n; ++sidx) {
+        bool h = cacheable && ctx->cache.valid && sidx < ctx->cache.n && ctx->cache.ok[sidx];
+        if (h) h = memcmp(&ctx->cache.key[(size_t)sidx * kn], hyp + (row0 + sidx) * P, sizeof(double) * kn) == 0;
+        (h ? hit : miss).push_back(sidx);
+      }
+      ctx->cache.hits += (long long)hit.size();
+      ctx->cache.misses += (long long)miss.size();
+      ctx->cache.valid = false;                  // stays invalid if anything below fails
+      rc = factor_with_retry(ctx, b, md, ctx->N, miss, want_grad != 0, status_h);
+      if (rc != GPB_OK) return rc;
+      if (!hit.empty()) {
+        CK(cudaMemcpyAsync(b.sel4, hit.data(), sizeof(int) * hit.size(), cudaMemcpyHostToDevice, ctx->stream));
+        run_solve_only(ctx, b, md, ctx->N, b.sel4, (int)hit.size());
+      }
+      if (cacheable) {
+        ctx->cache.key.resize((size_t)std::max(n, ctx->cache.n) * kn);
+        ctx->cache.ok.resize((size_t)std::max(n, ctx->cache.n), 0);
+        for (int sidx : miss) {
+          memcpy(&ctx->cache.key[(size_t)sidx * kn], hyp + (row0 + sidx) * P, sizeof(double) * kn);
+          ctx->cache.ok[sidx] = status_h[sidx] == 0;
+        }
+        ctx->cache.n = std::max(n, ctx->cache.n);
+        ctx->cache.valid = true;
+      }
+    }
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     NlzArgs na;
     na.sel = b.sel;
@@ -807,6 +910,7 @@ extern "C" int gpb_posterior_batch(gpb_ctx* ctx, const double* hyp, int64_t B, g
     // the evaluation workspace is a cache: give it back before giving up
     CK(cudaStreamSynchronize(ctx->stream));
     free_bufs(ctx->ws);
+    ctx->cache.valid = false;
     CK(cudaMemGetInfo(&freeb, &totalb));
   }
   if (need > freeb * 0.95)
@@ -840,8 +944,15 @@ extern "C" int gpb_posterior_batch(gpb_ctx* ctx, const double* hyp, int64_t B, g
                                     ctx->stream);
     if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return bail(GPB_ECUDA); }
   }
-  rc = factor_with_retry(ctx, b, md, ctx->N, (int)B, true, post->status);
-  if (rc != GPB_OK) return bail(rc);
+  {
+    std::vector<int> ident((size_t)B);
+    for (int i = 0; i < (int)B; ++i) ident[i] = i;
+    cudaError_t e = cudaMemcpyAsync(b.sel, ident.data(), sizeof(int) * B, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return bail(GPB_ECUDA); }
+    post->status.assign((size_t)B, 0);
+    rc = factor_with_retry(ctx, b, md, ctx->N, ident, true, post->status);
+    if (rc != GPB_OK) return bail(rc);
+  }
   run_bwd(ctx, b, b.sel, (int)B);
   post->sp.resize(B);
   cudaError_t e = cudaMemcpyAsync(post->sp.data(), b.sp, sizeof(SlotP) * B, cudaMemcpyDeviceToHost,

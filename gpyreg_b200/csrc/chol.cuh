@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
     const int rr = tid;
     double s = 0.0;
     if (rr < nact)
-      for (int c = 0; c <= rr; ++c) s += Dval(rr, c) * bsh[c];
+      for (int c = 0; c <= rr; ++c) s = __fma_rn(Dval(rr, c), bsh[c], s);   // same order as diag_solve_kernel
     a.zvec[(long long)slot * Np + k * T + rr] = s;
   }
   __syncthreads();
@@ -360,6 +360,27 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
     for (int i = 0; i < nst; ++i) a.dbg[1 + i] = stamps[i];
   }
 #undef STAMP
+}
+
+// z_k = D_k b_k on an existing factor (solve-only replay; same arithmetic as diag_kernel's tail)
+struct DiagSolveArgs {
+  const double* Dbuf; const int* sel;
+  int Np, Nt, N, k;
+  const double* bvec; double* zvec;
+};
+
+__global__ void __launch_bounds__(T) diag_solve_kernel(DiagSolveArgs a) {
+  __shared__ double bsh[T];
+  const int slot = a.sel[blockIdx.x];
+  const int rr = threadIdx.x;
+  const int nact = min(T, a.N - a.k * T);
+  bsh[rr] = a.bvec[(long long)slot * a.Np + a.k * T + rr];
+  __syncthreads();
+  const double* Dk = a.Dbuf + ((long long)slot * a.Nt + a.k) * T * T;
+  double s = 0.0;
+  if (rr < nact)
+    for (int c = 0; c <= rr; ++c) s = __fma_rn(Dk[c * T + rr], bsh[c], s);
+  a.zvec[(long long)slot * a.Np + a.k * T + rr] = s;
 }
 
 struct VecArgs {
@@ -499,6 +520,10 @@ __global__ void fill_kernel(double* p, double v, long long n) {
 __global__ void copy_kernel(double* dst, const double* src, long long n) {
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
        e += (long long)gridDim.x * blockDim.x) dst[e] = src[e];
+}
+__global__ void set_mult_kernel(double* mult, int* fail, const int* sel, int nsel, double v) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < nsel) { mult[sel[t]] = v; fail[sel[t]] = 0; }
 }
 __global__ void scale_mult_kernel(double* mult, const int* fail, const int* sel, int nsel) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;

@@ -349,7 +349,9 @@ gemm_nt_kernel(const __grid_constant__ Op op) {
 #pragma unroll
         for (int ni = 0; ni < NI; ++ni) {
           const int n = wn + ni * 8 + 2 * tq;
-          s += (t.alpha * acc[mi][ni][0]) * t.vdot[n] + (t.alpha * acc[mi][ni][1]) * t.vdot[n + 1];
+          // explicit FMAs: every instantiation (fused panel, solve-only replay) rounds identically
+          s = __fma_rn(t.alpha * acc[mi][ni][0], t.vdot[n], s);
+          s = __fma_rn(t.alpha * acc[mi][ni][1], t.vdot[n + 1], s);
         }
       }
       s += __shfl_xor_sync(0xffffffffu, s, 1);
@@ -460,6 +462,30 @@ struct OpPanel {
       t.vdot = zvec + (long long)slot * b.Np + (long long)k * T;
       t.vdst = bvec + (long long)slot * b.Np + (long long)i * T;
     }
+    return t;
+  }
+};
+
+// forward substitution only, on an existing factor:  b_i -= L_ik z_k  through the SAME epilogue
+// as the fused panel (K = 0: the accumulators are just the stored L_ik), so replaying the solve
+// for a new right-hand side is bit-identical to a full evaluation
+struct OpFwd {
+  static constexpr bool SLOT_MAJOR = false;
+  static constexpr int MODE = GM_BETA | GM_ROWDOT;
+  BatchBufs b; int k;
+  const double* zvec; double* bvec;
+  __device__ GemmTile resolve(int bx, int by) const {
+    GemmTile t = empty_tile();
+    const int slot = b.sel[by];
+    const int i = k + 1 + bx;
+    double* tile = b.Abuf + slot * b.smat + (long long)i * T + (long long)k * T * b.Np;
+    t.A = tile; t.lda = b.Np;
+    t.B = tile; t.ldb = b.Np;
+    t.C = tile; t.ldc = b.Np;
+    t.K = 0; t.cscale = 1.0;
+    t.mvalid = b.N - i * T;
+    t.vdot = zvec + (long long)slot * b.Np + (long long)k * T;
+    t.vdst = bvec + (long long)slot * b.Np + (long long)i * T;
     return t;
   }
 };

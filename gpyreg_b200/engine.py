@@ -229,6 +229,12 @@ class Engine:
     def launch_count(self):
         return int(self.lib.gpb_launch_count(self._h))
 
+    def cache_stats(self):
+        """(hits, misses) of the nlZ factor cache, in hyperparameter rows."""
+        out = np.zeros(2, dtype=np.int64)
+        self._check(self.lib.gpb_cache_stats(self._h, out.ctypes.data, out.ctypes.data + 8))
+        return int(out[0]), int(out[1])
+
 
 _default = None
 

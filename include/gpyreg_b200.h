@@ -149,6 +149,10 @@ int gpb_debug_gemm_bench(gpb_ctx* ctx, int M, int N, int K, int reps, double* ms
 int gpb_last_timings(const gpb_ctx* ctx, double out[6]);
 /* Number of kernels launched by this context so far. */
 int64_t gpb_launch_count(const gpb_ctx* ctx);
+/* Factor cache of gpb_nlz_batch (nlZ-only calls): a row whose covariance and noise
+ * hyperparameters equal those of the row last evaluated in the same batch position re-uses that
+ * Cholesky factor and only replays the O(N^2) forward solve (bit-identical result).  Counts rows. */
+int gpb_cache_stats(const gpb_ctx* ctx, int64_t* hits, int64_t* misses);
 
 #ifdef __cplusplus
 }

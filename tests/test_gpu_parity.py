@@ -371,3 +371,47 @@ def test_full_size_properties(eng):
     setup_engine(eng, spec, X[perm], y[perm], None)
     nlz_p, dnlz_p, _, _ = eng.nlz_batch(hyp[:1], want_grad=True)
     assert rel_err(nlz_p, nlz[:1]) <= 1e-11 and grad_err(dnlz_p, dnlz[:1]) <= 1e-9
+
+
+def test_factor_cache_is_bit_identical(eng):
+    """nlZ-only calls re-use the cached Cholesky factor when only MEAN hyperparameters changed
+    (a slice sampler moves one coordinate at a time) and replay the O(N^2) forward solve: the
+    value must equal a from-scratch evaluation bit for bit, for mean-only, noise and covariance
+    moves, in batches, and after gradient calls invalidate the cache."""
+    from bench import benign_hyp, synth_data
+    from gpyreg_b200 import Engine
+    N, D = 700, 4
+    spec = orc.ModelSpec(D=D, cov_kind=1, degree=5, ard=True, mean_kind=2)
+    X, y = synth_data(N, D, seed=0)
+    base = benign_hyp(spec, 3, y, seed=1)
+    rng = np.random.default_rng(0)
+    cov_n, noise_n = spec.cov_n, spec.noise_n
+    seq = [base.copy()]
+    for step in range(6):
+        h = seq[-1].copy()
+        # mean location, mean location, NOISE, a length scale (COVARIANCE), mean constant, mean scale
+        col = [cov_n + noise_n + 1, cov_n + noise_n + 3, cov_n, 2, cov_n + noise_n, h.shape[1] - 1][step]
+        h[:, col] += 0.05 * rng.standard_normal(3)
+        if step == 1:
+            h[1] = seq[-1][1]                  # one row of the batch unchanged
+        seq.append(h)
+    setup_engine(eng, spec, X, y, None)
+    h0, m0 = eng.cache_stats()
+    got = [eng.nlz_batch(h)[0] for h in seq]
+    h1, m1 = eng.cache_stats()
+    fresh = Engine(0)
+    fresh.set_model(spec.cov_kind, spec.degree, spec.ard, spec.mean_kind, spec.noise_params)
+    fresh.set_data(X, y, None)
+    for h, g in zip(seq, got):
+        ref = fresh.nlz_batch(h, want_grad=True)[0]        # gradient calls never use the cache
+        np.testing.assert_array_equal(g, ref)
+    fresh.close()
+    # moves 1, 2, 5, 6 touch mean hyperparameters only: 4 x 3 rows re-use the factor
+    assert h1 - h0 == 12 and m1 - m0 == 9
+    ref_nlz = orc.nlz_batch(spec, seq[2], X, y, None, False)
+    assert rel_err(got[2], ref_nlz) <= TOL_NLZ
+    # a gradient call overwrites the factors with the inverse: the next nlZ call must not hit
+    eng.nlz_batch(seq[-1], want_grad=True)
+    again = eng.nlz_batch(seq[-1])[0]
+    np.testing.assert_array_equal(again, got[-1])
+    assert eng.cache_stats()[0] == h1
