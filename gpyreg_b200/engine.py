@@ -96,11 +96,25 @@ class Engine:
         self._check(self.lib.gpb_set_workspace_limit(self._h, int(nbytes)))
 
     # -- hot path ---------------------------------------------------------------
-    def nlz_batch(self, hyp, want_grad=False):
-        """-> nlZ (B,), dnlZ (B,P) or None, sn2_mult (B,), status (B,) int32."""
+    def hyp_n(self):
+        """Length of a hyperparameter row for the current model and data: cov | noise | mean."""
+        from .spec import ModelSpec
+        ck, deg, ard, mk, nz = self.model
+        return ModelSpec(D=self.D, cov_kind=ck, degree=deg, ard=bool(ard), mean_kind=mk, noise_params=nz).hyp_n
+
+    def _check_hyp(self, hyp):
         hyp = f64(hyp)
         if hyp.ndim == 1:
             hyp = hyp[None, :]
+        if self.model is None or self.N == 0:
+            raise GpbError(4, "set_model and set_data first")
+        if hyp.ndim != 2 or hyp.shape[1] != self.hyp_n():
+            raise ValueError(f"hyperparameter rows must have {self.hyp_n()} entries, got shape {hyp.shape}")
+        return hyp
+
+    def nlz_batch(self, hyp, want_grad=False):
+        """-> nlZ (B,), dnlZ (B,P) or None, sn2_mult (B,), status (B,) int32."""
+        hyp = self._check_hyp(hyp)
         B, P = hyp.shape
         nlz = np.empty(B)
         dnlz = np.empty((B, P)) if want_grad else None
@@ -116,9 +130,7 @@ class Engine:
                                                d_mult or None, d_status or None))
 
     def posterior_batch(self, hyp):
-        hyp = f64(hyp)
-        if hyp.ndim == 1:
-            hyp = hyp[None, :]
+        hyp = self._check_hyp(hyp)
         h = C.c_void_p()
         self._check(self.lib.gpb_posterior_batch(self._h, ptr(hyp), hyp.shape[0], C.byref(h)))
         return PosteriorBatch(self, h, hyp.shape[0], self.N)

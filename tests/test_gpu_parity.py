@@ -169,6 +169,15 @@ def test_lownoise_golden(eng, golden_lownoise, tag):
     post.free()
 
 
+def test_wrong_hyperparameter_count_is_rejected(eng):
+    spec = orc.ModelSpec(D=2, cov_kind=0, ard=True, mean_kind=1)
+    setup_engine(eng, spec, np.zeros((5, 2)) + np.arange(5)[:, None], np.arange(5.0), None)
+    with pytest.raises(ValueError, match="must have 5 entries"):
+        eng.nlz_batch(np.zeros((2, 4)))
+    with pytest.raises(ValueError, match="must have 5 entries"):
+        eng.posterior_batch(np.zeros(7))
+
+
 def test_cholesky_failure_status(eng):
     """A NaN hyperparameter makes every attempt fail: status 1, nlZ NaN, others unaffected."""
     rng = np.random.default_rng(5)
