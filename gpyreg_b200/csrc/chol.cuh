@@ -1,7 +1,7 @@
 // Panel-level kernels of the batched blocked Cholesky / triangular solves.
 //   diag_kernel       factor one 128x128 diagonal tile in shared memory, invert it, write
 //                     D_k, D_k^T, log-det partial, and the forward-solve block z_k = D_k b_k
-//   fwd_update_kernel b_i -= L_ik z_k                     (forward substitution, i > k)
+//   diag_solve_kernel z_k = D_k b_k on an existing factor (solve-only replay, factor cache)
 //   bwd_step_kernel   w_i = D_i^T b_i ; b_j -= L_ij^T w_i (backward substitution, j < i)
 //   nlz_kernel        nlZ = z^T z/(2 sl) + sum log L_ii + N log(2 pi sl)/2
 // The dense O(N^3) work between these is the tile GEMM in gemm.cuh.
@@ -392,20 +392,6 @@ struct VecArgs {
   double* alpha;             // [nslots][Np]
   const SlotP* sp;
 };
-
-// forward substitution update after step k: b_i -= L_ik z_k, i = k+1+blockIdx.x
-__global__ void __launch_bounds__(T) fwd_update_kernel(VecArgs a) {
-  __shared__ double z[T];
-  const int slot = a.sel[blockIdx.y];
-  const int i = a.k + 1 + blockIdx.x;
-  z[threadIdx.x] = a.zvec[(long long)slot * a.Np + a.k * T + threadIdx.x];
-  __syncthreads();
-  const double* L = a.Abuf + slot * a.smat + (long long)i * T + (long long)a.k * T * a.Np;
-  double s = 0.0;
-#pragma unroll 8
-  for (int q = 0; q < T; ++q) s += L[(long long)q * a.Np + threadIdx.x] * z[q];
-  a.bvec[(long long)slot * a.Np + i * T + threadIdx.x] -= s;
-}
 
 // backward substitution, block row i = a.k (descending): every CTA recomputes
 // w_i = D_i^T b_i; CTA j < i applies b_j -= L_ij^T w_i; CTA 0 stores alpha_i = w_i / sl.
