@@ -173,7 +173,18 @@ class GP:
         body = "Dimension: " + str(self.D) + "\n" + cov + mean + noise + priors + samples
         return "GP:\n" + "".join("    " + ln for ln in body.splitlines(True))
 
-    __repr__ = __str__
+    def __repr__(self):
+        """One ``self.<attribute> = <summary>`` line per public attribute, small arrays printed in
+        full and large ones by shape (the reference's layout, gaussian_process.py:64-80)."""
+        def brief(v):
+            if not isinstance(v, np.ndarray):
+                return repr(v)
+            if v.dtype != object and v.size < 10:
+                return np.array2string(v, precision=4, suppress_small=True, separator=", ") + " : ndarray"
+            return f"{v.shape} ndarray"
+        names = ["D", "covariance", "mean", "noise", "X", "y", "s2", "lower_bounds", "upper_bounds",
+                 "posteriors"]
+        return "GP:\n" + "\n".join(f"    self.{n} = {brief(getattr(self, n))}" for n in names)
 
     # ------------------------------------------------------------------ bounds
     def set_bounds(self, bounds=None):

@@ -59,6 +59,9 @@ def test_counts_and_names():
     with pytest.raises(ValueError, match="Missing hyperparameter"):
         gp.set_bounds({"covariance_log_lengthscale": None})
     assert "Covariance function: RationalQuadraticARD, 5 parameters" in str(gp)
+    r = repr(gp)
+    assert "self.covariance = <gpyreg_b200.covariance_functions.RationalQuadraticARD object at " in r
+    assert "self.lower_bounds = (16,) ndarray" in r and "self.X = None" in r
 
 
 def _prior_gp(h):
