@@ -1,11 +1,19 @@
 #!/bin/bash
-# final evidence for the round: gpu tests, default bench, ncu launch list of the default bench command
+# evidence for the round: gpu tests, benches, ncu launch list of the default bench command,
+# one ncu --set full capture of the dominant kernel
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -q --timeout 900 2>&1 | tail -4
-timeout 600 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "bench exit $?"; cut -c1-300 gpurun_out/bench_default.json
-python -c "import json;d=json.load(open('gpurun_out/bench_default.json'));print('launches per run', d['gpu_launches'], 'steps', d['steps'], 'roofline', d['roofline']['achieved'], d['roofline']['frac'], 'e2e', d['e2e']['value'], 'cpu', d['cpu_baseline'])"
+timeout 1200 python -m pytest tests -m gpu -q --timeout 900 2>&1 | tail -4 | tee gpurun_out/pytest_gpu_tail.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+for wl in cfg3 cfg2 cfg5; do
+  timeout 600 python bench.py --workload $wl > gpurun_out/bench_$wl.json 2> gpurun_out/bench_$wl.err; echo "bench $wl exit $?"
+  python -c "import json;d=json.load(open('gpurun_out/bench_$wl.json'));print(d['metric'], round(d['value'],1), d['unit'], '| e2e', round(d['e2e']['value'],1), '| roofline', round(d['roofline']['achieved'],2), round(d['roofline']['frac'],3), '| cpu', d['cpu_baseline']['value'], '| launches', d['gpu_launches'], '| clocks', d['clocks'])"
+done
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2>/dev/null; cut -c1-200 gpurun_out/bench_ref.json
 CMD="python bench.py --steps 1 --warmup 3"
 $CMD > gpurun_out/plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -s 648 -c 260 --csv --log-file gpurun_out/launches_default.csv $CMD > gpurun_out/ncu_launch.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -s 650 -c 260 --csv --log-file gpurun_out/launches_default.csv $CMD > gpurun_out/ncu_launch.log 2>&1
 echo "ncu launches exit $?"
 python tools/launch_summary.py gpurun_out/launches_default.csv
+$CMD > gpurun_out/plain2.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:gemm_nt_kernel -s 410 -c 5 -o gpurun_out/prof_gemm $CMD > gpurun_out/ncu_full.log 2>&1
+echo "ncu full exit $?"; tail -1 gpurun_out/ncu_full.log | cut -c1-120
