@@ -24,8 +24,20 @@ import scipy.stats
 from .batched_drivers import MultiChainSliceSampler, minimize_lockstep
 from .engine import Engine
 from .f_min_fill import (f_min_fill, smoothbox_cdf, smoothbox_student_t_cdf)
+from .sharding import sharded_nlz, sharded_rows
 from .slice_sample import SliceSampler
 from .spec import ModelSpec
+
+
+def _world_size():
+    """Number of ranks when the process runs under torch.distributed (one process per GPU)."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_world_size()
+    except ImportError:
+        pass
+    return 1
 
 
 def _scipy_at_least(major, minor):
@@ -472,7 +484,15 @@ class GP:
         reference's LinAlgError if any row's Cholesky fails all 10 jitter retries."""
         hyp = np.atleast_2d(np.asarray(hyp, dtype=float))
         eng = self._sync_engine()
-        nlz, dnlz, _, status = eng.nlz_batch(hyp, want_grad=compute_grad)
+        world = _world_size()
+        if world > 1 and hyp.shape[0] >= 2 * world:
+            # one process per GPU, same batch on every rank (same seeds): each rank evaluates its
+            # block of rows and one all-gather returns all of them -- results are bitwise those of
+            # a single-GPU run, because a row's value does not depend on the batch it is in
+            nlz, dnlz, _, status = sharded_nlz(lambda rows, g: eng.nlz_batch(rows, want_grad=g), hyp,
+                                               compute_grad)
+        else:
+            nlz, dnlz, _, status = eng.nlz_batch(hyp, want_grad=compute_grad)
         if status.any():
             raise sp.linalg.LinAlgError("Singular matrix for L Cholesky decomposition")
         if compute_prior:
@@ -585,9 +605,18 @@ class GP:
                 any(p._batch is not batch for p in self.posteriors):
             raise RuntimeError("GP.predict: the posteriors hold no device factors; call "
                                "update(compute_posterior=True) first")
-        return self.engine.predict(batch, x_star, None if y_star is None else y_star.reshape(-1),
-                                   None if s2_star is None else s2_star.reshape(-1),
-                                   add_noise=add_noise, separate=separate_samples, want_lpd=return_lpd)
+        ys = None if y_star is None else y_star.reshape(-1)
+        s2s = None if s2_star is None else s2_star.reshape(-1)
+
+        def run(lo, hi):
+            return self.engine.predict(batch, x_star[lo:hi], None if ys is None else ys[lo:hi],
+                                       None if s2s is None else s2s[lo:hi], add_noise=add_noise,
+                                       separate=separate_samples, want_lpd=return_lpd)
+        world = _world_size()
+        if world > 1 and x_star.shape[0] >= 4096 * world:
+            # test points sharded over the GPUs (every rank holds all posterior samples)
+            return sharded_rows(run, x_star.shape[0])
+        return run(0, x_star.shape[0])
 
     def _predict_prior(self, x_star, y_star, s2_star, add_noise, separate, return_lpd):
         """GP without training data: prior mean and variance through the plugin kernels

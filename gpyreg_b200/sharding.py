@@ -69,28 +69,38 @@ def sharded_nlz(evaluate, hyp, want_grad, group=None):
             full[:, 2].astype(np.int32))
 
 
-def sharded_predict(evaluate, Xs, group=None):
-    """Predictive mean/variance at every row of Xs (M, D); rank r handles test-point block r
-    through ``evaluate(points) -> (mu, s2)`` with all posterior samples replicated on every
-    GPU (so the across-sample average stays local).  Returns (mu, s2) for all M points."""
-    Xs = np.ascontiguousarray(Xs, dtype=np.float64)
-    M = Xs.shape[0]
+def sharded_rows(evaluate, M, group=None):
+    """Generic row-sharded evaluation: rank r calls ``evaluate(lo, hi)`` for its block of the M
+    rows and gets back a tuple of (hi-lo, c_i) arrays; every rank receives the tuple of full
+    (M, c_i) arrays.  Used for predictions over test points (all posterior samples replicated on
+    every GPU, so the across-sample average stays local)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     lo, hi = shard_bounds(M, world)[rank]
+    widths, local = None, None
     if hi > lo:
-        mu, s2 = evaluate(Xs[lo:hi])
-        local = np.concatenate([np.asarray(mu).reshape(hi - lo, -1),
-                                np.asarray(s2).reshape(hi - lo, -1)], axis=1)
-        ncol = local.shape[1]
-    else:
-        ncol, local = None, None
-    if world > 1:                       # agree on the column count (empty shards know nothing)
-        t = torch.tensor([ncol or 0], dtype=torch.int64, device=_device(group))
+        parts = [np.asarray(p, dtype=np.float64).reshape(hi - lo, -1) for p in evaluate(lo, hi)]
+        widths = [p.shape[1] for p in parts]
+        local = np.concatenate(parts, axis=1)
+    if world > 1:                       # agree on the column layout (empty shards know nothing)
+        t = torch.zeros(8, dtype=torch.int64, device=_device(group))
+        if widths is not None:
+            t[0] = len(widths)
+            t[1:1 + len(widths)] = torch.tensor(widths, dtype=torch.int64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
-        ncol = int(t.item())
+        widths = [int(v) for v in t[1:1 + int(t[0])].tolist()]
     if local is None:
-        local = np.zeros((0, ncol))
+        local = np.zeros((0, sum(widths)))
     full = all_gather_rows(local, M, group)
-    h = ncol // 2
-    return full[:, :h], full[:, h:]
+    out, c = [], 0
+    for w in widths:
+        out.append(full[:, c:c + w])
+        c += w
+    return tuple(out)
+
+
+def sharded_predict(evaluate, Xs, group=None):
+    """Predictive mean/variance at every row of Xs (M, D); rank r handles test-point block r
+    through ``evaluate(points) -> (mu, s2)``.  Returns (mu, s2) for all M points."""
+    Xs = np.ascontiguousarray(Xs, dtype=np.float64)
+    return sharded_rows(lambda lo, hi: evaluate(Xs[lo:hi]), Xs.shape[0], group)
