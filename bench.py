@@ -232,6 +232,8 @@ def run_b200(args, wl):
     # NCCL prints its version banner on stdout when NCCL_DEBUG is set in the environment:
     # divert it so stdout carries only the one JSON line
     os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_debug.%h.%p.log")
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ.pop("NCCL_DEBUG")
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     spec, N, B = wl["spec"], wl["N"], (args.batch or wl["B"])
