@@ -28,7 +28,7 @@ struct Bufs {              // device storage for `cap` batch slots
   int Np = 0, Nt = 0, D = 0, P = 0, cov_n = 0;
   double *Abuf = nullptr, *Wbuf = nullptr, *Dbuf = nullptr, *DTbuf = nullptr;
   double *xs = nullptr, *resid = nullptr, *sn2v = nullptr, *bvec = nullptr, *zvec = nullptr,
-         *alpha = nullptr, *logdet = nullptr, *mult = nullptr, *hyp = nullptr, *nlz = nullptr,
+         *alpha = nullptr, *logdet = nullptr, *mult = nullptr, *fmult = nullptr, *hyp = nullptr, *nlz = nullptr,
          *dnlz = nullptr, *gpart = nullptr;
   SlotP* sp = nullptr;
   int *fail = nullptr, *sel = nullptr, *sel2 = nullptr, *sel3 = nullptr, *sel4 = nullptr;
@@ -257,7 +257,7 @@ extern "C" int gpb_create(int device, gpb_ctx** out) {
 
 static void free_bufs(Bufs& b) {
   double** ptrs[] = {&b.Abuf, &b.Wbuf, &b.Dbuf, &b.DTbuf, &b.xs, &b.resid, &b.sn2v, &b.bvec, &b.zvec,
-                     &b.alpha, &b.logdet, &b.mult, &b.hyp, &b.nlz, &b.dnlz, &b.gpart};
+                     &b.alpha, &b.logdet, &b.mult, &b.fmult, &b.hyp, &b.nlz, &b.dnlz, &b.gpart};
   for (auto p : ptrs) {
     if (*p) cudaFree(*p);
     *p = nullptr;
@@ -427,6 +427,7 @@ static int alloc_bufs(gpb_ctx* ctx, Bufs& b, int cap, bool with_w, int Np, int D
   CK(cudaMalloc(&b.alpha, (size_t)Np * 8 * cap));
   CK(cudaMalloc(&b.logdet, nt * 8 * cap));
   CK(cudaMalloc(&b.mult, (size_t)8 * cap));
+  CK(cudaMalloc(&b.fmult, (size_t)8 * cap));   // multiplier of the factor kept in each slot (cache)
   CK(cudaMalloc(&b.hyp, (size_t)std::max(md.P, 1) * 8 * cap));
   CK(cudaMalloc(&b.nlz, (size_t)8 * cap));
   CK(cudaMalloc(&b.dnlz, (size_t)std::max(md.P, 1) * 8 * cap));
@@ -717,7 +718,11 @@ static int factor_with_retry(gpb_ctx* ctx, Bufs& b, const Model& md, long long N
 
 // Replay only the forward solve z = L^-1 (y - m) on slots whose factor is cached (their
 // covariance and noise hyperparameters are unchanged): O(N^2) instead of O(N^3).
-static void run_solve_only(gpb_ctx* ctx, Bufs& b, const Model& md, long long N, const int* sel, int nsel) {
+static void run_solve_only(gpb_ctx* ctx, Bufs& b, const Model& md, long long N, const int* sel,
+                           const int* fsel, int nsel) {
+  // the factor's jitter multiplier belongs to the row as well
+  copy_mult_kernel<<<(unsigned)((nsel + 255) / 256), 256, 0, ctx->stream>>>(b.mult, b.fmult, sel, fsel, nsel);
+  LAUNCHED(ctx);
   PrepArgs pa;
   pa.md = md;
   pa.N = (int)N;
@@ -741,6 +746,7 @@ static void run_solve_only(gpb_ctx* ctx, Bufs& b, const Model& md, long long N, 
     DiagSolveArgs da;
     da.Dbuf = b.Dbuf;
     da.sel = sel;
+    da.fsel = fsel;
     da.Np = b.Np;
     da.Nt = b.Nt;
     da.N = (int)N;
@@ -753,7 +759,7 @@ static void run_solve_only(gpb_ctx* ctx, Bufs& b, const Model& md, long long N, 
     if (n <= 0) break;
     // same CTA shape as the fused panel, so the reduction order (and every bit) is the same
     dim3 grid((unsigned)n, (unsigned)nsel);
-    const OpFwd op{bb, k, b.zvec, b.bvec};
+    const OpFwd op{bb, k, b.zvec, b.bvec, fsel};
     if (ctx->gemm_bn != 128) launch_shape<OpFwd, 64, 128>(ctx, op, grid, false);
     else launch_shape<OpFwd, 128, 128>(ctx, op, grid, false);
   }
@@ -790,24 +796,50 @@ static int nlz_batch_impl(gpb_ctx* ctx, const double* hyp, bool hyp_on_device, i
       for (int i = 0; i < n; ++i) ident[i] = i;
       CK(cudaMemcpyAsync(b.sel, ident.data(), sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
       status_h.assign(n, 0);
-      // which rows can re-use the factor still sitting in their slot?
+      // which rows can re-use a factor still sitting in some workspace slot?  (Rows that differ
+      // only in mean hyperparameters share one factor: all speculative proposals of a slice-
+      // sampling move along a mean coordinate hit the factor of the current point.)
       const int kn = md.cov_n + md.noise_n;
       const bool cacheable = ctx->cache_enabled && !hyp_on_device && !want_grad && B <= b.cap;
-      std::vector<int> miss, hit;
+      std::vector<int> miss, hit, hit_f;
       for (int sidx = 0; sidx < n; ++sidx) {
-        bool h = cacheable && ctx->cache.valid && sidx < ctx->cache.n && ctx->cache.ok[sidx];
-        if (h) h = memcmp(&ctx->cache.key[(size_t)sidx * kn], hyp + (row0 + sidx) * P, sizeof(double) * kn) == 0;
-        (h ? hit : miss).push_back(sidx);
+        int found = -1;
+        if (cacheable && ctx->cache.valid) {
+          const double* key = hyp + (row0 + sidx) * P;
+          auto same = [&](int j) {
+            return j < ctx->cache.n && ctx->cache.ok[j] &&
+                   memcmp(&ctx->cache.key[(size_t)j * kn], key, sizeof(double) * kn) == 0;
+          };
+          if (same(sidx)) found = sidx;
+          for (int j = 0; found < 0 && j < ctx->cache.n; ++j)
+            if (same(j)) found = j;
+        }
+        if (found >= 0) { hit.push_back(sidx); hit_f.push_back(found); }
+        else miss.push_back(sidx);
       }
       ctx->cache.hits += (long long)hit.size();
       ctx->cache.misses += (long long)miss.size();
       ctx->cache.valid = false;                  // stays invalid if anything below fails
+      if (!hit.empty()) {                        // first: the misses below overwrite factor slots
+        CK(cudaMemcpyAsync(b.sel4, hit.data(), sizeof(int) * hit.size(), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(b.sel2, hit_f.data(), sizeof(int) * hit.size(), cudaMemcpyHostToDevice, ctx->stream));
+        run_solve_only(ctx, b, md, ctx->N, b.sel4, b.sel2, (int)hit.size());
+        NlzArgs nh;
+        nh.sel = b.sel4;
+        nh.fsel = b.sel2;
+        nh.N = (int)ctx->N;
+        nh.Np = b.Np;
+        nh.Nt = b.Nt;
+        nh.zvec = b.zvec;
+        nh.logdet = b.logdet;
+        nh.sp = b.sp;
+        nh.nlz = b.nlz;
+        nlz_kernel<<<(unsigned)hit.size(), 256, 0, ctx->stream>>>(nh);
+        LAUNCHED(ctx);
+        CK(cudaStreamSynchronize(ctx->stream));   // sel2 is reused by the retry loop below
+      }
       rc = factor_with_retry(ctx, b, md, ctx->N, miss, want_grad != 0, status_h);
       if (rc != GPB_OK) return rc;
-      if (!hit.empty()) {
-        CK(cudaMemcpyAsync(b.sel4, hit.data(), sizeof(int) * hit.size(), cudaMemcpyHostToDevice, ctx->stream));
-        run_solve_only(ctx, b, md, ctx->N, b.sel4, (int)hit.size());
-      }
       if (cacheable) {
         ctx->cache.key.resize((size_t)std::max(n, ctx->cache.n) * kn);
         ctx->cache.ok.resize((size_t)std::max(n, ctx->cache.n), 0);
@@ -818,19 +850,27 @@ static int nlz_batch_impl(gpb_ctx* ctx, const double* hyp, bool hyp_on_device, i
         ctx->cache.n = std::max(n, ctx->cache.n);
         ctx->cache.valid = true;
       }
+      // nlZ of the freshly factored rows; remember each new factor's jitter multiplier
+      if (!miss.empty()) {
+        CK(cudaMemcpyAsync(b.sel4, miss.data(), sizeof(int) * miss.size(), cudaMemcpyHostToDevice, ctx->stream));
+        copy_mult_kernel<<<(unsigned)((miss.size() + 255) / 256), 256, 0, ctx->stream>>>(
+            b.fmult, b.mult, b.sel4, b.sel4, (int)miss.size());
+        LAUNCHED(ctx);
+        NlzArgs nm;
+        nm.sel = b.sel4;
+        nm.fsel = nullptr;
+        nm.N = (int)ctx->N;
+        nm.Np = b.Np;
+        nm.Nt = b.Nt;
+        nm.zvec = b.zvec;
+        nm.logdet = b.logdet;
+        nm.sp = b.sp;
+        nm.nlz = b.nlz;
+        nlz_kernel<<<(unsigned)miss.size(), 256, 0, ctx->stream>>>(nm);
+        LAUNCHED(ctx);
+      }
     }
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-    NlzArgs na;
-    na.sel = b.sel;
-    na.N = (int)ctx->N;
-    na.Np = b.Np;
-    na.Nt = b.Nt;
-    na.zvec = b.zvec;
-    na.logdet = b.logdet;
-    na.sp = b.sp;
-    na.nlz = b.nlz;
-    nlz_kernel<<<n, 256, 0, ctx->stream>>>(na);
-    LAUNCHED(ctx);
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     if (want_grad) {
       run_bwd(ctx, b, b.sel, n);

@@ -365,6 +365,7 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
 // z_k = D_k b_k on an existing factor (solve-only replay; same arithmetic as diag_kernel's tail)
 struct DiagSolveArgs {
   const double* Dbuf; const int* sel;
+  const int* fsel;                 // slot holding the factor used by entry t (null = its own)
   int Np, Nt, N, k;
   const double* bvec; double* zvec;
 };
@@ -376,7 +377,8 @@ __global__ void __launch_bounds__(T) diag_solve_kernel(DiagSolveArgs a) {
   const int nact = min(T, a.N - a.k * T);
   bsh[rr] = a.bvec[(long long)slot * a.Np + a.k * T + rr];
   __syncthreads();
-  const double* Dk = a.Dbuf + ((long long)slot * a.Nt + a.k) * T * T;
+  const int fslot = a.fsel ? a.fsel[blockIdx.x] : slot;
+  const double* Dk = a.Dbuf + ((long long)fslot * a.Nt + a.k) * T * T;
   double s = 0.0;
   if (rr < nact)
     for (int c = 0; c <= rr; ++c) s = __fma_rn(Dk[c * T + rr], bsh[c], s);
@@ -452,6 +454,7 @@ __global__ void __launch_bounds__(256) bwd_step_kernel(VecArgs a) {
 
 struct NlzArgs {
   const int* sel;
+  const int* fsel;   // optional: slot whose factor (log-det partials) entry t uses; null = its own
   int N, Np, Nt;
   const double* zvec; const double* logdet;
   const SlotP* sp;
@@ -468,7 +471,8 @@ __global__ void __launch_bounds__(256) nlz_kernel(NlzArgs a) {
   if (threadIdx.x == 0) {
     const SlotP p = a.sp[slot];
     double ld = 0.0;
-    for (int k = 0; k < a.Nt; ++k) ld += a.logdet[(long long)slot * a.Nt + k];
+    const int fslot = a.fsel ? a.fsel[blockIdx.x] : slot;
+    for (int k = 0; k < a.Nt; ++k) ld += a.logdet[(long long)fslot * a.Nt + k];
     // gaussian_process.py:2469-2473 with (y-m)^T alpha = z^T z / sl
     a.nlz[slot] = s / p.sl / 2 + ld + a.N * log(2 * M_PI * p.sl) / 2;
   }
@@ -506,6 +510,11 @@ __global__ void fill_kernel(double* p, double v, long long n) {
 __global__ void copy_kernel(double* dst, const double* src, long long n) {
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
        e += (long long)gridDim.x * blockDim.x) dst[e] = src[e];
+}
+// out[dst[t]] = in[src[t]]  (jitter multipliers: per-row value <-> value of the factor in a slot)
+__global__ void copy_mult_kernel(double* out, const double* in, const int* dst, const int* src, int n) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) out[dst[t]] = in[src[t]];
 }
 __global__ void set_mult_kernel(double* mult, int* fail, const int* sel, int nsel, double v) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;

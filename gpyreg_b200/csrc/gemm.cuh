@@ -474,11 +474,13 @@ struct OpFwd {
   static constexpr int MODE = GM_BETA | GM_ROWDOT;
   BatchBufs b; int k;
   const double* zvec; double* bvec;
+  const int* fsel;                       // slot whose factor entry `by` uses (several rows may share one)
   __device__ GemmTile resolve(int bx, int by) const {
     GemmTile t = empty_tile();
     const int slot = b.sel[by];
+    const int fslot = fsel ? fsel[by] : slot;
     const int i = k + 1 + bx;
-    double* tile = b.Abuf + slot * b.smat + (long long)i * T + (long long)k * T * b.Np;
+    double* tile = b.Abuf + fslot * b.smat + (long long)i * T + (long long)k * T * b.Np;
     t.A = tile; t.lda = b.Np;
     t.B = tile; t.ldb = b.Np;
     t.C = tile; t.ldc = b.Np;

@@ -789,8 +789,12 @@ class GP:
             hyp = np.transpose(kept, (1, 0, 2)).reshape(-1, kept.shape[2])[:s_N]
             self.update(hyp=hyp)
             return hyp, optimize_result, sampling_result
+        # speculative shrinking: the next few proposals of a coordinate update go to the GPU as one
+        # batch (same chain as the sequential sampler, fewer and better-filled calls)
         slicer = SliceSampler(lambda h: self.__gp_obj_fun(h, False, True), hyp_start, widths, LB, UB,
-                              {"display": "off", "diagnostics": False})
+                              {"display": "off", "diagnostics": False,
+                               "log_f_batch": lambda H: -self._nlz_batch(H, False, use_prior),
+                               "speculate": int(options.get("speculate", 3))})
         sampling_result = slicer.sample(s_N * thin, burn=burn_in)
         hyp = sampling_result["samples"][thin - 1::thin, :]
         self.update(hyp=hyp)

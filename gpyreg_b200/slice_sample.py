@@ -7,6 +7,14 @@ The global NumPy RNG is consumed in the same order as the reference (one shuffle
 sweep; per coordinate one draw for the slice level, one for the bracket position, one per
 shrink proposal), so a fixed ``np.random.seed`` gives the same chain whenever the
 log-density values agree.
+
+Speculative shrinking (``options["log_f_batch"]``, ``options["speculate"] = k``): the next
+proposals of the shrink loop are a deterministic function of the random numbers still to be
+drawn (if proposal 1 is rejected the bracket shrinks to a known side, proposal 2 follows, ...).
+With a batched log density the sampler evaluates the next k proposals in ONE call and accepts
+the first that clears the slice level; the RNG state is rewound so that exactly as many draws
+are consumed as the sequential algorithm would have used.  The chain is identical, bit for
+bit; only the number of (batched) calls drops, from ~2 per coordinate to ~1.
 """
 import logging
 
@@ -57,6 +65,9 @@ class SliceSampler:
         self.adaptive = options.get("adaptive", True)
         self.log_prior = options.get("log_prior", None)
         self.diagnostics = options.get("diagnostics", True)
+        self.log_f_batch = options.get("log_f_batch", None)
+        self.speculate = int(options.get("speculate", 3 if self.log_f_batch is not None else 1))
+        self.batch_calls = 0
         self.logger = logging.getLogger("SliceSampler")
         self.logger.setLevel({"off": logging.WARN, "summary": logging.INFO}.get(self.display, logging.DEBUG))
 
@@ -81,6 +92,18 @@ class SliceSampler:
             self.logger.warning("Target density function returned NaN. Trying to continue.")
             return -np.inf, f_val, lp
         return f_sum + lp, f_val, lp
+
+    def _log_density_many(self, pts):
+        """Batched log density of the rows of pts (no prior): -inf outside the bounds / for NaN."""
+        inside = np.all((pts >= self.LB) & (pts <= self.UB), axis=1)
+        out = np.full((pts.shape[0],), -np.inf)
+        if np.any(inside):
+            vals = np.asarray(self.log_f_batch(pts[inside]), dtype=float).reshape(-1)
+            self.batch_calls += 1
+            if np.any(np.isnan(vals)):
+                self.logger.warning("Target density function returned NaN. Trying to continue.")
+            out[inside] = np.where(np.isnan(vals), -np.inf, vals)
+        return out, inside
 
     # -- sampling --------------------------------------------------------------------
     def sample(self, N, thin=1, burn=None):
@@ -118,7 +141,49 @@ class SliceSampler:
                     while self._log_density(hi)[0] > level:
                         hi[d] += self.widths[d]
                 n_shrink = 0
+                speculative = (self.log_f_batch is not None and self.speculate > 1
+                               and self.log_prior is None)
                 while True:                                        # shrink until accepted
+                    if speculative:
+                        # the next k proposals, assuming each one before is rejected
+                        state = np.random.get_state()
+                        us = np.random.rand(self.speculate)
+                        np.random.set_state(state)
+                        l_, h_, cands = lo[d], hi[d], []
+                        for u in us:
+                            c = u * (h_ - l_) + l_
+                            cands.append(c)
+                            if c > xx[d]:
+                                h_ = c
+                            elif c < xx[d]:
+                                l_ = c
+                            else:
+                                break
+                        pts = np.tile(prop, (len(cands), 1))
+                        pts[:, d] = cands
+                        vals, inside = self._log_density_many(pts)
+                        stop = False
+                        for c, v, ins in zip(cands, vals, inside):
+                            n_shrink += 1
+                            np.random.rand()                       # the draw the sequential sampler makes
+                            prop[d] = c
+                            log_Px, f_val, log_prior = v, (v if ins else np.nan), (0.0 if ins else -np.inf)
+                            self.func_count += int(ins)
+                            if v > level:
+                                stop = True
+                                break
+                            if c > xx[d]:
+                                hi[d] = c
+                            elif c < xx[d]:
+                                lo[d] = c
+                            else:
+                                self.logger.warning("WARNING: Shrunk to current position and still "
+                                                    " not acceptable!")
+                                stop = True
+                                break
+                        if stop:
+                            break
+                        continue
                     n_shrink += 1
                     prop[d] = np.random.rand() * (hi[d] - lo[d]) + lo[d]
                     log_Px, f_val, log_prior = self._log_density(prop)

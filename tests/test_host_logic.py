@@ -149,6 +149,38 @@ def test_slice_sampler_matches_reference_chain(h):
     assert ss.func_count == int(h["ss.func_count"])
 
 
+def test_speculative_slice_sampler_is_the_same_chain(h):
+    """Batched speculative shrinking must reproduce the sequential chain bit for bit (and so
+    the reference's), with fewer calls."""
+    logp = lambda x: float(-0.5 * (x[0] ** 2 + (x[1] - 0.5 * x[0]) ** 2 / 0.25 + x[2] ** 2 / 4))
+    sizes = []
+
+    def logp_batch(X):
+        sizes.append(X.shape[0])
+        return np.array([logp(x) for x in X])
+    for k in (2, 3, 5):
+        np.random.seed(9)
+        ss = SliceSampler(logp, np.array([0.1, 0.2, -0.3]), np.array([1.0, 1.0, 2.0]),
+                          np.array([-3.0, -3.0, -5.0]), np.array([3.0, 3.0, 5.0]),
+                          {"display": "off", "diagnostics": False, "log_f_batch": logp_batch, "speculate": k})
+        res = ss.sample(40, thin=2, burn=30)
+        np.testing.assert_array_equal(res["samples"], h["ss.samples"])
+        np.testing.assert_array_equal(res["f_vals"], h["ss.f_vals"])
+        np.testing.assert_array_equal(ss.widths, h["ss.widths"])
+        assert ss.func_count == int(h["ss.func_count"])        # evaluations the sequential sampler counts
+        assert ss.batch_calls < ss.func_count and max(sizes) <= k
+    # the RNG stream ends where the sequential sampler leaves it
+    np.random.seed(9)
+    SliceSampler(logp, np.array([0.1, 0.2, -0.3]), np.array([1.0, 1.0, 2.0]), np.array([-3.0, -3.0, -5.0]),
+                 np.array([3.0, 3.0, 5.0]), {"display": "off", "diagnostics": False}).sample(40, thin=2, burn=30)
+    after_seq = np.random.rand()
+    np.random.seed(9)
+    SliceSampler(logp, np.array([0.1, 0.2, -0.3]), np.array([1.0, 1.0, 2.0]), np.array([-3.0, -3.0, -5.0]),
+                 np.array([3.0, 3.0, 5.0]), {"display": "off", "diagnostics": False, "log_f_batch": logp_batch,
+                                             "speculate": 3}).sample(40, thin=2, burn=30)
+    assert np.random.rand() == after_seq
+
+
 def test_slice_sampler_argument_checks():
     f = lambda x: -0.5 * float(np.sum(x ** 2))
     with pytest.raises(ValueError, match="outside the bounds"):
