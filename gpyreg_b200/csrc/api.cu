@@ -1118,16 +1118,18 @@ static int predict_impl(gpb_ctx* ctx, const gpb_post* cpost, const double* Xs, c
   const int need_ys2 = (add_noise || want_lpd) ? 1 : 0;
   const int Mc = (int)std::min<int64_t>(M, 8192);
   const int McpMax = round_up(Mc, T);
+  const int ns = ctx->gemm_bn == 128 ? 1 : 2;
+  // samples per launch: all of them when the per-sample scratch (Mcp x Np doubles) allows
+  const size_t per_sample = (size_t)McpMax * Np;
+  const int G = (int)std::max<size_t>(1, std::min<size_t>((size_t)Ns, ((size_t)2 << 30) / (per_sample * 8)));
   if ((rc = grow(ctx, &ctx->pXs, &ctx->pXs_n, (size_t)3 * McpMax * std::max(D, 1))) != GPB_OK) return rc;
-  if ((rc = grow(ctx, &ctx->pBt, &ctx->pBt_n, (size_t)McpMax * Np)) != GPB_OK) return rc;
-  if ((rc = grow(ctx, &ctx->pmu, &ctx->ppart_n, (size_t)3 * Nt * McpMax)) != GPB_OK) return rc;
+  if ((rc = grow(ctx, &ctx->pBt, &ctx->pBt_n, (size_t)G * per_sample)) != GPB_OK) return rc;
+  if ((rc = grow(ctx, &ctx->pmu, &ctx->ppart_n, (size_t)G * 3 * Nt * McpMax)) != GPB_OK) return rc;
   if ((rc = grow(ctx, &ctx->psamp, &ctx->psamp_n, (size_t)4 * Ns * McpMax)) != GPB_OK) return rc;
   if ((rc = grow(ctx, &ctx->pout, &ctx->pout_n, (size_t)3 * McpMax * (separate ? Ns : 1))) != GPB_OK) return rc;
   double* dXs = ctx->pXs;
   double* dys = ctx->pXs + (size_t)McpMax * D;
   double* ds2s = dys + McpMax;
-  double* mupart = ctx->pmu;
-  double* vpart = ctx->pmu + (size_t)Nt * McpMax;
   const int kc = kind_code(md.cov_kind, md.degree);
   const size_t ks_smem = ((size_t)2 * D * T + T + 8 * T) * 8;
 
@@ -1153,8 +1155,13 @@ static int predict_impl(gpb_ctx* ctx, const gpb_post* cpost, const double* Xs, c
     double* s2_s = mu_s + (size_t)Ns * Mcp;
     double* ys2_s = s2_s + (size_t)Ns * Mcp;
     double* lpd_s = ys2_s + (size_t)Ns * Mcp;
-    for (int s = 0; s < Ns; ++s) {
-      const SlotP& p = post->sp[s];
+    const long long sBt = (long long)Mcp * Np, smu = (long long)Nt * Mcp, sv = (long long)Nt * ns * Mcp;
+    double* mupart = ctx->pmu;
+    double* vpart = ctx->pmu + (size_t)G * smu;
+    // every kernel below covers a whole group of samples (grid z / y = sample): a predict call
+    // is 3 launches + 1, not 3 per sample
+    for (int s0 = 0; s0 < Ns; s0 += G) {
+      const int g = std::min(G, Ns - s0);
       KsArgs ka;
       ka.md = md;
       ka.N = (int)post->N;
@@ -1163,14 +1170,15 @@ static int predict_impl(gpb_ctx* ctx, const gpb_post* cpost, const double* Xs, c
       ka.mc = mc;
       ka.Mcp = Mcp;
       ka.Xs = cXs;
-      ka.hyp = b.hyp + (size_t)s * md.P;
-      ka.xs = b.xs + (size_t)s * D * Np;
-      ka.alpha = b.alpha + (size_t)s * Np;
-      ka.sp = p;
-      ka.scale = p.lchol ? 1.0 / sqrt(p.sn2_min * p.mult) : 1.0;
+      ka.hyp = b.hyp + (size_t)s0 * md.P;
+      ka.xs = b.xs + (size_t)s0 * D * Np;
+      ka.alpha = b.alpha + (size_t)s0 * Np;
+      ka.sp = b.sp + s0;
       ka.Bt = ctx->pBt;
+      ka.sBt = sBt;
       ka.mupart = mupart;
-      dim3 kgrid((unsigned)(Mcp / T), (unsigned)Nt);
+      ka.smu = smu;
+      dim3 kgrid((unsigned)(Mcp / T), (unsigned)Nt, (unsigned)g);
       switch (kc) {
         case 0: launch_ks<0>(ctx, ka, kgrid, ks_smem); break;
         case 1: launch_ks<1>(ctx, ka, kgrid, ks_smem); break;
@@ -1181,38 +1189,42 @@ static int predict_impl(gpb_ctx* ctx, const gpb_post* cpost, const double* Xs, c
       OpPred op;
       op.Bt = ctx->pBt;
       op.ldbt = Mcp;
-      op.Wm = p.lchol ? b.Wbuf + (size_t)s * b.smat() : b.Abuf + (size_t)s * b.smat();
-      op.ldw = Np;
+      op.sBt = sBt;
+      op.Wbuf = b.Wbuf + (size_t)s0 * b.smat();
+      op.Abuf = b.Abuf + (size_t)s0 * b.smat();
+      op.smat = b.smat();
+      op.sp = b.sp + s0;
       op.part = vpart;
+      op.spart = sv;
       op.Mcp = Mcp;
-      op.tri = p.lchol ? 1 : 0;
       op.Np = Np;
-      op.ns = ctx->gemm_bn == 128 ? 1 : 2;
+      op.ns = ns;
       op.N = (int)post->N;
       op.mc = mc;
-      launch_gemm(ctx, op, dim3((unsigned)(Mcp / T), (unsigned)Nt));
+      launch_gemm(ctx, op, dim3((unsigned)(Mcp / T), (unsigned)Nt, (unsigned)g));
       FinishArgs fa;
       fa.md = md;
       fa.Nt = Nt;
-      fa.nv = Nt * (ctx->gemm_bn == 128 ? 1 : 2);
+      fa.nv = Nt * ns;
       fa.mc = mc;
       fa.Mcp = Mcp;
       fa.has_data = 1;
-      fa.lchol = p.lchol;
       fa.Xs = cXs;
       fa.ys = cys;
       fa.s2s = cs2s;
-      fa.hyp = b.hyp + (size_t)s * md.P;
-      fa.sp = p;
+      fa.hyp = b.hyp + (size_t)s0 * md.P;
+      fa.sp = b.sp + s0;
       fa.mupart = mupart;
+      fa.smu = smu;
       fa.vpart = vpart;
+      fa.sv = sv;
       fa.need_ys2 = need_ys2;
       fa.want_lpd = want_lpd && separate;
-      fa.mu_s = mu_s + (size_t)s * Mcp;
-      fa.s2_s = s2_s + (size_t)s * Mcp;
-      fa.ys2_s = ys2_s + (size_t)s * Mcp;
-      fa.lpd_s = lpd_s + (size_t)s * Mcp;
-      pred_finish_kernel<<<(unsigned)((mc + 255) / 256), 256, 0, ctx->stream>>>(fa);
+      fa.mu_s = mu_s + (size_t)s0 * Mcp;
+      fa.s2_s = s2_s + (size_t)s0 * Mcp;
+      fa.ys2_s = ys2_s + (size_t)s0 * Mcp;
+      fa.lpd_s = lpd_s + (size_t)s0 * Mcp;
+      pred_finish_kernel<<<dim3((unsigned)((mc + 255) / 256), (unsigned)g), 256, 0, ctx->stream>>>(fa);
       LAUNCHED(ctx);
     }
     const size_t ocols = separate ? Ns : 1;
@@ -1327,16 +1339,19 @@ extern "C" int gpb_quad(gpb_ctx* ctx, const gpb_post* cpost, const double* mu, c
         OpPred op;
         op.Bt = ctx->pBt;
         op.ldbt = Mcp;
-        op.Wm = p.lchol ? b.Wbuf + (size_t)s * b.smat() : b.Abuf + (size_t)s * b.smat();
-        op.ldw = Np;
+        op.sBt = 0;
+        op.Wbuf = b.Wbuf + (size_t)s * b.smat();
+        op.Abuf = b.Abuf + (size_t)s * b.smat();
+        op.smat = b.smat();
+        op.sp = b.sp + s;
         op.part = vpart;
+        op.spart = 0;
         op.Mcp = Mcp;
-        op.tri = p.lchol ? 1 : 0;
         op.Np = Np;
         op.ns = ns;
         op.N = (int)post->N;
         op.mc = mc;
-        launch_gemm(ctx, op, dim3((unsigned)(Mcp / T), (unsigned)Nt));
+        launch_gemm(ctx, op, dim3((unsigned)(Mcp / T), (unsigned)Nt, 1));
       }
       QuadFinishArgs fa;
       fa.md = md;
@@ -1450,11 +1465,12 @@ extern "C" int gpb_predict_full(gpb_ctx* ctx, const gpb_post* cpost, const doubl
     ka.hyp = b.hyp + (size_t)s * md.P;
     ka.xs = b.xs + (size_t)s * D * Np;
     ka.alpha = b.alpha + (size_t)s * Np;
-    ka.sp = p;
-    ka.scale = p.lchol ? 1.0 / sqrt(p.sn2_min * p.mult) : 1.0;
+    ka.sp = b.sp + s;
     ka.Bt = Bt;
+    ka.sBt = 0;
     ka.mupart = mupart;
-    dim3 kgrid((unsigned)(Mcp / T), (unsigned)Nt);
+    ka.smu = 0;
+    dim3 kgrid((unsigned)(Mcp / T), (unsigned)Nt, 1);
     switch (kc) {
       case 0: launch_ks<0>(ctx, ka, kgrid, ks_smem); break;
       case 1: launch_ks<1>(ctx, ka, kgrid, ks_smem); break;

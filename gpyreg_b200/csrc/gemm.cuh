@@ -594,23 +594,28 @@ struct OpSyrk2 {
 struct OpPred {
   static constexpr bool SLOT_MAJOR = false;
   static constexpr int MODE = GM_REDUCE;
-  const double* Bt; long long ldbt;   // (Mcp x Np) column-major
-  const double* Wm; long long ldw;    // (Np x Np) column-major
-  double* part;                       // [Nt*ns][Mcp]
-  int Mcp; int tri;                   // tri = 1: Wm lower triangular -> K = (nt+1)*T
-  int Np; int ns;                     // ns = column halves per tile (BN / BN_)
-  int N, mc;                          // training rows / test points that hold data
+  // blockIdx.z = posterior sample within the group handled by this launch
+  const double* Bt; long long ldbt, sBt;   // per sample (Mcp x Np) column-major, stride sBt
+  const double* Wbuf; const double* Abuf;  // W = L^-1 (L_chol samples) / Ainv (low noise), stride smat
+  long long smat;
+  const SlotP* sp;                         // per-sample scalars: sp[z].lchol picks the operand
+  double* part; long long spart;           // per sample [Nt*ns][Mcp]
+  int Mcp, Np, ns;                         // ns = column halves per tile (BN / BN_)
+  int N, mc;                               // training rows / test points that hold data
   __device__ GemmTile resolve(int bx, int by) const {
     GemmTile t = empty_tile();
+    const int z = blockIdx.z;
+    const int tri = sp[z].lchol;             // W lower triangular -> K = (nt+1)*T
+    const double* bt = Bt + z * sBt;
     const int jt = bx, nt = (int)gridDim.y - 1 - by;   // longest K first
-    t.A = Bt + (long long)jt * BM; t.lda = ldbt;
-    t.B = Wm + (long long)nt * BN; t.ldb = ldw;
+    t.A = bt + (long long)jt * BM; t.lda = ldbt;
+    t.B = (tri ? Wbuf : Abuf) + z * smat + (long long)nt * BN; t.ldb = Np;
     const int n16 = (N + BK - 1) / BK * BK;
     t.K = tri ? min((nt + 1) * T, n16) : n16;
     t.mvalid = mc - jt * BM;
     t.nvalid = N - nt * BN;
-    if (!tri) { t.E = Bt + (long long)jt * BM + (long long)nt * BN * ldbt; t.lde = ldbt; }
-    t.rowsum = part + (long long)nt * ns * Mcp + (long long)jt * BM;
+    if (!tri) { t.E = bt + (long long)jt * BM + (long long)nt * BN * ldbt; t.lde = ldbt; }
+    t.rowsum = part + z * spart + (long long)nt * ns * Mcp + (long long)jt * BM;
     t.rs_half = Mcp;
     return t;
   }

@@ -16,13 +16,13 @@ struct KsArgs {
   int N, Np, Nt;
   int mc, Mcp;                 // valid test points in this chunk, padded to 128
   const double* Xs;            // (mc, D) row-major, this chunk
-  const double* hyp;           // this sample's hyperparameter row
-  const double* xs;            // this sample's pre-scaled training inputs [D][Np]
-  const double* alpha;         // [Np]
-  SlotP sp;
-  double scale;                // sW (L_chol) or 1
-  double* Bt;                  // (Mcp, Np) column-major
-  double* mupart;              // [Nt][Mcp]
+  // blockIdx.z = posterior sample within the group; all per-sample arrays are strided
+  const double* hyp;           // hyperparameter rows, stride md.P
+  const double* xs;            // pre-scaled training inputs [D][Np] per sample, stride D*Np
+  const double* alpha;         // [Np] per sample, stride Np
+  const SlotP* sp;             // per-sample scalars
+  double* Bt; long long sBt;   // (Mcp, Np) column-major per sample:  sW * Ks  (L_chol) or Ks
+  double* mupart; long long smu;   // [Nt][Mcp] per sample
 };
 
 // tile: rows = test points j (tx + 32a), columns = training points k (ty*16 + b)
@@ -31,7 +31,14 @@ __global__ void __launch_bounds__(256) ks_build_kernel(KsArgs a) {
   extern __shared__ double bsm[];
   const Model& md = a.md;
   const int D = md.D, Np = a.Np;
-  const int jt = blockIdx.x, kt = blockIdx.y;
+  const int jt = blockIdx.x, kt = blockIdx.y, z = blockIdx.z;
+  const double* hyp = a.hyp + (long long)z * md.P;
+  const double* xs = a.xs + (long long)z * D * Np;
+  const double* alpha = a.alpha + (long long)z * Np;
+  const SlotP sp = a.sp[z];
+  const double scale = sp.lchol ? 1.0 / sqrt(sp.sn2_min * sp.mult) : 1.0;   // sW, gaussian_process.py:2517
+  double* Bt = a.Bt + z * a.sBt;
+  double* mupart = a.mupart + z * a.smu;
   double* xr = bsm;               // [D][128] scaled test points
   double* xc = bsm + D * T;       // [D][128] scaled training points
   double* al = bsm + 2 * D * T;   // [128]
@@ -41,13 +48,13 @@ __global__ void __launch_bounds__(256) ks_build_kernel(KsArgs a) {
     const int j = jt * T + i;
     double v = 0.0;
     if (j < a.mc) {
-      const double ell = exp(a.hyp[md.ard ? k : 0]);
+      const double ell = exp(hyp[md.ard ? k : 0]);
       v = scale_coord(md.cov_kind, md.ard, md.degree, a.Xs[(long long)j * D + k], ell);
     }
     xr[e] = v;
-    xc[e] = a.xs[(long long)k * Np + kt * T + i];
+    xc[e] = xs[(long long)k * Np + kt * T + i];
   }
-  if (threadIdx.x < T) al[threadIdx.x] = a.alpha[kt * T + threadIdx.x];
+  if (threadIdx.x < T) al[threadIdx.x] = alpha[kt * T + threadIdx.x];
   __syncthreads();
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   double musum[4] = {0.0, 0.0, 0.0, 0.0};
@@ -80,8 +87,8 @@ __global__ void __launch_bounds__(256) ks_build_kernel(KsArgs a) {
         const int jl = tx + 32 * aa;
         const int gj = jt * T + jl;
         double K = 0.0;
-        if (gk < a.N && gj < a.mc) K = kern_value<KIND>(r2[aa][bb], a.sp.sf2, a.sp.rq_a);
-        a.Bt[(long long)gk * a.Mcp + gj] = a.scale * K;
+        if (gk < a.N && gj < a.mc) K = kern_value<KIND>(r2[aa][bb], sp.sf2, sp.rq_a);
+        Bt[(long long)gk * a.Mcp + gj] = scale * K;
         musum[aa] += K * al[kl];
       }
     }
@@ -92,7 +99,7 @@ __global__ void __launch_bounds__(256) ks_build_kernel(KsArgs a) {
   if (threadIdx.x < T) {
     double s = 0.0;
     for (int w = 0; w < 8; ++w) s += red[w * T + threadIdx.x];
-    a.mupart[(long long)kt * a.Mcp + jt * T + threadIdx.x] = s;
+    mupart[(long long)kt * a.Mcp + jt * T + threadIdx.x] = s;
   }
 }
 
@@ -100,48 +107,55 @@ struct FinishArgs {
   Model md;
   int Nt, nv, mc, Mcp;         // nv = number of variance partials (Nt * column halves)
   int has_data;                // 0: GP without training data -> prior mean / variance
-  int lchol;
   const double* Xs; const double* ys; const double* s2s;    // chunk pointers (ys/s2s may be null)
-  const double* hyp;
-  SlotP sp;
-  const double* mupart; const double* vpart;
+  // blockIdx.y = posterior sample within the group
+  const double* hyp;           // stride md.P
+  const SlotP* sp;
+  const double* mupart; long long smu;
+  const double* vpart; long long sv;
   int need_ys2, want_lpd;
-  double* mu_s; double* s2_s; double* ys2_s; double* lpd_s;   // this sample's rows, [Mcp]
+  double* mu_s; double* s2_s; double* ys2_s; double* lpd_s;   // [samples][Mcp], first sample of the group
 };
 
 __global__ void __launch_bounds__(256) pred_finish_kernel(FinishArgs a) {
   const Model& md = a.md;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= a.mc) return;
-  const double* hn = a.hyp + md.cov_n;
-  const double* hm = a.hyp + md.cov_n + md.noise_n;
+  const int z = blockIdx.y;
+  const double* hyp = a.hyp + (long long)z * md.P;
+  const SlotP sp = a.sp[z];
+  const double* mupart = a.mupart + z * a.smu;
+  const double* vpart = a.vpart + z * a.sv;
+  const double* hn = hyp + md.cov_n;
+  const double* hm = hyp + md.cov_n + md.noise_n;
   double mu = mean_value(md.mean_kind, md.D, hm, a.Xs + (long long)j * md.D);   // :1734-1739
   // kss = covariance.compute(hyp, x_star, compute_diag=True) = sf2 * f(0) * exp(0)   (:1741)
   const int kc = kind_code(md.cov_kind, md.degree);
   double kss;
-  if (kc == 2) kss = kern_value<2>(0.0, a.sp.sf2, a.sp.rq_a);
-  else if (kc == 0) kss = kern_value<0>(0.0, a.sp.sf2, a.sp.rq_a);
-  else kss = kern_value<3>(0.0, a.sp.sf2, a.sp.rq_a);
+  if (kc == 2) kss = kern_value<2>(0.0, sp.sf2, sp.rq_a);
+  else if (kc == 0) kss = kern_value<0>(0.0, sp.sf2, sp.rq_a);
+  else kss = kern_value<3>(0.0, sp.sf2, sp.rq_a);
   double s2 = kss;
   if (a.has_data) {
     double m = 0.0, v = 0.0;
-    for (int t = 0; t < a.Nt; ++t) m += a.mupart[(long long)t * a.Mcp + j];
-    for (int t = 0; t < a.nv; ++t) v += a.vpart[(long long)t * a.Mcp + j];
+    for (int t = 0; t < a.Nt; ++t) m += mupart[(long long)t * a.Mcp + j];
+    for (int t = 0; t < a.nv; ++t) v += vpart[(long long)t * a.Mcp + j];
     mu += m;                                        // :1747
     s2 = kss - v;                                   // :1758 / :1762 (L = -Ainv)
   }
   s2 = fmax(s2, 0.0);                               // :1770
-  a.mu_s[j] = mu;
-  a.s2_s[j] = s2;
+  const long long o = (long long)z * a.Mcp + j;
+  a.mu_s[o] = mu;
+  a.s2_s[o] = s2;
   if (a.need_ys2) {
     const double sn2 = noise_value(md.nz0, md.nz1, md.nz2, hn, a.ys != nullptr,
                                    a.ys ? a.ys[j] : 0.0, a.s2s != nullptr,
                                    a.s2s ? a.s2s[j] : 0.0);
-    const double ys2 = s2 + sn2 * a.sp.mult;        // :1779
-    a.ys2_s[j] = ys2;
+    const double ys2 = s2 + sn2 * sp.mult;          // :1779
+    a.ys2_s[o] = ys2;
     if (a.want_lpd) {
       const double dlt = a.ys[j] - mu;
-      a.lpd_s[j] = -0.5 * (dlt * dlt) / ys2 - 0.5 * log(2 * M_PI * ys2);   // :1783-1787
+      a.lpd_s[o] = -0.5 * (dlt * dlt) / ys2 - 0.5 * log(2 * M_PI * ys2);   // :1783-1787
     }
   }
 }
