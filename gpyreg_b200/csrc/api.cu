@@ -1297,15 +1297,15 @@ extern "C" int gpb_quad(gpb_ctx* ctx, const gpb_post* cpost, const double* mu, c
   const int Mc = (int)std::min<int64_t>(M, 8192);
   const int McpMax = round_up(Mc, T);
   const int ns = ctx->gemm_bn == 128 ? 1 : 2;
+  const size_t per_sample = (size_t)McpMax * Np;
+  const int G = (int)std::max<size_t>(1, std::min<size_t>((size_t)Ns, ((size_t)2 << 30) / (per_sample * 8)));
   if ((rc = grow(ctx, &ctx->pXs, &ctx->pXs_n, (size_t)3 * McpMax * std::max(D, 1))) != GPB_OK) return rc;
-  if ((rc = grow(ctx, &ctx->pBt, &ctx->pBt_n, (size_t)McpMax * Np)) != GPB_OK) return rc;
-  if ((rc = grow(ctx, &ctx->pmu, &ctx->ppart_n, (size_t)3 * Nt * McpMax)) != GPB_OK) return rc;
+  if ((rc = grow(ctx, &ctx->pBt, &ctx->pBt_n, (size_t)G * per_sample)) != GPB_OK) return rc;
+  if ((rc = grow(ctx, &ctx->pmu, &ctx->ppart_n, (size_t)G * 3 * Nt * McpMax)) != GPB_OK) return rc;
   if ((rc = grow(ctx, &ctx->psamp, &ctx->psamp_n, (size_t)4 * Ns * McpMax)) != GPB_OK) return rc;
   if ((rc = grow(ctx, &ctx->pout, &ctx->pout_n, (size_t)3 * McpMax * (separate ? Ns : 1))) != GPB_OK) return rc;
   double* dmu = ctx->pXs;
   double* dsg = ctx->pXs + (size_t)McpMax * D;
-  double* mupart = ctx->pmu;
-  double* vpart = ctx->pmu + (size_t)Nt * McpMax;
   const size_t smem = ((size_t)3 * D * T + 2 * T + 8 * T) * 8;
   for (int64_t c0 = 0; c0 < M; c0 += Mc) {
     const int mc = (int)std::min<int64_t>(Mc, M - c0);
@@ -1314,10 +1314,11 @@ extern "C" int gpb_quad(gpb_ctx* ctx, const gpb_post* cpost, const double* mu, c
     CK(cudaMemcpyAsync(dsg, sigma + c0 * D, sizeof(double) * mc * D, cudaMemcpyHostToDevice, ctx->stream));
     double* F_s = ctx->psamp;
     double* V_s = F_s + (size_t)Ns * Mcp;
-    for (int s = 0; s < Ns; ++s) {
-      const SlotP& p = post->sp[s];
-      const double* hyp_s = b.hyp + (size_t)s * md.P;
-      const double sn2_eff = exp(2 * post->hyp[(size_t)s * md.P + md.cov_n]) * p.mult;   // :1919-1920
+    const long long sBt = (long long)Mcp * Np, smu = (long long)Nt * Mcp, sv = (long long)Nt * ns * Mcp;
+    double* mupart = ctx->pmu;
+    double* vpart = ctx->pmu + (size_t)G * smu;
+    for (int s0 = 0; s0 < Ns; s0 += G) {               // a whole group of samples per launch
+      const int g = std::min(G, Ns - s0);
       QuadArgs qa;
       qa.md = md;
       qa.N = (int)post->N;
@@ -1328,30 +1329,32 @@ extern "C" int gpb_quad(gpb_ctx* ctx, const gpb_post* cpost, const double* mu, c
       qa.mu = dmu;
       qa.sigma = dsg;
       qa.X = post->X;
-      qa.hyp = hyp_s;
-      qa.alpha = b.alpha + (size_t)s * Np;
-      qa.scale = p.lchol ? 1.0 / sqrt(sn2_eff) : 1.0;
+      qa.hyp = b.hyp + (size_t)s0 * md.P;
+      qa.alpha = b.alpha + (size_t)s0 * Np;
+      qa.sp = b.sp + s0;
       qa.Bt = ctx->pBt;
+      qa.sBt = sBt;
       qa.mupart = mupart;
-      quad_build_kernel<<<dim3((unsigned)(Mcp / T), (unsigned)Nt), 256, smem, ctx->stream>>>(qa);
+      qa.smu = smu;
+      quad_build_kernel<<<dim3((unsigned)(Mcp / T), (unsigned)Nt, (unsigned)g), 256, smem, ctx->stream>>>(qa);
       LAUNCHED(ctx);
       if (compute_var) {
         OpPred op;
         op.Bt = ctx->pBt;
         op.ldbt = Mcp;
-        op.sBt = 0;
-        op.Wbuf = b.Wbuf + (size_t)s * b.smat();
-        op.Abuf = b.Abuf + (size_t)s * b.smat();
+        op.sBt = sBt;
+        op.Wbuf = b.Wbuf + (size_t)s0 * b.smat();
+        op.Abuf = b.Abuf + (size_t)s0 * b.smat();
         op.smat = b.smat();
-        op.sp = b.sp + s;
+        op.sp = b.sp + s0;
         op.part = vpart;
-        op.spart = 0;
+        op.spart = sv;
         op.Mcp = Mcp;
         op.Np = Np;
         op.ns = ns;
         op.N = (int)post->N;
         op.mc = mc;
-        launch_gemm(ctx, op, dim3((unsigned)(Mcp / T), (unsigned)Nt, 1));
+        launch_gemm(ctx, op, dim3((unsigned)(Mcp / T), (unsigned)Nt, (unsigned)g));
       }
       QuadFinishArgs fa;
       fa.md = md;
@@ -1362,12 +1365,14 @@ extern "C" int gpb_quad(gpb_ctx* ctx, const gpb_post* cpost, const double* mu, c
       fa.compute_var = compute_var;
       fa.mu = dmu;
       fa.sigma = dsg;
-      fa.hyp = hyp_s;
+      fa.hyp = b.hyp + (size_t)s0 * md.P;
       fa.mupart = mupart;
+      fa.smu = smu;
       fa.vpart = vpart;
-      fa.F_s = F_s + (size_t)s * Mcp;
-      fa.V_s = V_s + (size_t)s * Mcp;
-      quad_finish_kernel<<<(unsigned)((mc + 255) / 256), 256, 0, ctx->stream>>>(fa);
+      fa.sv = sv;
+      fa.F_s = F_s + (size_t)s0 * Mcp;
+      fa.V_s = V_s + (size_t)s0 * Mcp;
+      quad_finish_kernel<<<dim3((unsigned)((mc + 255) / 256), (unsigned)g), 256, 0, ctx->stream>>>(fa);
       LAUNCHED(ctx);
     }
     const size_t ocols = separate ? Ns : 1;

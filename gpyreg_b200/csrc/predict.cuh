@@ -226,17 +226,25 @@ struct QuadArgs {
   const double* mu;            // (mc, D) chunk
   const double* sigma;         // (mc, D) chunk
   const double* X;             // (N, D) training inputs, row-major
-  const double* hyp;
-  const double* alpha;         // [Np]
-  double scale;                // 1/sqrt(sn2_eff) (L_chol) or 1
-  double* Bt;                  // (Mcp, Np) column-major
-  double* mupart;              // [Nt][Mcp]
+  // blockIdx.z = posterior sample within the group; per-sample arrays are strided
+  const double* hyp;           // stride md.P
+  const double* alpha;         // [Np] per sample
+  const SlotP* sp;
+  double* Bt; long long sBt;   // (Mcp, Np) column-major per sample
+  double* mupart; long long smu;   // [Nt][Mcp] per sample
 };
 
 __global__ void __launch_bounds__(256) quad_build_kernel(QuadArgs a) {
   extern __shared__ double bsm[];
   const int D = a.md.D;
-  const int jt = blockIdx.x, kt = blockIdx.y;
+  const int jt = blockIdx.x, kt = blockIdx.y, z = blockIdx.z;
+  const double* hyp = a.hyp + (long long)z * a.md.P;
+  const double* alpha = a.alpha + (long long)z * a.Np;
+  const SlotP sp = a.sp[z];
+  // 1/sqrt(sn2_eff), sn2_eff = exp(2 hyp[cov_N]) * sn2_mult  (gaussian_process.py:1919-1920)
+  const double scale = sp.lchol ? 1.0 / sqrt(exp(2 * hyp[a.md.cov_n]) * sp.mult) : 1.0;
+  double* Bt = a.Bt + z * a.sBt;
+  double* mupart = a.mupart + z * a.smu;
   double* mr = bsm;                 // [D][128] measure means
   double* it = bsm + D * T;         // [D][128] 1 / tau
   double* xc = bsm + 2 * D * T;     // [D][128] training inputs
@@ -248,7 +256,7 @@ __global__ void __launch_bounds__(256) quad_build_kernel(QuadArgs a) {
     const int j = jt * T + i, gi = kt * T + i;
     double m = 0.0, itau = 0.0;
     if (j < a.mc) {
-      const double sg = a.sigma[(long long)j * D + k], ell = exp(a.hyp[k]);
+      const double sg = a.sigma[(long long)j * D + k], ell = exp(hyp[k]);
       m = a.mu[(long long)j * D + k];
       itau = 1.0 / sqrt(sg * sg + ell * ell);
     }
@@ -262,14 +270,14 @@ __global__ void __launch_bounds__(256) quad_build_kernel(QuadArgs a) {
     if (j < a.mc) {
       double sl = 0.0, st = 0.0;            // sum log ell, sum log tau
       for (int k = 0; k < D; ++k) {
-        const double sg = a.sigma[(long long)j * D + k], ell = exp(a.hyp[k]);
-        sl += a.hyp[k];
+        const double sg = a.sigma[(long long)j * D + k], ell = exp(hyp[k]);
+        sl += hyp[k];
         st += log(sqrt(sg * sg + ell * ell));
       }
-      v = 2 * a.hyp[D] + sl - st;          // :1925-1927
+      v = 2 * hyp[D] + sl - st;            // :1925-1927
     }
     lnnf[threadIdx.x] = v;
-    al[threadIdx.x] = a.alpha[kt * T + threadIdx.x];
+    al[threadIdx.x] = alpha[kt * T + threadIdx.x];
   }
   __syncthreads();
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -288,10 +296,10 @@ __global__ void __launch_bounds__(256) quad_build_kernel(QuadArgs a) {
 #pragma unroll
     for (int aa = 0; aa < 4; ++aa) {
       const int jl = tx + 32 * aa, gj = jt * T + jl;
-      double z = 0.0;
-      if (gi < a.N && gj < a.mc) z = exp(lnnf[jl] - 0.5 * d2[aa]);     // :1937
-      a.Bt[(long long)gi * a.Mcp + gj] = a.scale * z;
-      fsum[aa] += z * al[il];
+      double zz = 0.0;
+      if (gi < a.N && gj < a.mc) zz = exp(lnnf[jl] - 0.5 * d2[aa]);    // :1937
+      Bt[(long long)gi * a.Mcp + gj] = scale * zz;
+      fsum[aa] += zz * al[il];
     }
   }
 #pragma unroll
@@ -300,16 +308,18 @@ __global__ void __launch_bounds__(256) quad_build_kernel(QuadArgs a) {
   if (threadIdx.x < T) {
     double s = 0.0;
     for (int w = 0; w < 8; ++w) s += red[w * T + threadIdx.x];
-    a.mupart[(long long)kt * a.Mcp + jt * T + threadIdx.x] = s;
+    mupart[(long long)kt * a.Mcp + jt * T + threadIdx.x] = s;
   }
 }
 
 struct QuadFinishArgs {
   Model md;
   int Nt, nv, mc, Mcp, compute_var;
-  const double* mu; const double* sigma; const double* hyp;
-  const double* mupart; const double* vpart;
-  double* F_s; double* V_s;      // this sample's rows, [Mcp]
+  const double* mu; const double* sigma;
+  const double* hyp;             // stride md.P, blockIdx.y = sample
+  const double* mupart; long long smu;
+  const double* vpart; long long sv;
+  double* F_s; double* V_s;      // [samples][Mcp], first sample of the group
 };
 
 __global__ void __launch_bounds__(256) quad_finish_kernel(QuadFinishArgs a) {
@@ -317,11 +327,15 @@ __global__ void __launch_bounds__(256) quad_finish_kernel(QuadFinishArgs a) {
   const int D = md.D;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= a.mc) return;
-  const double* hm = a.hyp + md.cov_n + md.noise_n;
+  const int z = blockIdx.y;
+  const double* hyp = a.hyp + (long long)z * md.P;
+  const double* mupart = a.mupart + z * a.smu;
+  const double* vpart = a.vpart + z * a.sv;
+  const double* hm = hyp + md.cov_n + md.noise_n;
   const double* mu = a.mu + (long long)j * D;
   const double* sg = a.sigma + (long long)j * D;
   double F = (md.mean_kind == 0) ? 0.0 : hm[0];                      // :1906-1909
-  for (int t = 0; t < a.Nt; ++t) F += a.mupart[(long long)t * a.Mcp + j];
+  for (int t = 0; t < a.Nt; ++t) F += mupart[(long long)t * a.Mcp + j];
   if (md.mean_kind == 2) {                                           // :1939-1946
     double nu = 0.0;
     for (int k = 0; k < D; ++k) {
@@ -330,18 +344,19 @@ __global__ void __launch_bounds__(256) quad_finish_kernel(QuadFinishArgs a) {
     }
     F += -0.5 * nu;
   }
-  a.F_s[j] = F;
+  const long long o = (long long)z * a.Mcp + j;
+  a.F_s[o] = F;
   if (a.compute_var) {
     double sl = 0.0, st = 0.0;
     for (int k = 0; k < D; ++k) {
-      const double ell = exp(a.hyp[k]);
-      sl += a.hyp[k];
+      const double ell = exp(hyp[k]);
+      sl += hyp[k];
       st += log(sqrt(2 * sg[k] * sg[k] + ell * ell));
     }
-    const double nf_kk = exp(2 * a.hyp[D] + sl - st);                // :1949-1950
+    const double nf_kk = exp(2 * hyp[D] + sl - st);                  // :1949-1950
     double v = 0.0;
-    for (int t = 0; t < a.nv; ++t) v += a.vpart[(long long)t * a.Mcp + j];
-    a.V_s[j] = fmax(2.220446049250313e-16, nf_kk - v);               // :1966-1969
+    for (int t = 0; t < a.nv; ++t) v += vpart[(long long)t * a.Mcp + j];
+    a.V_s[o] = fmax(2.220446049250313e-16, nf_kk - v);               // :1966-1969
   }
 }
 
