@@ -31,6 +31,8 @@ SYMBOLS = {
     "gpb_posterior_count": (C.c_int64, [_vp]),
     "gpb_posterior_fetch": (C.c_int, [_vp, C.c_int64, C.c_int, _vp]),
     "gpb_posterior_free": (None, [_vp]),
+    "gpb_posterior_size": (C.c_int64, [_vp]),
+    "gpb_posterior_append": (C.c_int, [_vp, _vp, _vp, C.c_double, _vp]),
     "gpb_predict": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_int,
                               _vp, _vp, _vp]),
     "gpb_predict_dev": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int, C.c_int, _vp, _vp]),

@@ -15,6 +15,7 @@
 #include "cov.cuh"
 #include "gemm.cuh"
 #include "predict.cuh"
+#include "append.cuh"
 
 using namespace gpb;
 
@@ -974,7 +975,7 @@ extern "C" int gpb_posterior_batch(gpb_ctx* ctx, const double* hyp, int64_t B, g
     return code;
   };
   {
-    cudaError_t e = cudaMalloc(&post->X, sizeof(double) * ctx->N * ctx->D);
+    cudaError_t e = cudaMalloc(&post->X, sizeof(double) * ctx->Np * ctx->D);   // room for appends
     if (e == cudaSuccess)
       e = cudaMemcpyAsync(post->X, ctx->dX, sizeof(double) * ctx->N * ctx->D, cudaMemcpyDeviceToDevice, ctx->stream);
     if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return bail(GPB_ECUDA); }
@@ -1410,6 +1411,100 @@ extern "C" int gpb_quad(gpb_ctx* ctx, const gpb_post* cpost, const double* mu, c
 // ---------------------------------------------------------------------------------
 // full predictive covariance (GP.predict_full)
 // ---------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------
+// rank-one append (GP.update, gaussian_process.py:737-844)
+// ---------------------------------------------------------------------------------
+extern "C" int64_t gpb_posterior_size(const gpb_post* post) { return post ? post->N : 0; }
+
+template <int KIND>
+static void launch_append_ks(gpb_ctx* ctx, const AppendArgs& a, dim3 grid) {
+  append_ks_kernel<KIND><<<grid, 256, 0, ctx->stream>>>(a);
+  LAUNCHED(ctx);
+}
+
+static int predict_impl(gpb_ctx* ctx, const gpb_post* cpost, const double* Xs, const double* ys,
+                        const double* s2s, int64_t M, int add_noise, int separate, int want_lpd,
+                        double* mu, double* s2, double* lpd, bool on_device);
+
+extern "C" int gpb_posterior_append(gpb_ctx* ctx, gpb_post* post, const double* x_new, double y_new,
+                                    int32_t* status) {
+  if (!ctx || !post || !x_new || !status) return GPB_EINVAL;
+  if (post->ctx != ctx) FAIL(GPB_EINVAL, "gpb_posterior_append: posterior belongs to another context");
+  const Model md = post->md;
+  if (md.nz1 != 0 || md.nz2 != 0)
+    FAIL(GPB_EAGAIN, "gpb_posterior_append: point-dependent noise, rebuild the batch");
+  Bufs& b = post->b;
+  const int N = (int)post->N, Np = b.Np, Ns = b.cap, D = md.D;
+  if (N + 1 > Np) FAIL(GPB_EAGAIN, "gpb_posterior_append: no free row in the padded layout, rebuild the batch");
+  for (int st : post->status)
+    if (st) FAIL(GPB_ESTATE, "gpb_posterior_append: a posterior sample has no valid factorisation");
+  CK(cudaSetDevice(ctx->device));
+  // m*, v* of the new point under the current posterior, per sample (:756-758)
+  double* dx = b.sn2v;                       // scratch of the posterior's own buffers
+  double* mstar = b.nlz;
+  double* vstar = b.logdet;                  // Nt >= 1 doubles per sample
+  CK(cudaMemcpyAsync(dx, x_new, sizeof(double) * D, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = predict_impl(ctx, post, dx, nullptr, nullptr, 1, /*add_noise=*/1, /*separate=*/1, 0, mstar,
+                        vstar, nullptr, /*on_device=*/true);
+  if (rc != GPB_OK) return rc;
+  AppendArgs a;
+  a.md = md;
+  a.N = N;
+  a.Np = Np;
+  a.xnew = dx;
+  a.ynew = y_new;
+  a.hyp = b.hyp;
+  a.sp = b.sp;
+  a.xs = b.xs;
+  a.Abuf = b.Abuf;
+  a.Wbuf = b.Wbuf;
+  a.smat = b.smat();
+  a.alpha = b.alpha;
+  a.kvec = b.bvec;
+  a.cvec = b.zvec;
+  a.avec = b.resid;
+  a.mstar = mstar;
+  a.vstar = vstar;
+  a.status = b.fail;
+  const dim3 kgrid((unsigned)((Np + 255) / 256), (unsigned)Ns);
+  switch (kind_code(md.cov_kind, md.degree)) {
+    case 0: launch_append_ks<0>(ctx, a, kgrid); break;
+    case 1: launch_append_ks<1>(ctx, a, kgrid); break;
+    case 3: launch_append_ks<3>(ctx, a, kgrid); break;
+    case 5: launch_append_ks<5>(ctx, a, kgrid); break;
+    default: launch_append_ks<2>(ctx, a, kgrid); break;
+  }
+  bool any_high = false, any_low = false;
+  for (const SlotP& p : post->sp) (p.lchol ? any_high : any_low) = true;
+  const int nt = (N + T - 1) / T;
+  if (any_high) {
+    append_gemv_n_kernel<<<dim3((unsigned)nt, (unsigned)Ns), 256, 0, ctx->stream>>>(a);
+    LAUNCHED(ctx);
+  }
+  append_gemv_t_kernel<<<dim3((unsigned)((N + 7) / 8), (unsigned)Ns), 256, 0, ctx->stream>>>(a);
+  LAUNCHED(ctx);
+  if (any_low) {
+    append_outer_kernel<<<dim3((unsigned)nt, (unsigned)nt, (unsigned)Ns), 256, 0, ctx->stream>>>(a);
+    LAUNCHED(ctx);
+  }
+  append_finish_kernel<<<(unsigned)Ns, 256, 0, ctx->stream>>>(a);
+  LAUNCHED(ctx);
+  CK(cudaMemcpyAsync(post->X + (size_t)N * D, dx, sizeof(double) * D, cudaMemcpyDeviceToDevice, ctx->stream));
+  std::vector<int> st((size_t)Ns);
+  CK(cudaMemcpyAsync(st.data(), b.fail, sizeof(int) * Ns, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  bool ok = true;
+  for (int s = 0; s < Ns; ++s) {
+    status[s] = st[s];
+    ok = ok && st[s] == 0;
+  }
+  // with an unstable sample the batch is inconsistent (some samples hold N+1 points): the caller
+  // rebuilds it; mark it unusable for predict until then
+  if (ok) post->N = N + 1;
+  else for (int s = 0; s < Ns; ++s) post->status[s] = 1;
+  return GPB_OK;
+}
+
 template <int KIND>
 static void launch_full(gpb_ctx* ctx, const FullArgs& a) {
   full_finish_kernel<KIND><<<grid1d((long long)a.M * a.M), 256, 0, ctx->stream>>>(a);

@@ -135,6 +135,20 @@ class Engine:
         self._check(self.lib.gpb_posterior_batch(self._h, ptr(hyp), hyp.shape[0], C.byref(h)))
         return PosteriorBatch(self, h, hyp.shape[0], self.N)
 
+    def posterior_append(self, post, x_new, y_new):
+        """Rank-one append of one training point to every sample of ``post``, in place on the
+        device (gaussian_process.py:737-844).  Returns the per-sample status (1 = the reference's
+        stability test failed; the batch must then be rebuilt), or None when the in-place update
+        does not apply (GPB_EAGAIN: point-dependent noise / no free row in the padded layout)."""
+        x_new = f64(x_new).reshape(-1)
+        status = np.zeros((post.count,), dtype=np.int32)
+        rc = self.lib.gpb_posterior_append(self._h, post._h, ptr(x_new), float(y_new), ptr(status))
+        if rc == 5:
+            return None
+        self._check(rc)
+        post.N = int(self.lib.gpb_posterior_size(post._h))
+        return status
+
     def predict(self, post, Xs, ys=None, s2s=None, add_noise=False, separate=False, want_lpd=False):
         Xs = f64(Xs)
         M = Xs.shape[0]

@@ -8,10 +8,14 @@ places where the reference loops over hyperparameter vectors one at a time are b
 the ``f_min_fill`` design (f_min_fill.py:174-176), the posterior rebuild in ``update``
 (gaussian_process.py:870-879) and the per-sample loop of ``predict`` (:1727).
 
-Not built: ``plot`` (matplotlib); a one-point ``update`` is done as a full (batched)
-recompute instead of the reference's rank-1 append -- same posterior, different cost.
+A one-point ``update`` takes the reference's rank-one path (:737-844) in place on the device
+(``gpb_posterior_append``) when the noise variance does not depend on the point; otherwise, and
+every 128th point (padded layout full), the batch is rebuilt -- same posterior up to rounding.
+
+Not built: ``plot`` (matplotlib).
 """
 import math
+import warnings
 import zlib
 
 import numpy as np
@@ -559,15 +563,29 @@ class GP:
     # ------------------------------------------------------------------ update / clean
     def update(self, X_new=None, y_new=None, s2_new=None, hyp=None, compute_posterior=True):
         """Add data and/or replace the hyperparameter samples (gaussian_process.py:691-884).
-        The posteriors of all samples are rebuilt in ONE batched GPU call."""
+        One new point without ``s2`` on a GP that already holds posteriors takes the reference's
+        rank-one path (:737-844), done in place on the device for all samples at once; everything
+        else rebuilds the posteriors of all samples in ONE batched GPU call."""
         X_new, y_new, s2_new = self._convert_shapes(X_new, y_new, s2_new)
+        rank_one = (X_new is not None and y_new is not None and compute_posterior
+                    and self.X is not None and self.y is not None
+                    and X_new.shape[0] == 1 and y_new.shape[0] == 1 and s2_new is None)   # :738-748
+        appended = False
+        if rank_one:
+            appended = self._rank_one_append(X_new, y_new)
         if X_new is not None:
             self.X = X_new.copy() if self.X is None else np.concatenate((self.X, X_new))
         if y_new is not None:
             self.y = y_new.copy() if self.y is None else np.concatenate((self.y, y_new))
         if s2_new is not None:
             self.s2 = s2_new.copy() if self.s2 is None else np.concatenate((self.s2, s2_new))
-        hyp = self.get_hyperparameters(as_array=True) if hyp is None else np.array(hyp, dtype=float)
+        if appended:
+            return
+        if rank_one and self.posteriors is not None:
+            # the rank-one branch keeps the current samples and ignores ``hyp`` (:864-868)
+            hyp = np.array([p.hyp for p in self.posteriors], dtype=float)
+        else:
+            hyp = self.get_hyperparameters(as_array=True) if hyp is None else np.array(hyp, dtype=float)
         if hyp.ndim == 1:
             hyp = hyp.reshape(1, -1)
         if compute_posterior and self.X is not None and self.y is not None:
@@ -577,6 +595,27 @@ class GP:
             self.posteriors = np.empty((hyp.shape[0],), dtype=object)
             for i in range(hyp.shape[0]):
                 self.posteriors[i] = Posterior(hyp[i, :], None, None, None, None, None)
+
+    def _rank_one_append(self, X_new, y_new):
+        """The device rank-one update; False when it does not apply or was unstable (the caller
+        then rebuilds all samples, which the reference does per unstable sample, :864-868)."""
+        batch = self._post_batch
+        if batch is None or batch._h is None or self.posteriors is None or \
+                any(p._batch is not batch for p in self.posteriors):
+            return False
+        status = batch.engine.posterior_append(batch, X_new[0], float(y_new[0, 0]))
+        if status is None:
+            return False
+        if status.any():
+            for s in np.flatnonzero(status):
+                warnings.warn("Rank-one update of Cholesky factor unstable "
+                              + f"for posterior {s}. Reverting to full update.", stacklevel=3)
+            return False
+        for p in self.posteriors:                 # alpha, sW, L changed on the device
+            for k in ("alpha", "sW", "L"):
+                p._have[k] = False
+                p._val[k] = None
+        return True
 
     def clean(self):
         """Drop the factors (gaussian_process.py:886-905); ``update()`` rebuilds them."""

@@ -32,7 +32,8 @@ enum {
   GPB_EINVAL = 1,    /* bad argument / unsupported shape */
   GPB_ECUDA = 2,     /* CUDA runtime error (text in gpb_last_error) */
   GPB_ENOMEM = 3,    /* workspace does not fit on the device */
-  GPB_ESTATE = 4     /* call order: model/data not set */
+  GPB_ESTATE = 4,    /* call order: model/data not set */
+  GPB_EAGAIN = 5     /* gpb_posterior_append: not applicable here, do the full rebuild */
 };
 /* gpb_posterior_fetch fields -- the members of Posterior, gaussian_process.py:2568-2586 */
 enum {
@@ -90,6 +91,18 @@ int gpb_posterior_batch(gpb_ctx* ctx, const double* hyp, int64_t B, gpb_post** o
 int64_t gpb_posterior_count(const gpb_post* post);
 int gpb_posterior_fetch(const gpb_post* post, int64_t b, int field, double* out);
 void gpb_posterior_free(gpb_post* post);
+/* Number of training points the factors of `post` currently cover. */
+int64_t gpb_posterior_size(const gpb_post* post);
+/* Rank-one update of GP.update, gaussian_process.py:737-844: append ONE training point
+ * (x_new (D), y_new, no s2) to every sample of `post`, in place on the device.
+ *   status[s] = 1  <=>  the reference's stability test fails for sample s
+ *   (sqrt_arg <= 0, :784-798, "Rank-one update of Cholesky factor unstable"): that sample
+ *   is left untouched and the caller rebuilds the batch with gpb_posterior_batch.
+ * Returns GPB_EAGAIN (nothing changed) when the in-place update does not apply: the noise
+ * variance depends on the point (user-provided or output-dependent terms), or the padded
+ * device layout has no free row left (every 128 points) -- rebuild with gpb_posterior_batch. */
+int gpb_posterior_append(gpb_ctx* ctx, gpb_post* post, const double* x_new, double y_new,
+                         int32_t* status);
 
 /* GP.predict, gaussian_process.py:1663-1816, over all samples of `post`.
  *   Xs (M,D); ys (M) or NULL; s2s (M) or NULL; outputs mu, s2 [, lpd]:

@@ -454,7 +454,46 @@ def gen_next():
     print("next.npz", len(out), "arrays; low-noise L_chol", out["lown.L_chol"])
 
 
+def gen_rank1():
+    """the rank-one branch of GP.update (gaussian_process.py:737-844).  Half the
+    data through a full update, then one point at a time across a 128-row tile boundary."""
+    out = {}
+    rng = np.random.default_rng(600)
+    cases = [("se", COVS[0], 1, False), ("mat5", COVS[3], 2, False), ("rq", COVS[4], 0, False),
+             ("mat3iso", COVS[7], 1, False), ("lown", COVS[0], 1, True)]
+    for tag, cov, mk, lownoise in cases:
+        N0, NA, D, B = 123, 8, 3, 2
+        X, y = synth(rng, N0 + NA, D)
+        npar = (1, 0, 0)
+        gp = make_gp(D, cov, mk, npar)
+        hyps = benign_hyp(rng, B, D, cov, mk, npar, y)
+        if lownoise:
+            cov_n = cov[4]().hyperparameter_count(D)
+            hyps[:, cov_n] = np.log(3e-4)          # noise variance 9e-8 < 1e-6: low-noise branch
+            hyps[:, :D] = np.log(0.6)
+        gp.update(X_new=X[:N0], y_new=y[:N0], hyp=hyps)
+        for i in range(N0, N0 + NA):
+            gp.update(X_new=X[i:i + 1], y_new=y[i:i + 1])
+        Xs = rng.uniform(-3, 3, (6, D))
+        mu, s2 = gp.predict(Xs, add_noise=True, separate_samples=True)
+        out[f"{tag}.spec"] = np.array([D, cov[1], cov[2], cov[3], mk, *npar])
+        out[f"{tag}.X"], out[f"{tag}.y"], out[f"{tag}.hyp"] = X, y, hyps
+        out[f"{tag}.N0"] = np.array(N0)
+        out[f"{tag}.alpha"] = np.stack([p.alpha.reshape(-1) for p in gp.posteriors])
+        out[f"{tag}.sW"] = np.stack([p.sW.reshape(-1) for p in gp.posteriors])
+        out[f"{tag}.L"] = np.stack([p.L for p in gp.posteriors])
+        out[f"{tag}.L_chol"] = np.array([int(p.L_chol) for p in gp.posteriors])
+        out[f"{tag}.sn2_mult"] = np.array([float(p.sn2_mult) for p in gp.posteriors])
+        out[f"{tag}.Xs"], out[f"{tag}.mu"], out[f"{tag}.s2"] = Xs, mu, s2
+    np.savez_compressed(os.path.join(HERE, "rank1.npz"), **out)
+    print("rank1.npz", len(out), "arrays; L_chol", [out[f"{c[0]}.L_chol"].tolist() for c in cases])
+
+
 if __name__ == "__main__":
+    if "rank1" in sys.argv[1:]:
+        gen_rank1()
+        sys.exit(0)
+    gen_rank1()
     gen_next()
     gen_fit()
     gen_host()

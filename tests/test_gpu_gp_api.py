@@ -264,3 +264,72 @@ def test_random_function_matches_reference_draws():
     np.random.seed(12)
     pdraw = gp0.random_function(c["Xs"])
     assert np.max(np.abs(pdraw - c["prior_draw"])) <= 1e-6 * (1 + np.max(np.abs(c["prior_draw"])))
+
+
+@pytest.mark.parametrize("tag", ["se", "mat5", "rq", "mat3iso", "lown"])
+def test_rank_one_update_matches_reference(tag):
+    """GP.update with one point at a time (gaussian_process.py:737-844; the reference's own test is
+    testing/test_gaussian_process.py:387-411) against the posteriors the REAL reference holds after
+    the same sequence of rank-one updates; the appends run in place on the device."""
+    c = case(_load("rank1.npz"), tag)
+    N0 = int(c["N0"])
+    X, y = c["X"], c["y"]
+    gp = build_gp(c["spec"])
+    gp.update(X_new=X[:N0], y_new=y[:N0], hyp=c["hyp"])
+    calls = {"n": 0, "declined": 0}
+    eng = gp.engine
+    inner = eng.posterior_append
+
+    def counted(post, x_new, y_new):
+        st = inner(post, x_new, y_new)
+        calls["n"] += 1
+        calls["declined"] += st is None
+        return st
+
+    eng.posterior_append = counted
+    launches0 = eng.launch_count()
+    for i in range(N0, X.shape[0]):
+        gp.update(X_new=X[i:i + 1], y_new=y[i:i + 1])
+        assert gp._post_batch.N == i + 1
+    # every update tried the device append; only the one at the 128-row tile boundary was a rebuild
+    assert calls == {"n": X.shape[0] - N0, "declined": 1}
+    assert eng.launch_count() > launches0
+    assert np.array_equal(gp.X, X) and np.array_equal(gp.y, y)
+    for b, p in enumerate(gp.posteriors):
+        np.testing.assert_array_equal(p.hyp, c["hyp"][b])
+        assert p.L_chol == bool(c["L_chol"][b]) and p.sn2_mult == c["sn2_mult"][b]
+        assert p.alpha.shape == (X.shape[0], 1) and p.sW.shape == (X.shape[0], 1)
+        tol = 1e-8 if p.L_chol else 1e-6          # low noise: L = -inverse, cond ~ 1e7
+        assert np.max(np.abs(p.alpha[:, 0] - c["alpha"][b])) <= tol * np.max(np.abs(c["alpha"][b]))
+        assert np.max(np.abs(p.sW[:, 0] - c["sW"][b])) <= 1e-12 * np.max(np.abs(c["sW"][b]))
+        assert p.L.shape == c["L"][b].shape
+        assert np.max(np.abs(p.L - c["L"][b])) <= tol * np.max(np.abs(c["L"][b]))
+    mu, s2 = gp.predict(c["Xs"], add_noise=True, separate_samples=True)
+    assert np.max(np.abs(mu - c["mu"])) <= 1e-8 * (1 + np.max(np.abs(c["mu"])))
+    assert np.max(np.abs(s2 - c["s2"])) <= 1e-8 * np.max(np.abs(c["s2"]))
+    # and the in-place result agrees with a full rebuild of the same posterior
+    gp_full = build_gp(c["spec"])
+    gp_full.update(X_new=X, y_new=y, hyp=c["hyp"])
+    for p, q in zip(gp.posteriors, gp_full.posteriors):
+        tol = 1e-8 if p.L_chol else 1e-6
+        assert np.max(np.abs(p.alpha - q.alpha)) <= tol * np.max(np.abs(q.alpha))
+        assert np.max(np.abs(p.L - q.L)) <= tol * np.max(np.abs(q.L))
+    # nlZ on the grown data set still goes through (engine data re-synchronised)
+    nlz = gp._GP__compute_nlZ(c["hyp"][0], False, False)
+    assert nlz == gp_full._GP__compute_nlZ(c["hyp"][0], False, False)
+
+
+def test_rank_one_declined_for_point_dependent_noise():
+    """User-provided / output-dependent noise: the in-place append does not apply; update()
+    rebuilds the batch and the result is the full posterior."""
+    rng = np.random.default_rng(5)
+    X = rng.uniform(-2, 2, (40, 2))
+    y = np.sin(X.sum(1, keepdims=True))
+    gp = g.GP(2, SquaredExponential(), ConstantMean(), GaussianNoise(constant_add=True, rectified_linear_output_dependent_add=True))
+    hyp = np.array([[0.1, -0.2, 0.3, np.log(0.1), 0.5, np.log(0.2), 0.2]])
+    gp.update(X_new=X[:-1], y_new=y[:-1], hyp=hyp)
+    assert gp.engine.posterior_append(gp._post_batch, X[-1], float(y[-1, 0])) is None
+    gp.update(X_new=X[-1:], y_new=y[-1:])
+    ref = g.GP(2, SquaredExponential(), ConstantMean(), GaussianNoise(constant_add=True, rectified_linear_output_dependent_add=True))
+    ref.update(X_new=X, y_new=y, hyp=hyp)
+    np.testing.assert_array_equal(gp.posteriors[0].alpha, ref.posteriors[0].alpha)

@@ -215,3 +215,63 @@ def test_convert_shapes_and_posterior_record():
     assert (p.alpha, p.sW, p.L, p.sn2_mult, p.L_chol) == (1, 2, 3, 4, True)
     gp.clean()
     assert gp.posteriors[0].L is None
+
+
+def test_rank_one_update_host_logic():
+    """update() with one new point: device append when it applies, otherwise (declined, or the
+    reference's stability test failed, gaussian_process.py:790-798) a rebuild of all samples with the
+    CURRENT hyperparameter samples -- the ``hyp`` argument is ignored on this branch (:864-868)."""
+    from gpyreg_b200.gaussian_process import Posterior
+
+    class FakeEngine:
+        def __init__(self, status):
+            self.status, self.calls = status, []
+
+        def posterior_append(self, post, x_new, y_new):
+            self.calls.append((np.array(x_new), y_new))
+            if self.status is not None and not np.any(self.status):
+                post.N += 1
+            return self.status
+
+    class FakeBatch:
+        def __init__(self, engine):
+            self.engine, self._h, self.N, self.count = engine, 1, 5, 2
+
+    def make(status):
+        gp = g.GP(2, SquaredExponential(), ConstantMean(), GaussianNoise(constant_add=True))
+        gp.X, gp.y = np.zeros((5, 2)), np.zeros((5, 1))
+        batch = FakeBatch(FakeEngine(status))
+        gp._post_batch = batch
+        gp.posteriors = np.empty((2,), dtype=object)
+        for s in range(2):
+            gp.posteriors[s] = Posterior(np.full(5, float(s)), None, None, None, None, None, _batch=batch, _index=s)
+            gp.posteriors[s]._set("alpha", np.zeros((5, 1)))
+        rebuilt = []
+
+        def fake_posteriors_for(hyp):
+            rebuilt.append(hyp.copy())
+            return gp.posteriors, batch
+
+        gp._posteriors_for = fake_posteriors_for
+        return gp, batch, rebuilt
+
+    x, y = np.array([[1.0, 2.0]]), np.array([[3.0]])
+    # stable append: no rebuild, cached fields invalidated, data grown
+    gp, batch, rebuilt = make(np.zeros(2, dtype=np.int32))
+    gp.update(X_new=x, y_new=y, hyp=np.full((1, 5), 9.0))
+    assert rebuilt == [] and batch.N == 6 and gp.X.shape == (6, 2) and gp.y.shape == (6, 1)
+    assert not gp.posteriors[0]._have["alpha"] and len(batch.engine.calls) == 1
+    assert batch.engine.calls[0][1] == 3.0 and np.array_equal(batch.engine.calls[0][0], [1.0, 2.0])
+    # unstable sample: warning with the reference's text, rebuild with the samples' own hyp
+    gp, batch, rebuilt = make(np.array([0, 1], dtype=np.int32))
+    with pytest.warns(UserWarning, match="Rank-one update of Cholesky factor unstable for posterior 1"):
+        gp.update(X_new=x, y_new=y, hyp=np.full((1, 5), 9.0))
+    assert len(rebuilt) == 1 and np.array_equal(rebuilt[0], [[0.0] * 5, [1.0] * 5]) and gp.X.shape == (6, 2)
+    # declined by the library (GPB_EAGAIN): silent rebuild
+    gp, batch, rebuilt = make(None)
+    gp.update(X_new=x, y_new=y)
+    assert len(rebuilt) == 1 and rebuilt[0].shape == (2, 5)
+    # two points at once, or s2 given: never the rank-one branch; ``hyp`` is honoured
+    gp, batch, rebuilt = make(np.zeros(2, dtype=np.int32))
+    gp.update(X_new=np.zeros((2, 2)), y_new=np.zeros((2, 1)), hyp=np.full((1, 5), 9.0))
+    assert batch.engine.calls == [] and np.array_equal(rebuilt[0], np.full((1, 5), 9.0))
