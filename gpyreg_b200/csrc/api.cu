@@ -39,6 +39,11 @@ struct Bufs {              // device storage for `cap` batch slots
 struct gpb_ctx {
   int device = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr;
+  // look-ahead of the blocked Cholesky: the part of an outer trailing update the next outer
+  // block does not touch runs on `aux` while the main stream factors that block
+  cudaStream_t aux = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int lookahead = 1;         // env GPB_LOOKAHEAD: 0 off, 1 small batches (default), 2 always
   std::string err;
   Model md{};
   bool has_model = false, has_data = false;
@@ -239,6 +244,15 @@ extern "C" int gpb_create(int device, gpb_ctx** out) {
     return GPB_ECUDA;
   }
   ctx->stream = ctx->own_stream;
+  e = cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    g_create_err = std::string("aux stream/events: ") + cudaGetErrorString(e);
+    delete ctx;
+    return GPB_ECUDA;
+  }
+  if (const char* la = getenv("GPB_LOOKAHEAD")) ctx->lookahead = atoi(la);
   if (const char* bn = getenv("GPB_GEMM_BN")) ctx->gemm_bn = (atoi(bn) == 128) ? 128 : 64;
   if (const char* ld = getenv("GPB_LOADER"))
     ctx->loader = (strcmp(ld, "tma") == 0) ? 1 : (strcmp(ld, "cpasync") == 0 ? 0 : 2);
@@ -286,6 +300,9 @@ extern "C" void gpb_destroy(gpb_ctx* ctx) {
     if (q) cudaFree(q);
   for (auto& ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->aux) cudaStreamDestroy(ctx->aux);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -543,6 +560,8 @@ static void run_potrf(gpb_ctx* ctx, Bufs& b, long long N, const int* sel, int ns
                       bool with_rhs = true) {
   const BatchBufs bb = batch_bufs(b, sel, N);
   const int Nt = b.Nt, OB = ctx->outer_block;          // outer block = OB tile columns
+  const bool look = ctx->lookahead == 2 || (ctx->lookahead == 1 && nsel <= 8);
+  bool joined_pending = false;
   for (int k = 0; k < Nt; ++k) {
     DiagArgs da;
     da.Abuf = b.Abuf;
@@ -575,10 +594,34 @@ static void run_potrf(gpb_ctx* ctx, Bufs& b, long long N, const int* sel, int ns
       launch_gemm(ctx, OpSyrk{bb, k, 1, k + 1, obe}, dim3((unsigned)cnt, (unsigned)nsel));
     }
     if (k + 1 == obe && obe < Nt) {                    // outer block done: update the rest, long K
-      const int cnt = OpSyrk::count(Nt, obe, Nt);
-      launch_gemm(ctx, OpSyrk{bb, ob0, obe - ob0, obe, Nt}, dim3((unsigned)cnt, (unsigned)nsel));
+      const int kw = obe - ob0;
+      const int obe2 = std::min(obe + OB, Nt);         // end of the NEXT outer block
+      if (joined_pending) {                            // the previous remainder wrote these tiles
+        cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
+        joined_pending = false;
+      }
+      if (!look || obe2 >= Nt) {
+        const int cnt = OpSyrk::count(Nt, obe, Nt);
+        launch_gemm(ctx, OpSyrk{bb, ob0, kw, obe, Nt}, dim3((unsigned)cnt, (unsigned)nsel));
+      } else {
+        // look-ahead: the next outer block only needs its own tile columns [obe, obe2); the rest
+        // of the update, columns [obe2, Nt), runs on the aux stream while the main stream
+        // factors that block (one CTA per matrix in diag_kernel leaves the GPU idle otherwise)
+        cudaEventRecord(ctx->ev_fork, ctx->stream);    // panels of [ob0, obe) are complete
+        launch_gemm(ctx, OpSyrk{bb, ob0, kw, obe, obe2},
+                    dim3((unsigned)OpSyrk::count(Nt, obe, obe2), (unsigned)nsel));
+        cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0);
+        cudaStream_t main_stream = ctx->stream;
+        ctx->stream = ctx->aux;
+        launch_gemm(ctx, OpSyrk{bb, ob0, kw, obe2, Nt},
+                    dim3((unsigned)OpSyrk::count(Nt, obe2, Nt), (unsigned)nsel));
+        ctx->stream = main_stream;
+        cudaEventRecord(ctx->ev_join, ctx->aux);
+        joined_pending = true;
+      }
     }
   }
+  if (joined_pending) cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
 }
 
 // alpha = L^-T z / sl

@@ -40,56 +40,149 @@ __device__ __forceinline__ void dmma_t(double& d0, double& d1, double a, double 
 
 // --- 32x32 diagonal block in registers, one row per lane; every register index is a
 // compile-time constant (the steps are instantiated through a fold expression).
+//  * The lane's own diagonal entry lives in a separate register `dg`: its update
+//    dg -= L(lane,J)^2 needs no other lane, so the pivot -> rsqrt -> scale -> next pivot chain is one
+//    shuffle, one MUFU and five dependent FP64 operations per step.
+//  * rsqrt is written out (MUFU seed, relative error 2^-22.4, then one third-order step -- the
+//    arithmetic of the library's main path) so that the scaling of the column is folded into its
+//    last FMA: L(lane,J) = a*y0 + (a*y0*e)*p.
+//  * The finished column is broadcast through shared memory (one 8-byte store per lane, 16-byte
+//    loads): a 64-bit warp shuffle per element costs two slots of the slow shuffle pipe, which
+//    was what bounded this loop.
+//  * A pivot <= 0 or NaN only raises the flag (LAPACK dpotrf: info > 0): the NaNs it produces
+//    flow through harmlessly and the host retries that matrix with more jitter.
 template <int J>
-__device__ __forceinline__ void chol32_step(double (&arow)[SB], int lane, double* rsq_blk, int& failed,
-                                            bool publish) {
-  double piv = __shfl_sync(0xffffffffu, arow[J], J);
-  if (!(piv > 0.0)) { failed = 1; piv = 1.0; }       // LAPACK dpotrf: ajj <= 0 or NaN -> info > 0
-  // branch-free: on lane J arow[J] IS the pivot, so one predicated multiply gives
-  // L_JJ = piv * rsqrt(piv) there and L_rJ = a_rJ * rsqrt(piv) below it (a divergent
-  // if/else here makes the compiler clone the rsqrt sequence into every branch)
-  const double rinv = rsqrt(piv);
-  const double scaled = ((lane == J) ? piv : arow[J]) * rinv;
-  arow[J] = (lane >= J) ? scaled : arow[J];
-  // all broadcasts first, then the rank-1 update: the shuffles pipeline instead of each FMA
-  // waiting for its own shuffle
-  double l[SB];
+__device__ __forceinline__ void chol32_step(double (&arow)[SB], double& dg, double& rdiag, double& piv,
+                                            int lane, int& failed, double* colbuf) {
+  if (!(piv > 0.0)) failed = 1;
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(piv));
+  const double a = (lane == J) ? dg : arow[J];        // the diagonal lane scales the pivot itself
+  const double ay0 = a * y0;
+  const double e = fma(-(y0 * y0), piv, 1.0);
+  const double p = fma(e, 0.375, 0.5);
+  const double lj = fma(p, ay0 * e, ay0);             // a / sqrt(piv)
+  if (lane == J) {
+    dg = lj;                                          // L(J, J)
+    rdiag = fma(p, y0 * e, y0);                       // 1 / L(J, J)
+  }
+  if (lane > J) {
+    arow[J] = lj;
+    dg = fma(-lj, lj, dg);
+  }
+  if (J + 1 < SB) {
+    piv = __shfl_sync(0xffffffffu, dg, J + 1);        // next pivot first: it heads the chain
+    double* cb = colbuf + (J & 1) * SB;               // double-buffered: no WAR hazard across steps
+    cb[lane] = lj;                                    // L(lane, J), valid for lanes > J
+    __syncwarp();
+    constexpr int CS = (J + 1) & ~1;
 #pragma unroll
-  for (int c = J + 1; c < SB; ++c) l[c] = __shfl_sync(0xffffffffu, arow[J], c);
-#pragma unroll
-  for (int c = J + 1; c < SB; ++c)
-    if (lane >= c) arow[c] -= arow[J] * l[c];
+    for (int c = CS; c < SB; c += 2) {
+      const double2 v = *reinterpret_cast<const double2*>(cb + c);
+      if (c > J && lane > c) arow[c] = fma(-lj, v.x, arow[c]);
+      if (lane > c + 1) arow[c + 1] = fma(-lj, v.y, arow[c + 1]);
+    }
+  }
 }
 template <int... Js>
-__device__ __forceinline__ void chol32_all(double (&arow)[SB], int lane, double* rsq_blk, int& failed,
-                                           bool publish, std::integer_sequence<int, Js...>) {
-  (chol32_step<Js>(arow, lane, rsq_blk, failed, publish), ...);
+__device__ __forceinline__ void chol32_all(double (&arow)[SB], double& dg, double& rdiag, double& piv,
+                                           int lane, int& failed, double* colbuf,
+                                           std::integer_sequence<int, Js...>) {
+  (chol32_step<Js>(arow, dg, rdiag, piv, lane, failed, colbuf), ...);
 }
-// lane c owns column c of Inv = L^-1: inv[q] = Inv(q, c)
-template <int RR>
-__device__ __forceinline__ void inv32_step(const double (&arow)[SB], double (&inv)[SB], int lane,
-                                           const double* rsq_blk) {
-  if (RR == 0) return;
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  double lr[SB];
+
+// Inverse of the 32x32 factor, both 16x16 diagonal halves at once in one warp: lane (h, c), h = lane & 16,
+// c = lane & 15, owns column c of the inverse of the half-block L_hh: inv[q] = Inv_hh(q, c).
+// Right-looking: once x_Q = inv[Q] is final it is pushed into the partial sums of the rows below,
+// then row Q+1 is finished -- the chain from x_Q to x_{Q+1} is one FMA and one multiply.  The factor
+// is read back from shared memory (it was just stored there), two rows per 16-byte load.  The
+// off-diagonal block Inv_21 = -Inv_22 L_21 Inv_11 is two 16x16x16 products on the tensor pipe.
+constexpr int HB = SB / 2;
+template <int Q>
+__device__ __forceinline__ void inv16_step(const double* Lcol, const double* rd, double (&inv)[HB],
+                                           int lane) {
+  if (Q >= HB - 1) return;
+  // Lcol -> L(h, h) of this lane's half; column h+Q of the factor, rows h+Q+1 .. h+15
+  const double* col = Lcol + Q * DP_PITCH;
+  const int cc = lane & (HB - 1);
+  constexpr int RS = (Q + 1) & ~1;
 #pragma unroll
-  for (int q = 0; q < RR; ++q) lr[q] = __shfl_sync(0xffffffffu, arow[q], RR);   // L(RR, q) from lane RR
-#pragma unroll
-  for (int q = 0; q < RR; ++q) {
-    if ((q & 3) == 0) s0 += lr[q] * inv[q];
-    else if ((q & 3) == 1) s1 += lr[q] * inv[q];
-    else if ((q & 3) == 2) s2 += lr[q] * inv[q];
-    else s3 += lr[q] * inv[q];
+  for (int r = RS; r < HB; r += 2) {
+    const double2 v = *reinterpret_cast<const double2*>(col + r);     // L(h+r, h+Q), L(h+r+1, h+Q)
+    if (r > Q && cc < r) inv[r] = fma(v.x, inv[Q], inv[r]);
+    if (cc < r + 1) inv[r + 1] = fma(v.y, inv[Q], inv[r + 1]);
   }
-  s0 += s2;
-  s1 += s3;
-  const double drr = rsq_blk[RR];
-  if (lane < RR) inv[RR] = -(s0 + s1) * drr;
+  const double dn = rd[Q + 1];                                        // 1 / L(h+Q+1, h+Q+1)
+  if (cc < Q + 1) inv[Q + 1] = -inv[Q + 1] * dn;
 }
-template <int... Rs>
-__device__ __forceinline__ void inv32_all(const double (&arow)[SB], double (&inv)[SB], int lane,
-                                          const double* rsq_blk, std::integer_sequence<int, Rs...>) {
-  (inv32_step<Rs>(arow, inv, lane, rsq_blk), ...);
+template <int... Qs>
+__device__ __forceinline__ void inv16_all(const double* Lcol, const double* rd, double (&inv)[HB],
+                                          int lane, std::integer_sequence<int, Qs...>) {
+  (inv16_step<Qs>(Lcol, rd, inv, lane), ...);
+}
+
+// Factor the 32x32 diagonal block at (c0, c0) of the tile S (one warp): Cholesky in registers,
+// factor back to S, inverse of the factor to Ivp.  Kept out of line so that its register
+// allocation and instruction schedule do not depend on the rest of diag_kernel.
+__device__ __noinline__ int factor_block32(double* S, double* Ivp, double* Tm, int c0, int lane) {
+  const int g = lane >> 2, tq = lane & 3;
+  double* colbuf = Tm;               // [2][32] column broadcast buffers
+  double* rd = Tm + 2 * SB;          // [32] 1 / L_rr
+  double arow[SB];                   // strictly lower part of the lane's row; the diagonal is dg
+#pragma unroll
+  for (int c = 0; c < SB; ++c) arow[c] = (c < lane) ? S[(c0 + c) * DP_PITCH + c0 + lane] : 0.0;
+  double dg = S[(c0 + lane) * DP_PITCH + c0 + lane];
+  int failed = 0;
+  double rdiag = 0.0;                // 1 / L_rr of the lane's own row
+  double piv = __shfl_sync(0xffffffffu, dg, 0);
+  chol32_all(arow, dg, rdiag, piv, lane, failed, colbuf, std::make_integer_sequence<int, SB>{});
+#pragma unroll
+  for (int c = 0; c < SB; ++c)
+    if (c < lane) S[(c0 + c) * DP_PITCH + c0 + lane] = arow[c];
+  S[(c0 + lane) * DP_PITCH + c0 + lane] = dg;
+  rd[lane] = rdiag;
+  __syncwarp();
+  // inverses of the two 16x16 diagonal halves
+  const int h = lane & HB;
+  double inv[HB];
+#pragma unroll
+  for (int q = 0; q < HB; ++q) inv[q] = (q == (lane & (HB - 1))) ? rdiag : 0.0;
+  inv16_all(S + (c0 + h) * DP_PITCH + c0 + h, rd + h, inv, lane, std::make_integer_sequence<int, HB>{});
+#pragma unroll
+  for (int q = 0; q < HB; ++q) Ivp[lane * IVP + h + q] = inv[q];     // column `lane`, rows h..h+15
+  __syncwarp();
+  // Inv_21 = -Inv_22 (L_21 Inv_11): four 8x8 output blocks, K = 16, on DMMA
+  double t[2][2][2];
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 2; ++ni) {
+      t[mi][ni][0] = t[mi][ni][1] = 0.0;
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+        const double af = S[(c0 + k4 * 4 + tq) * DP_PITCH + c0 + HB + mi * 8 + g];   // L_21(m, k)
+        const double bf = Ivp[(ni * 8 + g) * IVP + k4 * 4 + tq];                     // Inv_11(k, n)
+        dmma_t(t[mi][ni][0], t[mi][ni][1], af, bf);
+      }
+      Tm[(ni * 8 + 2 * tq) * IVP + mi * 8 + g] = t[mi][ni][0];
+      Tm[(ni * 8 + 2 * tq + 1) * IVP + mi * 8 + g] = t[mi][ni][1];
+    }
+  __syncwarp();
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 2; ++ni) {
+      double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+        const double af = -Ivp[(HB + k4 * 4 + tq) * IVP + HB + mi * 8 + g];          // -Inv_22(m, k)
+        const double bf = Tm[(ni * 8 + g) * IVP + k4 * 4 + tq];                      // T(k, n)
+        dmma_t(d0, d1, af, bf);
+      }
+      Ivp[(ni * 8 + 2 * tq) * IVP + HB + mi * 8 + g] = d0;
+      Ivp[(ni * 8 + 2 * tq + 1) * IVP + HB + mi * 8 + g] = d1;
+    }
+  return failed;
 }
 
 // One CTA factors a 128x128 diagonal tile and inverts the factor.
@@ -123,10 +216,11 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
   const int nact = min(T, a.N - k * T);         // rows/cols holding data (the rest is identity)
   const int nact8 = (nact + 7) & ~7;
 
-  // whole tile with 16-byte async copies (all in flight at once); the strict upper triangle
-  // holds the symmetric counterpart, which nothing reads before it is overwritten
+  // lower triangle of the tile with 16-byte async copies (all in flight at once); nothing reads
+  // the strict upper triangle of S before it is overwritten
   for (int e = tid; e < T * T / 2; e += 256) {
     const int r2 = (e & 63) * 2, c = e >> 6;
+    if (r2 + 1 < c) continue;                         // chunk entirely above the diagonal
     const unsigned dst = (unsigned)__cvta_generic_to_shared(S + c * DP_PITCH + r2);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(A + (long long)c * Np + r2));
   }
@@ -151,38 +245,7 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
     // ---- 1. diagonal block in registers (warp 0 only: the SM's shuffle unit is shared, so
     // redundant copies in the other warps would slow this one down): lane r owns row r
     if (warp == 0) {
-      double arow[SB];
-#pragma unroll
-      for (int c = 0; c < SB; ++c) arow[c] = (c <= lane) ? S[(c0 + c) * DP_PITCH + c0 + lane] : 0.0;
-      int failed = 0;
-      const bool pub = (warp == 0);
-      chol32_all(arow, lane, rsq + c0, failed, pub, std::make_integer_sequence<int, SB>{});
-      if (failed && pub && lane == 0) s_failed = 1;
-      {                                // 1 / L_rr of the lane's own row (select chain: static indices)
-        double dl = 1.0;
-#pragma unroll
-        for (int c = 0; c < SB; ++c) dl = (c == lane) ? arow[c] : dl;
-        rsq[c0 + lane] = 1.0 / dl;
-      }
-      __syncwarp();                    // rsq[] is published
-      STAMP();
-      if (pub) {
-#pragma unroll
-        for (int c = 0; c < SB; ++c)
-          if (c <= lane) S[(c0 + c) * DP_PITCH + c0 + lane] = arow[c];
-      }
-      // inverse of the 32x32 factor: lane c owns column c; inv[q] = Inv(q, c)
-      double inv[SB];
-      {
-        const double dc = rsq[c0 + lane];
-#pragma unroll
-        for (int q = 0; q < SB; ++q) inv[q] = (q == lane) ? dc : 0.0;
-      }
-      inv32_all(arow, inv, lane, rsq + c0, std::make_integer_sequence<int, SB>{});
-      if (pub) {
-#pragma unroll
-        for (int q = 0; q < SB; ++q) Ivp[lane * IVP + q] = inv[q];
-      }
+      if (factor_block32(S, Ivp, Tm, c0, lane)) s_failed = 1;
     }
     __syncthreads();
     STAMP();
@@ -251,16 +314,22 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
 
   if (tid < T) lg[tid] = (tid < nact) ? log(S[tid * DP_PITCH + tid]) : 0.0;
   __syncthreads();
-  // write L_kk back (lower triangle)
-  for (int e = tid; e < T * T; e += 256) {
-    const int rr = e & (T - 1), c = e >> 7;
-    if (rr >= c) A[(long long)c * Np + rr] = S[c * DP_PITCH + rr];
+  // write L_kk back (lower triangle), two rows per 16-byte store
+  for (int e = tid; e < T * T / 2; e += 256) {
+    const int r2 = (e & 63) * 2, c = e >> 6;
+    if (r2 + 1 < c) continue;
+    const double2 v = *reinterpret_cast<const double2*>(S + c * DP_PITCH + r2);
+    if (r2 >= c) *reinterpret_cast<double2*>(A + (long long)c * Np + r2) = v;
+    else A[(long long)c * Np + r2 + 1] = v.y;
   }
-  if (tid == 0) {
-    double s = 0.0;
-    for (int j = 0; j < nact; ++j) s += lg[j];       // fixed order
-    a.logdet[(long long)slot * a.Nt + k] = s;
-    if (s_failed) a.fail[slot] = 1;
+  if (warp == 0) {                                     // sum of log L_jj, fixed order
+    double sl = (lg[lane] + lg[lane + 32]) + (lg[lane + 64] + lg[lane + 96]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sl += __shfl_xor_sync(0xffffffffu, sl, o);
+    if (lane == 0) {
+      a.logdet[(long long)slot * a.Nt + k] = sl;
+      if (s_failed) a.fail[slot] = 1;
+    }
   }
 
   __syncthreads();
@@ -336,22 +405,47 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
   double* Dk = a.Dbuf + ((long long)slot * a.Nt + k) * T * T;
   double* DTk = a.DTbuf + ((long long)slot * a.Nt + k) * T * T;
   double* Wd = a.Wbuf ? a.Wbuf + slot * a.smat + (long long)k * T + (long long)k * T * Np : nullptr;
-  for (int e = tid; e < T * T; e += 256) {
-    const int rr = e & (T - 1), c = e >> 7;          // element (rr, c) of D
-    const double v = (rr >= c) ? Dval(rr, c) : 0.0;
-    Dk[c * T + rr] = v;
-    if (Wd) Wd[(long long)c * Np + rr] = v;
-  }
-  for (int e = tid; e < T * T; e += 256) {
-    const int rr = e & (T - 1), c = e >> 7;          // element (rr, c) of D^T = D(c, rr)
-    DTk[c * T + rr] = (c >= rr) ? Dval(c, rr) : 0.0;
+  {
+    // thread = (row rr, column parity): per 32-column block the source is warp-uniform, so the
+    // shared-memory loads of a block are issued together ahead of the global stores
+    const int rr = tid & (T - 1), cpar = tid >> 7, rb = rr >> 5;
+#pragma unroll 1
+    for (int cb = 0; cb < T / SB; ++cb) {
+      double v[16], w[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int c = cb * SB + 2 * u + cpar;
+        // D(rr, c), rr >= c
+        v[u] = (cb == rb) ? ((rr >= c) ? Iv[cb * SB * IVP + (c & 31) * IVP + (rr & 31)] : 0.0)
+                          : ((cb < rb && rr < nact) ? S[rr * DP_PITCH + c] : 0.0);
+        // D^T(rr, c) = D(c, rr), c >= rr
+        w[u] = (cb == rb) ? ((c >= rr) ? Iv[cb * SB * IVP + (rr & 31) * IVP + (c & 31)] : 0.0)
+                          : ((cb > rb && c < nact) ? S[c * DP_PITCH + rr] : 0.0);
+      }
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int c = cb * SB + 2 * u + cpar;
+        Dk[c * T + rr] = v[u];
+        if (Wd) Wd[(long long)c * Np + rr] = v[u];
+        DTk[c * T + rr] = w[u];
+      }
+    }
   }
   if (a.zvec && tid < T) {
     const int rr = tid;
-    double s = 0.0;
-    if (rr < nact)
-      for (int c = 0; c <= rr; ++c) s = __fma_rn(Dval(rr, c), bsh[c], s);   // same order as diag_solve_kernel
-    a.zvec[(long long)slot * Np + k * T + rr] = s;
+    // four interleaved partial sums (c mod 4), same order as diag_solve_kernel
+    double s4[4] = {0.0, 0.0, 0.0, 0.0};
+    if (rr < nact) {
+      int c = 0;
+      for (; c + 3 <= rr; c += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) s4[u] = __fma_rn(Dval(rr, c + u), bsh[c + u], s4[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 3; ++u)
+        if (c + u <= rr) s4[u] = __fma_rn(Dval(rr, c + u), bsh[c + u], s4[u]);
+    }
+    a.zvec[(long long)slot * Np + k * T + rr] = __dadd_rn(__dadd_rn(s4[0], s4[1]), __dadd_rn(s4[2], s4[3]));
   }
   __syncthreads();
   STAMP();
@@ -379,10 +473,18 @@ __global__ void __launch_bounds__(T) diag_solve_kernel(DiagSolveArgs a) {
   __syncthreads();
   const int fslot = a.fsel ? a.fsel[blockIdx.x] : slot;
   const double* Dk = a.Dbuf + ((long long)fslot * a.Nt + a.k) * T * T;
-  double s = 0.0;
-  if (rr < nact)
-    for (int c = 0; c <= rr; ++c) s = __fma_rn(Dk[c * T + rr], bsh[c], s);
-  a.zvec[(long long)slot * a.Np + a.k * T + rr] = s;
+  double s4[4] = {0.0, 0.0, 0.0, 0.0};
+  if (rr < nact) {
+    int c = 0;
+    for (; c + 3 <= rr; c += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) s4[u] = __fma_rn(Dk[(c + u) * T + rr], bsh[c + u], s4[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 3; ++u)
+      if (c + u <= rr) s4[u] = __fma_rn(Dk[(c + u) * T + rr], bsh[c + u], s4[u]);
+  }
+  a.zvec[(long long)slot * a.Np + a.k * T + rr] = __dadd_rn(__dadd_rn(s4[0], s4[1]), __dadd_rn(s4[2], s4[3]));
 }
 
 struct VecArgs {
