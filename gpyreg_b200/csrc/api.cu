@@ -44,6 +44,8 @@ struct gpb_ctx {
   cudaStream_t aux = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int lookahead = 1;         // env GPB_LOOKAHEAD: 0 off, 1 small batches (default), 2 always
+  int la_chunk = 1 << 30;    // logical tiles per look-ahead launch (env GPB_LA_CHUNK; measured: uncut is best)
+  int la_ob = 0;             // outer block used with look-ahead (env GPB_LA_OB; 0 = 1 for <= 2 matrices, else 2)
   std::string err;
   Model md{};
   bool has_model = false, has_data = false;
@@ -237,14 +239,17 @@ extern "C" int gpb_create(int device, gpb_ctx** out) {
   gpb_ctx* ctx = new gpb_ctx();
   ctx->device = device;
   e = cudaSetDevice(device);
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+  int prio_lo = 0, prio_hi = 0;
+  if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  // the main stream carries the dependent chain of the factorisation: highest priority
+  if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->own_stream, cudaStreamNonBlocking, prio_hi);
   if (e != cudaSuccess) {
     g_create_err = std::string("cudaSetDevice/StreamCreate: ") + cudaGetErrorString(e);
     delete ctx;
     return GPB_ECUDA;
   }
   ctx->stream = ctx->own_stream;
-  e = cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking);
+  e = cudaStreamCreateWithPriority(&ctx->aux, cudaStreamNonBlocking, prio_lo);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   if (e != cudaSuccess) {
@@ -253,6 +258,8 @@ extern "C" int gpb_create(int device, gpb_ctx** out) {
     return GPB_ECUDA;
   }
   if (const char* la = getenv("GPB_LOOKAHEAD")) ctx->lookahead = atoi(la);
+  if (const char* lc = getenv("GPB_LA_CHUNK")) ctx->la_chunk = std::max(1, atoi(lc));
+  if (const char* lo = getenv("GPB_LA_OB")) ctx->la_ob = std::max(0, atoi(lo));
   if (const char* bn = getenv("GPB_GEMM_BN")) ctx->gemm_bn = (atoi(bn) == 128) ? 128 : 64;
   if (const char* ld = getenv("GPB_LOADER"))
     ctx->loader = (strcmp(ld, "tma") == 0) ? 1 : (strcmp(ld, "cpasync") == 0 ? 0 : 2);
@@ -559,7 +566,11 @@ static void run_prep_build(gpb_ctx* ctx, Bufs& b, const Model& md, long long N, 
 static void run_potrf(gpb_ctx* ctx, Bufs& b, long long N, const int* sel, int nsel, bool write_w,
                       bool with_rhs = true) {
   const BatchBufs bb = batch_bufs(b, sel, N);
-  const int Nt = b.Nt, OB = ctx->outer_block;          // outer block = OB tile columns
+  const bool look0 = ctx->lookahead == 2 || (ctx->lookahead == 1 && nsel <= 8);
+  const int Nt = b.Nt;                                 // outer block = OB tile columns
+  // with look-ahead the dependent chain (diag -> panel -> next column) decides, not GEMM
+  // efficiency: narrow outer blocks shorten it (measured, N=5000: B=1 5.0 -> 4.1 ms at OB=1)
+  const int OB = !look0 ? ctx->outer_block : (ctx->la_ob > 0 ? ctx->la_ob : (nsel <= 2 ? 1 : 2));
   const bool look = ctx->lookahead == 2 || (ctx->lookahead == 1 && nsel <= 8);
   bool joined_pending = false;
   for (int k = 0; k < Nt; ++k) {
@@ -613,8 +624,15 @@ static void run_potrf(gpb_ctx* ctx, Bufs& b, long long N, const int* sel, int ns
         cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0);
         cudaStream_t main_stream = ctx->stream;
         ctx->stream = ctx->aux;
-        launch_gemm(ctx, OpSyrk{bb, ob0, kw, obe2, Nt},
-                    dim3((unsigned)OpSyrk::count(Nt, obe2, Nt), (unsigned)nsel));
+        // (optionally in chunks; the low stream priority of aux already lets the main stream's
+        // CTAs in first, and chunking only added launch tails when measured)
+        const int total = OpSyrk::count(Nt, obe2, Nt);
+        const int chunk = std::max(1, ctx->la_chunk / std::max(nsel, 1));
+        for (int t0 = 0; t0 < total; t0 += chunk) {
+          OpSyrk op{bb, ob0, kw, obe2, Nt};
+          op.bx0 = t0;
+          launch_gemm(ctx, op, dim3((unsigned)std::min(chunk, total - t0), (unsigned)nsel));
+        }
         ctx->stream = main_stream;
         cudaEventRecord(ctx->ev_join, ctx->aux);
         joined_pending = true;

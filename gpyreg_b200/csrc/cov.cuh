@@ -92,16 +92,31 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepArgs a) {
   double* resid = a.resid + (long long)slot * Np;
   double* sn2v = a.sn2v + (long long)slot * Np;
 
+  // exp() of the length scales and of the mean's scales once per slot, not once per point
+  __shared__ double ells[MAXD], oms[MAXD];
+  if (threadIdx.x < D) {
+    ells[threadIdx.x] = exp(h[md.ard ? threadIdx.x : 0]);
+    oms[threadIdx.x] = (md.mean_kind == 2) ? exp(hm[1 + D + threadIdx.x]) : 1.0;
+  }
+  __syncthreads();
   double vmin = INFINITY;
   int anynan = 0;
   for (int i = threadIdx.x; i < Np; i += blockDim.x) {
     if (i < N) {
       const double* x = a.X + (long long)i * D;
-      for (int k = 0; k < D; ++k) {
-        const double ell = exp(h[md.ard ? k : 0]);
-        xs[(long long)k * Np + i] = scale_coord(md.cov_kind, md.ard, md.degree, x[k], ell);
+      for (int k = 0; k < D; ++k)
+        xs[(long long)k * Np + i] = scale_coord(md.cov_kind, md.ard, md.degree, x[k], ells[k]);
+      double m = 0.0;                                  // mean_value() with the hoisted exp
+      if (md.mean_kind == 1) m = hm[0];
+      else if (md.mean_kind == 2) {
+        double sq = 0.0;
+        for (int k = 0; k < D; ++k) {
+          const double z = (x[k] - hm[1 + k]) / oms[k];
+          sq += z * z;
+        }
+        m = hm[0] - 0.5 * sq;
       }
-      resid[i] = a.y[i] - mean_value(md.mean_kind, D, hm, x);
+      resid[i] = a.y[i] - m;
       const double v = noise_value(md.nz0, md.nz1, md.nz2, hn, true, a.y[i], a.s2 != nullptr,
                                    a.s2 ? a.s2[i] : 0.0);
       sn2v[i] = v;

@@ -501,6 +501,7 @@ struct OpSyrk {
   static constexpr bool SLOT_MAJOR = false;
   static constexpr int MODE = GM_BETA | GM_STORE;
   BatchBufs b; int k0, kw, jlo, jhi;
+  int bx0 = 0;     // first tile of this launch (a long update can be issued in chunks)
   // tile enumeration: column-major over the trapezoid {(i,j): jlo <= j < jhi, j <= i < Nt}
   __host__ __device__ static int count(int Nt, int jlo, int jhi) {
     const int nc = jhi - jlo;
@@ -509,7 +510,7 @@ struct OpSyrk {
   __device__ GemmTile resolve(int bx, int by) const {
     GemmTile t = empty_tile();
     const int slot = b.sel[by];
-    int j = jlo, rem = bx;
+    int j = jlo, rem = bx + bx0;
     while (rem >= b.Nt - j) { rem -= b.Nt - j; ++j; }      // at most jhi-jlo steps
     const int i = j + rem;
     double* base = b.Abuf + slot * b.smat;
