@@ -43,6 +43,9 @@ struct gpb_ctx {
   // block does not touch runs on `aux` while the main stream factors that block
   cudaStream_t aux = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int trtri = 2;             // env GPB_TRTRI: 2 recursive halving (default; as fast as the recurrence for large
+                             // batches, 4-5x faster for one matrix), 0 column recurrence, 1 recursive up to trtri_max
+  int trtri_max = 8;         // env GPB_TRTRI_MAX
   int lookahead = 1;         // env GPB_LOOKAHEAD: 0 off, 1 small batches (default), 2 always
   int la_chunk = 1 << 30;    // logical tiles per look-ahead launch (env GPB_LA_CHUNK; measured: uncut is best)
   int la_ob = 0;             // outer block used with look-ahead (env GPB_LA_OB; 0 = 1 for <= 2 matrices, else 2)
@@ -209,6 +212,8 @@ static int init_attrs(gpb_ctx* ctx) {
   CK(gemm_attr<OpSyrk>());
   CK(gemm_attr<OpHpass>());
   CK(gemm_attr<OpWrec>());
+  CK(gemm_attr<OpRecX>());
+  CK(gemm_attr<OpRecW>());
   CK(gemm_attr<OpSyrk2>());
   CK(gemm_attr<OpPred>());
   CK(cudaFuncSetAttribute(diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
@@ -258,6 +263,8 @@ extern "C" int gpb_create(int device, gpb_ctx** out) {
     return GPB_ECUDA;
   }
   if (const char* la = getenv("GPB_LOOKAHEAD")) ctx->lookahead = atoi(la);
+  if (const char* tr = getenv("GPB_TRTRI")) ctx->trtri = atoi(tr);
+  if (const char* tm = getenv("GPB_TRTRI_MAX")) ctx->trtri_max = atoi(tm);
   if (const char* lc = getenv("GPB_LA_CHUNK")) ctx->la_chunk = std::max(1, atoi(lc));
   if (const char* lo = getenv("GPB_LA_OB")) ctx->la_ob = std::max(0, atoi(lo));
   if (const char* bn = getenv("GPB_GEMM_BN")) ctx->gemm_bn = (atoi(bn) == 128) ? 128 : 64;
@@ -531,7 +538,7 @@ static void run_prep_build(gpb_ctx* ctx, Bufs& b, const Model& md, long long N, 
   pa.resid = b.resid;
   pa.sn2v = b.sn2v;
   pa.sp = b.sp;
-  prep_kernel<<<nsel, 256, 0, ctx->stream>>>(pa);
+  prep_kernel<<<nsel, PREP_THREADS, 0, ctx->stream>>>(pa);
   LAUNCHED(ctx);
 
   BuildArgs ba;
@@ -671,7 +678,16 @@ static void run_inverse(gpb_ctx* ctx, Bufs& b, long long N, const int* sel, int 
                         bool syrk2) {
   const BatchBufs bb = batch_bufs(b, sel, N);
   const int Nt = b.Nt;
-  if (Nt > 1) {
+  const bool recursive = ctx->trtri == 2 || (ctx->trtri == 1 && nsel <= ctx->trtri_max);
+  if (Nt > 1 && recursive) {
+    // recursive halving: few, wide launches (see OpRecX) -- the shape for a few matrices
+    for (int s = 1; s < Nt; s *= 2) {
+      const int P = (Nt - s + 2 * s - 1) / (2 * s);    // pairs whose second block is not empty
+      const dim3 grid((unsigned)(s * s * P), (unsigned)nsel);
+      launch_gemm(ctx, OpRecX{bb, s, P}, grid);
+      launch_gemm(ctx, OpRecW{bb, s, P}, grid);
+    }
+  } else if (Nt > 1) {
     launch_gemm(ctx, OpHpass{bb}, dim3((unsigned)(Nt * (Nt - 1) / 2), (unsigned)nsel));
     for (int j = Nt - 2; j >= 0; --j)
       launch_gemm(ctx, OpWrec{bb, j, dual ? 1 : 0}, dim3((unsigned)(Nt - 1 - j), (unsigned)nsel));
@@ -731,7 +747,7 @@ static void run_grad(gpb_ctx* ctx, Bufs& b, const Model& md, long long N, const 
   fa.gpart = b.gpart;
   fa.dnlZ = b.dnlz;
   fa.smat = b.smat();
-  grad_final_kernel<<<nsel, 256, 0, ctx->stream>>>(fa);
+  grad_final_kernel<<<dim3((unsigned)nsel, (unsigned)(1 + md.noise_n + md.mean_n)), 256, 0, ctx->stream>>>(fa);
   LAUNCHED(ctx);
 }
 
@@ -799,7 +815,7 @@ static void run_solve_only(gpb_ctx* ctx, Bufs& b, const Model& md, long long N, 
   pa.resid = b.resid;
   pa.sn2v = b.sn2v;
   pa.sp = b.sp;
-  prep_kernel<<<nsel, 256, 0, ctx->stream>>>(pa);
+  prep_kernel<<<nsel, PREP_THREADS, 0, ctx->stream>>>(pa);
   LAUNCHED(ctx);
   copy_kernel<<<grid1d((long long)b.Np * b.cap), 256, 0, ctx->stream>>>(b.bvec, b.resid, (long long)b.Np * b.cap);
   LAUNCHED(ctx);
@@ -935,9 +951,21 @@ static int nlz_batch_impl(gpb_ctx* ctx, const double* hyp, bool hyp_on_device, i
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     if (want_grad) {
-      run_bwd(ctx, b, b.sel, n);
       CK(cudaEventRecord(ctx->ev[3], ctx->stream));
       run_inverse(ctx, b, ctx->N, b.sel, n, /*dual=*/true, /*syrk2=*/true);
+      {                                        // alpha = W^T z / sl: W is there, no back substitution
+        AlphaArgs aa;
+        aa.Wbuf = b.Wbuf;
+        aa.sel = b.sel;
+        aa.smat = b.smat();
+        aa.Np = b.Np;
+        aa.N = (int)ctx->N;
+        aa.zvec = b.zvec;
+        aa.alpha = b.alpha;
+        aa.sp = b.sp;
+        alpha_gemv_kernel<<<dim3((unsigned)((b.Np + 7) / 8), (unsigned)n), 256, 0, ctx->stream>>>(aa);
+        LAUNCHED(ctx);
+      }
       CK(cudaEventRecord(ctx->ev[4], ctx->stream));
       run_grad(ctx, b, md, ctx->N, b.sel, n);
     } else {

@@ -554,6 +554,44 @@ __global__ void __launch_bounds__(256) bwd_step_kernel(VecArgs a) {
   }
 }
 
+// alpha = L^-T z / sl as W^T z once W = L^-1 exists (gradient path): one launch of column dot
+// products (one warp per column, coalesced along the column) instead of the Nt dependent launches
+// of the backward substitution.
+struct AlphaArgs {
+  const double* Wbuf; const int* sel;
+  long long smat;
+  int Np, N;
+  const double* zvec; double* alpha;
+  const SlotP* sp;
+};
+
+__global__ void __launch_bounds__(256) alpha_gemv_kernel(AlphaArgs a) {
+  const int slot = a.sel[blockIdx.y];
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (j >= a.Np) return;
+  double* alpha = a.alpha + (long long)slot * a.Np;
+  if (j >= a.N) {
+    if (lane == 0) alpha[j] = 0.0;
+    return;
+  }
+  const double* col = a.Wbuf + slot * a.smat + (long long)j * a.Np;
+  const double* z = a.zvec + (long long)slot * a.Np;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int i = (j & ~31) + lane;                    // aligned start: the loads coalesce
+  if (i < j) i += 32;
+  for (; i + 96 < a.N; i += 128) {
+    s0 = fma(col[i], z[i], s0);
+    s1 = fma(col[i + 32], z[i + 32], s1);
+    s2 = fma(col[i + 64], z[i + 64], s2);
+    s3 = fma(col[i + 96], z[i + 96], s3);
+  }
+  for (; i < a.N; i += 32) s0 = fma(col[i], z[i], s0);
+  double t = (s0 + s1) + (s2 + s3);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if (lane == 0) alpha[j] = t / a.sp[slot].sl;                       // :2455-2465
+}
+
 struct NlzArgs {
   const int* sel;
   const int* fsel;   // optional: slot whose factor (log-det partials) entry t uses; null = its own

@@ -78,9 +78,10 @@ struct PrepArgs {
   SlotP* sp;            // [nslots]
 };
 
-__global__ void __launch_bounds__(256) prep_kernel(PrepArgs a) {
-  __shared__ double sh[256];
-  __shared__ int shnan[256];
+constexpr int PREP_THREADS = 1024;     // one CTA per slot: wide, the per-point work is FP64 divisions
+__global__ void __launch_bounds__(PREP_THREADS) prep_kernel(PrepArgs a) {
+  __shared__ double sh[PREP_THREADS];
+  __shared__ int shnan[PREP_THREADS];
   const int slot = a.sel[blockIdx.x];
   const Model& md = a.md;
   const int D = md.D, N = a.N, Np = a.Np;
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepArgs a) {
   sh[threadIdx.x] = vmin;
   shnan[threadIdx.x] = anynan;
   __syncthreads();
-  for (int s = 128; s > 0; s >>= 1) {
+  for (int s = PREP_THREADS / 2; s > 0; s >>= 1) {
     if (threadIdx.x < s) {
       sh[threadIdx.x] = fmin(sh[threadIdx.x], sh[threadIdx.x + s]);
       shnan[threadIdx.x] |= shnan[threadIdx.x + s];
@@ -386,15 +387,22 @@ __global__ void __launch_bounds__(256) grad_final_kernel(GradFinalArgs a) {
   double* out = a.dnlZ + (long long)slot * md.P;
   const long long ntiles = (long long)a.Nt * (a.Nt + 1) / 2;
 
+  // blockIdx.y = task: 0 -> covariance hyperparameters, then one CTA per noise / mean
+  // hyperparameter (they are independent sums over the N points)
+  const int task = blockIdx.y;
   // covariance hyperparameters: ordered sum of the tile partials
-  if ((int)threadIdx.x < md.cov_n) {
-    const double* gp = a.gpart + (long long)slot * ntiles * md.cov_n + threadIdx.x;
-    double s = 0.0;
-    for (long long t = 0; t < ntiles; ++t) s += gp[t * md.cov_n];
-    out[threadIdx.x] = s;
+  if (task == 0) {
+    if ((int)threadIdx.x < md.cov_n) {
+      const double* gp = a.gpart + (long long)slot * ntiles * md.cov_n + threadIdx.x;
+      double s = 0.0;
+      for (long long t = 0; t < ntiles; ++t) s += gp[t * md.cov_n];
+      out[threadIdx.x] = s;
+    }
+    return;
   }
   // noise hyperparameters: 0.5 * sn2_mult * sum_i dsn2_iq * Q_ii   (:2491-2504)
-  for (int q = 0; q < md.noise_n; ++q) {
+  if (task <= md.noise_n) {
+    const int q = task - 1;
     double s = 0.0;
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
       const double Qii = Ainv[(long long)i * Np + i] / p.sl - alpha[i] * alpha[i];
@@ -413,17 +421,21 @@ __global__ void __launch_bounds__(256) grad_final_kernel(GradFinalArgs a) {
     }
     s = block_sum<256>(s, sh);
     if (threadIdx.x == 0) out[md.cov_n + q] = 0.5 * p.mult * s;
+    return;
   }
   // mean hyperparameters: -dm^T alpha   (:2507-2508; mean_functions.py:258, :390-395)
-  for (int q = 0; q < md.mean_n; ++q) {
+  {
+    const int q = task - 1 - md.noise_n;
+    if (q >= md.mean_n) return;
+    const int k = (q == 0) ? 0 : (q - 1) % D;
+    const double om = (q == 0) ? 1.0 : exp(hm[1 + D + k]);
+    const double xm = (q == 0) ? 0.0 : hm[1 + k];
     double s = 0.0;
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
       double d;
       if (q == 0) d = 1.0;
       else {
-        const int k = (q - 1) % D;
-        const double om = exp(hm[1 + D + k]);
-        const double diff = a.X[(long long)i * D + k] - hm[1 + k];
+        const double diff = a.X[(long long)i * D + k] - xm;
         if (q <= D) d = diff / (om * om);
         else { const double z = diff / om; d = z * z; }
       }

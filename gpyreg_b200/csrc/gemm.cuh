@@ -565,6 +565,59 @@ struct OpWrec {
   }
 };
 
+// Triangular inverse by recursive halving, bottom-up (block size s = 1, 2, 4, ... tiles).  A pair
+// of adjacent diagonal blocks [a, mid) and [mid, end) whose inverses are known is merged:
+//     W_21 = -W_22 (L_21 W_11)
+// in two passes, every pair of a level in the same launch -- 2*ceil(log2 Nt) launches in all,
+// with Nt^2/4 tiles in the top ones, where the column recurrence (OpWrec) needs Nt-1 launches whose
+// longest tile has K = Nt*T: the better shape for a few matrices.
+//   pass 1 (OpRecX): X = L_21 W_11, stored transposed in the (free) upper triangle of Abuf
+//   pass 2 (OpRecW): W_21 = -W_22 X into the lower tiles of Wbuf and transposed into the upper
+// Tile order: longest K first; bx = (kidx * P + pair) * s + other.
+struct OpRecX {
+  static constexpr bool SLOT_MAJOR = true;
+  static constexpr int MODE = GM_STORET;
+  BatchBufs b; int s, P;
+  __device__ GemmTile resolve(int bx, int by) const {
+    GemmTile t = empty_tile();
+    const int slot = b.sel[by];
+    const int il = bx % s, pr = (bx / s) % P, jl = bx / (s * P);
+    const int a = 2 * s * pr, mid = a + s;
+    const int i = mid + il, j = a + jl;                  // X(i, j) = sum_{k=j}^{mid-1} L(i,k) W(k,j)
+    if (i >= b.Nt || i * T >= b.N) { t.valid = false; return t; }
+    double* A = b.Abuf + slot * b.smat;
+    const double* W = b.Wbuf + slot * b.smat;
+    t.A = A + (long long)i * T + (long long)j * T * b.Np; t.lda = b.Np;
+    t.B = W + (long long)j * T + (long long)j * T * b.Np; t.ldb = b.Np;     // W^T: upper tiles
+    t.B0 = b.DTbuf + ((long long)slot * b.Nt + j) * T * T; t.ldb0 = T;      // W(j,j)^T = D_j^T
+    t.Ct = A + (long long)j * T + (long long)i * T * b.Np; t.ldct = b.Np;
+    t.K = min((mid - j) * T, b.n16() - j * T);
+    return t;
+  }
+};
+
+struct OpRecW {
+  static constexpr bool SLOT_MAJOR = true;
+  static constexpr int MODE = GM_STORE | GM_STORET;
+  BatchBufs b; int s, P;
+  __device__ GemmTile resolve(int bx, int by) const {
+    GemmTile t = empty_tile();
+    const int slot = b.sel[by];
+    const int jl = bx % s, pr = (bx / s) % P, il = s - 1 - bx / (s * P);
+    const int a = 2 * s * pr, mid = a + s;
+    const int i = mid + il, j = a + jl;                  // W(i, j) = -sum_{k=mid}^{i} W(i,k) X(k,j)
+    if (i >= b.Nt || i * T >= b.N) { t.valid = false; return t; }
+    double* W = b.Wbuf + slot * b.smat;
+    const double* A = b.Abuf + slot * b.smat;
+    t.A = W + (long long)i * T + (long long)mid * T * b.Np; t.lda = b.Np;   // last K tile: W(i,i) = D_i
+    t.B = A + (long long)j * T + (long long)mid * T * b.Np; t.ldb = b.Np;   // X^T
+    t.C = W + (long long)i * T + (long long)j * T * b.Np; t.ldc = b.Np;
+    t.Ct = W + (long long)j * T + (long long)i * T * b.Np; t.ldct = b.Np;
+    t.K = min((i - mid + 1) * T, b.n16() - mid * T); t.alpha = -1.0;
+    return t;
+  }
+};
+
 // K^-1 = W^T W (lower tiles a >= c) written over the lower triangle of Abuf
 struct OpSyrk2 {
   static constexpr bool SLOT_MAJOR = true;
