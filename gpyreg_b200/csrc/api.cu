@@ -206,7 +206,9 @@ static int init_attrs(gpb_ctx* ctx) {
   CK(gemm_attr<OpGeneric>());
   CK(gemm_attr<OpPlain>());
   CK(gemm_attr<OpPanel>());
+  CK(gemm_attr<OpFwdZ>());
   CK((gemm_attr_shape<OpFwd, 64, 128>()));
+  CK((gemm_attr_shape<OpFwdZ, 64, 128>()));
   CK((gemm_attr_shape<OpFwd, 128, 128>()));
   CK((gemm_attr_shape<OpPanel, 64, 128>()));
   CK(gemm_attr<OpSyrk>());
@@ -817,30 +819,31 @@ static void run_solve_only(gpb_ctx* ctx, Bufs& b, const Model& md, long long N, 
   pa.sp = b.sp;
   prep_kernel<<<nsel, PREP_THREADS, 0, ctx->stream>>>(pa);
   LAUNCHED(ctx);
-  copy_kernel<<<grid1d((long long)b.Np * b.cap), 256, 0, ctx->stream>>>(b.bvec, b.resid, (long long)b.Np * b.cap);
+  copy_sel_kernel<<<dim3((unsigned)((b.Np + 255) / 256), (unsigned)nsel), 256, 0, ctx->stream>>>(
+      b.bvec, b.resid, sel, b.Np);
   LAUNCHED(ctx);
   const BatchBufs bb = batch_bufs(b, sel, N);
-  for (int k = 0; k < b.Nt; ++k) {
-    DiagSolveArgs da;
-    da.Dbuf = b.Dbuf;
-    da.sel = sel;
-    da.fsel = fsel;
-    da.Np = b.Np;
-    da.Nt = b.Nt;
-    da.N = (int)N;
-    da.k = k;
-    da.bvec = b.bvec;
-    da.zvec = b.zvec;
-    diag_solve_kernel<<<nsel, T, 0, ctx->stream>>>(da);
-    LAUNCHED(ctx);
-    const int n = b.Nt - k - 1;
-    if (n <= 0) break;
-    // same CTA shape as the fused panel, so the reduction order (and every bit) is the same
-    dim3 grid((unsigned)n, (unsigned)nsel);
-    const OpFwd op{bb, k, b.zvec, b.bvec, fsel};
-    if (ctx->gemm_bn != 128) launch_shape<OpFwd, 64, 128>(ctx, op, grid, false);
-    else launch_shape<OpFwd, 128, 128>(ctx, op, grid, false);
+  // block column k < Nt-1: one launch computes z_k = D_k b_k (in every CTA) and b_i -= L_ik z_k
+  // with the CTA shape of the fused panel, so the reduction order (and every bit) is the same;
+  // the last block only needs the solve
+  for (int k = 0; k + 1 < b.Nt; ++k) {
+    dim3 grid((unsigned)(b.Nt - k - 1), (unsigned)nsel);
+    const OpFwdZ op{bb, k, b.zvec, b.bvec, fsel};
+    if (ctx->gemm_bn != 128) launch_shape<OpFwdZ, 64, 128>(ctx, op, grid, false);
+    else launch_shape<OpFwdZ, 128, 128>(ctx, op, grid, false);
   }
+  DiagSolveArgs da;
+  da.Dbuf = b.Dbuf;
+  da.sel = sel;
+  da.fsel = fsel;
+  da.Np = b.Np;
+  da.Nt = b.Nt;
+  da.N = (int)N;
+  da.k = b.Nt - 1;
+  da.bvec = b.bvec;
+  da.zvec = b.zvec;
+  diag_solve_kernel<<<nsel, T, 0, ctx->stream>>>(da);
+  LAUNCHED(ctx);
 }
 
 // ---------------------------------------------------------------------------------

@@ -473,18 +473,15 @@ __global__ void __launch_bounds__(T) diag_solve_kernel(DiagSolveArgs a) {
   __syncthreads();
   const int fslot = a.fsel ? a.fsel[blockIdx.x] : slot;
   const double* Dk = a.Dbuf + ((long long)fslot * a.Nt + a.k) * T * T;
-  double s4[4] = {0.0, 0.0, 0.0, 0.0};
-  if (rr < nact) {
-    int c = 0;
-    for (; c + 3 <= rr; c += 4) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) s4[u] = __fma_rn(Dk[(c + u) * T + rr], bsh[c + u], s4[u]);
-    }
-#pragma unroll
-    for (int u = 0; u < 3; ++u)
-      if (c + u <= rr) s4[u] = __fma_rn(Dk[(c + u) * T + rr], bsh[c + u], s4[u]);
-  }
-  a.zvec[(long long)slot * a.Np + a.k * T + rr] = __dadd_rn(__dadd_rn(s4[0], s4[1]), __dadd_rn(s4[2], s4[3]));
+  a.zvec[(long long)slot * a.Np + a.k * T + rr] = zsolve_row(Dk, bsh, rr, nact);
+}
+
+// dst[slot][:] = src[slot][:] for the listed slots only
+__global__ void copy_sel_kernel(double* dst, const double* src, const int* sel, int Np) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Np) return;
+  const long long o = (long long)sel[blockIdx.y] * Np + i;
+  dst[o] = src[o];
 }
 
 struct VecArgs {

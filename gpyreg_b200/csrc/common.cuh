@@ -92,6 +92,24 @@ __device__ __forceinline__ void kern_value_grad(double r2, double sf2, double a_
   }
 }
 
+// z_rr = sum_{c <= rr} D(rr, c) b_c for one row of a column-major 128x128 D_k: element c goes to
+// accumulator c mod 4 in increasing c, combined as (s0 + s1) + (s2 + s3) -- the order of
+// diag_kernel's tail, so a replayed solve is bit-identical.  Loads are issued 16 at a time.
+__device__ __forceinline__ double zsolve_row(const double* Dk, const double* bsh, int rr, int nact) {
+  double s4[4] = {0.0, 0.0, 0.0, 0.0};
+  if (rr < nact) {
+    for (int c0 = 0; c0 <= rr; c0 += 16) {
+      double v[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) v[u] = (c0 + u <= rr) ? Dk[(c0 + u) * T + rr] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 16; ++u)
+        if (c0 + u <= rr) s4[u & 3] = __fma_rn(v[u], bsh[c0 + u], s4[u & 3]);
+    }
+  }
+  return __dadd_rn(__dadd_rn(s4[0], s4[1]), __dadd_rn(s4[2], s4[3]));
+}
+
 __host__ __device__ inline int kind_code(int cov_kind, int degree) {
   return cov_kind == 0 ? 0 : (cov_kind == 2 ? 2 : degree);   // 0,1,3,5,2
 }

@@ -30,6 +30,7 @@ struct GemmTile {
   const double* E; long long lde;     // reduce mode: rowsum[m] = sum_n C(m,n)*E(m,n) (E null: C^2)
   double* rowsum; long long rs_half;  // rs_half: offset between the two column halves
   const double* vdot; double* vdst;   // GM_ROWDOT: vdst[m] -= sum_n C(m,n) * vdot[n]
+  const double* zD; const double* zb; double* zout; int znact;   // GM_ZSOLVE: D_k, b_k, where z_k goes (or null)
   int K;
   int mvalid, nvalid;                 // rows / columns of the 128x128 tile that hold data (rest is padding)
   double alpha, cscale;               // result = alpha * (cscale * C + A B^T); cscale = beta / alpha
@@ -87,6 +88,7 @@ constexpr int GM_STORE = 2;    // normal store
 constexpr int GM_STORET = 4;   // transposed store
 constexpr int GM_REDUCE = 8;   // row-sum epilogue (no store)
 
+constexpr int GM_ZSOLVE = 32;  // before the row-dot: every CTA first computes vdot = z_k = D_k b_k itself (solve-only replay)
 constexpr int GM_ROWDOT = 16;  // after the store: vdst[m] -= sum_n C(m,n) * vdot[n]   (fused forward solve)
 
 template <int BM_, int BN_>
@@ -335,6 +337,21 @@ gemm_nt_kernel(const __grid_constant__ Op op) {
       }
     }
   }
+  if (MODE & GM_ZSOLVE) {
+    // z_k = D_k b_k, recomputed by every CTA of the step (D_k is L2-resident after the first):
+    // one launch per block column instead of a solve launch and an update launch
+    double* zs = gsm + 1024;                   // clear of the reduction scratch below
+    double* zbs = zs + T;
+    if (tid < T) zbs[tid] = t.zb[tid];
+    __syncthreads();
+    if (tid < T) {
+      const double z = zsolve_row(t.zD, zbs, tid, t.znact);
+      zs[tid] = z;
+      if (t.zout) t.zout[tid] = z;
+    }
+    __syncthreads();
+    t.vdot = zs;
+  }
   if (MODE & GM_ROWDOT) {
     // fused forward substitution: vdst[m] -= sum_n C(m,n) * vdot[n]  (needs all columns of the
     // tile in this CTA: BN_ == BN), reduced in a fixed order
@@ -397,6 +414,9 @@ __device__ __forceinline__ GemmTile empty_tile() {
   t.rs_half = 0;
   t.vdot = nullptr;
   t.vdst = nullptr;
+  t.zD = t.zb = nullptr;
+  t.zout = nullptr;
+  t.znact = 0;
   t.K = 0;
   t.mvalid = BM;
   t.nvalid = BN;
@@ -487,6 +507,34 @@ struct OpFwd {
     t.K = 0; t.cscale = 1.0;
     t.mvalid = b.N - i * T;
     t.vdot = zvec + (long long)slot * b.Np + (long long)k * T;
+    t.vdst = bvec + (long long)slot * b.Np + (long long)i * T;
+    return t;
+  }
+};
+
+// solve-only replay, one launch per block column: like OpFwd, but every CTA first computes
+// z_k = D_k b_k itself (the CTAs of the first tile row also store it)
+struct OpFwdZ {
+  static constexpr bool SLOT_MAJOR = false;
+  static constexpr int MODE = GM_BETA | GM_ROWDOT | GM_ZSOLVE;
+  BatchBufs b; int k;
+  double* zvec; double* bvec;
+  const int* fsel;
+  __device__ GemmTile resolve(int bx, int by) const {
+    GemmTile t = empty_tile();
+    const int slot = b.sel[by];
+    const int fslot = fsel ? fsel[by] : slot;
+    const int i = k + 1 + bx;
+    double* tile = b.Abuf + fslot * b.smat + (long long)i * T + (long long)k * T * b.Np;
+    t.A = tile; t.lda = b.Np;
+    t.B = tile; t.ldb = b.Np;
+    t.C = tile; t.ldc = b.Np;
+    t.K = 0; t.cscale = 1.0;
+    t.mvalid = b.N - i * T;
+    t.zD = b.Dbuf + ((long long)fslot * b.Nt + k) * T * T;
+    t.zb = bvec + (long long)slot * b.Np + (long long)k * T;
+    t.zout = (bx == 0) ? zvec + (long long)slot * b.Np + (long long)k * T : nullptr;
+    t.znact = min(T, b.N - k * T);
     t.vdst = bvec + (long long)slot * b.Np + (long long)i * T;
     return t;
   }
