@@ -424,3 +424,68 @@ def test_factor_cache_is_bit_identical(eng):
     again = eng.nlz_batch(seq[-1])[0]
     np.testing.assert_array_equal(again, got[-1])
     assert eng.cache_stats()[0] == h1
+
+
+_TOGGLE_SCRIPT = r"""
+import json, sys
+import numpy as np
+sys.path.insert(0, ".")
+from bench import benign_hyp, synth_data
+from gpyreg_b200 import Engine
+from oracle import gp_oracle as orc
+N, D = 900, 5
+spec = orc.ModelSpec(D=D, cov_kind=1, degree=3, ard=True, mean_kind=2)
+X, y = synth_data(N, D, seed=0)
+hyp = benign_hyp(spec, 3, y, seed=1)
+eng = Engine(0)
+eng.set_model(spec.cov_kind, spec.degree, spec.ard, spec.mean_kind, spec.noise_params)
+eng.set_data(X, y, None)
+nlz, dnlz, _, _ = eng.nlz_batch(hyp, want_grad=True)
+nlz1 = eng.nlz_batch(hyp[:1])[0]
+print(json.dumps({"nlz": [v.hex() for v in nlz], "nlz1": nlz1[0].hex(), "dnlz": [v.hex() for v in dnlz.ravel()]}))
+"""
+
+
+_TOGGLE_CACHE = {}
+
+
+@pytest.mark.parametrize("env,exact", [
+    ({"GPB_LOOKAHEAD": "0"}, True),                        # no second stream
+    ({"GPB_LOOKAHEAD": "2", "GPB_LA_OB": "1"}, True),      # look-ahead with one-column outer blocks
+    ({"GPB_OUTER_BLOCK": "3", "GPB_LOOKAHEAD": "0"}, True),
+    ({"GPB_LOADER": "tma"}, True),                         # TMA bulk-copy loader for every launch
+    ({"GPB_LOADER": "cpasync"}, True),
+    ({"GPB_TRTRI": "0"}, False),                           # column-recurrence triangular inverse
+    ({"GPB_GEMM_BN": "128"}, False),                       # one CTA per tile: other reduction shapes
+])
+def test_schedule_toggles_do_not_change_results(env, exact):
+    """Every scheduling variant (streams, outer block, loader) performs the same FP64 operations
+    in the same order per element: results are bit-identical.  The alternative algorithms kept
+    behind environment switches agree to rounding."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    def run(extra):
+        e = dict(os.environ)
+        for k in ("GPB_LOOKAHEAD", "GPB_LA_OB", "GPB_OUTER_BLOCK", "GPB_LOADER", "GPB_TRTRI", "GPB_GEMM_BN"):
+            e.pop(k, None)
+        e.update(extra)
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        out = subprocess.run([sys.executable, "-c", _TOGGLE_SCRIPT], cwd=root, env=e, check=True,
+                             capture_output=True, text=True, timeout=600).stdout.strip().splitlines()[-1]
+        d = json.loads(out)
+        return (np.array([float.fromhex(v) for v in d["nlz"]]), float.fromhex(d["nlz1"]),
+                np.array([float.fromhex(v) for v in d["dnlz"]]))
+
+    if "base" not in _TOGGLE_CACHE:
+        _TOGGLE_CACHE["base"] = run({})
+    base = _TOGGLE_CACHE["base"]
+    got = run(env)
+    if exact:
+        assert np.array_equal(got[0], base[0]) and got[1] == base[1] and np.array_equal(got[2], base[2])
+    else:
+        assert rel_err(got[0], base[0]) <= 1e-12 and abs(got[1] - base[1]) <= 1e-12 * abs(base[1])
+        assert np.max(np.abs(got[2] - base[2])) <= 1e-10 * np.max(np.abs(base[2]))
+    assert base[1] == base[0][0]          # a row's value does not depend on its batch
