@@ -11,9 +11,12 @@ done
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2>/dev/null; cut -c1-200 gpurun_out/bench_ref.json
 CMD="python bench.py --steps 1 --warmup 3"
 $CMD > gpurun_out/plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -s 650 -c 260 --csv --log-file gpurun_out/launches_default.csv $CMD > gpurun_out/ncu_launch.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_default.csv $CMD > gpurun_out/ncu_launch.log 2>&1
 echo "ncu launches exit $?"
 python tools/launch_summary.py gpurun_out/launches_default.csv
 $CMD > gpurun_out/plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:gemm_nt_kernel -s 410 -c 5 -o gpurun_out/prof_gemm $CMD > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:gemm_nt_kernel -s 330 -c 8 -o gpurun_out/prof_gemm $CMD > gpurun_out/ncu_full.log 2>&1
 echo "ncu full exit $?"; tail -1 gpurun_out/ncu_full.log | cut -c1-120
+timeout 300 python tools/b1_latency.py 2>&1 | tail -3 | tee gpurun_out/b1_latency.txt
+timeout 300 python tools/append_latency.py 2>&1 | tail -4 | tee gpurun_out/append_latency.txt
+timeout 600 python tools/fit_profile.py 2>&1 | tail -9 | tee gpurun_out/fit_profile.txt
