@@ -833,11 +833,25 @@ class GP:
         slicer = SliceSampler(lambda h: self.__gp_obj_fun(h, False, True), hyp_start, widths, LB, UB,
                               {"display": "off", "diagnostics": False,
                                "log_f_batch": lambda H: -self._nlz_batch(H, False, use_prior),
-                               "speculate": int(options.get("speculate", 3))})
+                               "speculate": self._speculation_depths(options.get("speculate"))})
         sampling_result = slicer.sample(s_N * thin, burn=burn_in)
         hyp = sampling_result["samples"][thin - 1::thin, :]
         self.update(hyp=hyp)
         return hyp, optimize_result, sampling_result
+
+    def _speculation_depths(self, spec):
+        """Proposals per batched call and coordinate for the slice sampler.  A move along a MEAN
+        hyperparameter re-uses the cached factor (O(N^2), latency-bound: a deeper batch costs the
+        same), one along a covariance / noise hyperparameter refactors every row of the batch."""
+        cov_N, noise_N, mean_N = self._counts()
+        if spec is None:
+            spec = (2, 4)
+        if np.ndim(spec) == 0:
+            return int(spec)
+        spec = np.asarray(spec, dtype=int)
+        if spec.size == 2:
+            return np.concatenate((np.full(cov_N + noise_N, spec[0]), np.full(mean_N, spec[1])))
+        return spec
 
     # ------------------------------------------------------------------ not in this round
     def _not_built(self, name):

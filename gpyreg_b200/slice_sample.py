@@ -11,8 +11,8 @@ log-density values agree.
 Speculative shrinking (``options["log_f_batch"]``, ``options["speculate"] = k``): the next
 proposals of the shrink loop are a deterministic function of the random numbers still to be
 drawn (if proposal 1 is rejected the bracket shrinks to a known side, proposal 2 follows, ...).
-With a batched log density the sampler evaluates the next k proposals in ONE call and accepts
-the first that clears the slice level; the RNG state is rewound so that exactly as many draws
+With a batched log density the sampler evaluates the next k proposals in ONE call (k may differ
+per coordinate) and accepts the first that clears the slice level; the RNG state is rewound so that exactly as many draws
 are consumed as the sequential algorithm would have used.  The chain is identical, bit for
 bit; only the number of (batched) calls drops, from ~2 per coordinate to ~1.
 """
@@ -66,8 +66,14 @@ class SliceSampler:
         self.log_prior = options.get("log_prior", None)
         self.diagnostics = options.get("diagnostics", True)
         self.log_f_batch = options.get("log_f_batch", None)
-        self.speculate = int(options.get("speculate", 3 if self.log_f_batch is not None else 1))
+        # proposals evaluated per batched call: one number, or one per coordinate (a caller that
+        # knows which coordinates are cheap to evaluate in a batch can speculate deeper there)
+        spec = options.get("speculate", 3 if self.log_f_batch is not None else 1)
+        self.speculate = np.broadcast_to(np.asarray(spec, dtype=int), (D,)).copy()
+        if np.any(self.speculate < 1):
+            raise ValueError("The speculate option needs to be a positive integer (or one per coordinate).")
         self.batch_calls = 0
+        self.shrink_counts = np.zeros((D, 65), dtype=np.int64)   # [coordinate][proposals needed]
         self.logger = logging.getLogger("SliceSampler")
         self.logger.setLevel({"off": logging.WARN, "summary": logging.INFO}.get(self.display, logging.DEBUG))
 
@@ -141,13 +147,14 @@ class SliceSampler:
                     while self._log_density(hi)[0] > level:
                         hi[d] += self.widths[d]
                 n_shrink = 0
-                speculative = (self.log_f_batch is not None and self.speculate > 1
+                k_spec = int(self.speculate[d])
+                speculative = (self.log_f_batch is not None and k_spec > 1
                                and self.log_prior is None)
                 while True:                                        # shrink until accepted
                     if speculative:
                         # the next k proposals, assuming each one before is rejected
                         state = np.random.get_state()
-                        us = np.random.rand(self.speculate)
+                        us = np.random.rand(k_spec)
                         np.random.set_state(state)
                         l_, h_, cands = lo[d], hi[d], []
                         for u in us:
@@ -197,6 +204,7 @@ class SliceSampler:
                         self.logger.warning("WARNING: Shrunk to current position and still "
                                             " not acceptable!")
                         break
+                self.shrink_counts[d, min(n_shrink, 64)] += 1
                 if it < burn and self.adaptive:                    # width adaptation
                     span = self.UB[d] - self.LB[d]
                     if n_shrink > 3:

@@ -158,8 +158,9 @@ def test_speculative_slice_sampler_is_the_same_chain(h):
     def logp_batch(X):
         sizes.append(X.shape[0])
         return np.array([logp(x) for x in X])
-    for k in (2, 3, 5):
+    for k in (2, 3, 5, np.array([1, 4, 2])):                  # one depth, or one per coordinate
         np.random.seed(9)
+        del sizes[:]
         ss = SliceSampler(logp, np.array([0.1, 0.2, -0.3]), np.array([1.0, 1.0, 2.0]),
                           np.array([-3.0, -3.0, -5.0]), np.array([3.0, 3.0, 5.0]),
                           {"display": "off", "diagnostics": False, "log_f_batch": logp_batch, "speculate": k})
@@ -168,7 +169,10 @@ def test_speculative_slice_sampler_is_the_same_chain(h):
         np.testing.assert_array_equal(res["f_vals"], h["ss.f_vals"])
         np.testing.assert_array_equal(ss.widths, h["ss.widths"])
         assert ss.func_count == int(h["ss.func_count"])        # evaluations the sequential sampler counts
-        assert ss.batch_calls < ss.func_count and max(sizes) <= k
+        assert ss.batch_calls < ss.func_count and max(sizes) <= np.max(k)
+        # the histogram of proposals per coordinate update accounts for every evaluation but the first
+        assert np.sum(ss.shrink_counts * np.arange(65)) >= ss.func_count - 1
+        assert np.sum(ss.shrink_counts) == 3 * (40 + 39 + 30)        # one entry per coordinate update
     # the RNG stream ends where the sequential sampler leaves it
     np.random.seed(9)
     SliceSampler(logp, np.array([0.1, 0.2, -0.3]), np.array([1.0, 1.0, 2.0]), np.array([-3.0, -3.0, -5.0]),

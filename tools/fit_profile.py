@@ -36,7 +36,12 @@ def timed(hyp, want_grad=False):
 
 eng.nlz_batch = timed
 t0 = time.perf_counter()
-gp.fit(X=X, y=y, options={"n_samples": 8, "init_N": 1024})
+opts = {"n_samples": 8, "init_N": 1024}
+if os.environ.get("SPEC"):
+    v = [int(t) for t in os.environ["SPEC"].split(",")]
+    opts["speculate"] = v[0] if len(v) == 1 else v
+hyp_s, _, res = gp.fit(X=X, y=y, options=opts)
+print("speculate", opts.get("speculate", "default"), "sample checksum", float(np.sum(hyp_s)))
 total = time.perf_counter() - t0
 print(f"fit {total:.2f} s")
 spent = 0.0
