@@ -47,6 +47,7 @@ struct gpb_ctx {
                              // batches, 4-5x faster for one matrix), 0 column recurrence, 1 recursive up to trtri_max
   int trtri_max = 8;         // env GPB_TRTRI_MAX
   int lookahead = 1;         // env GPB_LOOKAHEAD: 0 off, 1 small batches (default), 2 always
+  long long la_wide = 6000;  // env GPB_LA_WIDE: matrices x (remaining tile columns)^2 above which blocks stay wide
   int la_chunk = 1 << 30;    // logical tiles per look-ahead launch (env GPB_LA_CHUNK; measured: uncut is best)
   int la_ob = 0;             // outer block used with look-ahead (env GPB_LA_OB; 0 = 1 for <= 2 matrices, else 2)
   std::string err;
@@ -268,6 +269,7 @@ extern "C" int gpb_create(int device, gpb_ctx** out) {
   if (const char* tr = getenv("GPB_TRTRI")) ctx->trtri = atoi(tr);
   if (const char* tm = getenv("GPB_TRTRI_MAX")) ctx->trtri_max = atoi(tm);
   if (const char* lc = getenv("GPB_LA_CHUNK")) ctx->la_chunk = std::max(1, atoi(lc));
+  if (const char* lw = getenv("GPB_LA_WIDE")) ctx->la_wide = atoll(lw);
   if (const char* lo = getenv("GPB_LA_OB")) ctx->la_ob = std::max(0, atoi(lo));
   if (const char* bn = getenv("GPB_GEMM_BN")) ctx->gemm_bn = (atoi(bn) == 128) ? 128 : 64;
   if (const char* ld = getenv("GPB_LOADER"))
@@ -577,12 +579,25 @@ static void run_potrf(gpb_ctx* ctx, Bufs& b, long long N, const int* sel, int ns
   const BatchBufs bb = batch_bufs(b, sel, N);
   const bool look0 = ctx->lookahead == 2 || (ctx->lookahead == 1 && nsel <= 8);
   const int Nt = b.Nt;                                 // outer block = OB tile columns
-  // with look-ahead the dependent chain (diag -> panel -> next column) decides, not GEMM
-  // efficiency: narrow outer blocks shorten it (measured, N=5000: B=1 5.0 -> 4.1 ms at OB=1)
-  const int OB = !look0 ? ctx->outer_block : (ctx->la_ob > 0 ? ctx->la_ob : (nsel <= 2 ? 1 : 2));
-  const bool look = ctx->lookahead == 2 || (ctx->lookahead == 1 && nsel <= 8);
+  // With look-ahead, the width of an outer block is chosen where the block starts: while the
+  // trailing matrix is large the update is GEMM-bound and wide blocks (long K) pay; once it is
+  // small, the dependent chain diag -> panel -> next column decides and narrow blocks shorten it
+  // (measured, N=5000, one matrix: 5.0 -> 4.1 ms at width 1).  The choice never changes a bit of
+  // the result: every element sees the same FP64 operations in the same order for any blocking.
+  const int narrow = ctx->la_ob > 0 ? ctx->la_ob : (nsel <= 2 ? 1 : 2);
+  auto width_at = [&](int k0) {
+    if (!look0) return ctx->outer_block;
+    const long long nrem = Nt - k0;
+    return ((long long)nsel * nrem * nrem >= ctx->la_wide) ? std::max(narrow, ctx->outer_block) : narrow;
+  };
+  const bool look = look0;
   bool joined_pending = false;
+  int ob0 = 0, obe = 0;                                // current outer block [ob0, obe)
   for (int k = 0; k < Nt; ++k) {
+    if (k == obe) {
+      ob0 = k;
+      obe = std::min(k + width_at(k), Nt);
+    }
     DiagArgs da;
     da.Abuf = b.Abuf;
     da.Wbuf = write_w ? b.Wbuf : nullptr;
@@ -607,15 +622,13 @@ static void run_potrf(gpb_ctx* ctx, Bufs& b, long long N, const int* sel, int ns
     launch_panel(ctx, OpPanel{bb, k, with_rhs ? b.zvec : nullptr, with_rhs ? b.bvec : nullptr},
                  dim3((unsigned)n, (unsigned)nsel));
     // two-level trailing update (see OpSyrk): inside the outer block only its own columns
-    const int ob0 = (k / OB) * OB;                     // first tile column of this outer block
-    const int obe = std::min(ob0 + OB, Nt);            // one past its last
     if (k + 1 < obe) {
       const int cnt = OpSyrk::count(Nt, k + 1, obe);
       launch_gemm(ctx, OpSyrk{bb, k, 1, k + 1, obe}, dim3((unsigned)cnt, (unsigned)nsel));
     }
     if (k + 1 == obe && obe < Nt) {                    // outer block done: update the rest, long K
       const int kw = obe - ob0;
-      const int obe2 = std::min(obe + OB, Nt);         // end of the NEXT outer block
+      const int obe2 = std::min(obe + width_at(obe), Nt);   // end of the NEXT outer block
       if (joined_pending) {                            // the previous remainder wrote these tiles
         cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
         joined_pending = false;
