@@ -442,6 +442,13 @@ class GP:
 
     def _sync_engine(self):
         """Upload (X, y, s2) when they changed since the last call."""
+        # fast path (a fit calls this thousands of times): same array objects, same buffers and the
+        # same values at a strided sample of positions -> nothing to do, no checksum over N*D values
+        probe = tuple((id(a), a.ctypes.data, a.shape, float(np.sum(a.reshape(-1)[::max(1, a.size // 61)])))
+                      for a in (self.X, self.y, self.s2) if isinstance(a, np.ndarray))
+        if probe == getattr(self, "_data_probe", None) and self._data_key is not None:
+            return self.engine
+        self._data_probe = probe
         X = np.ascontiguousarray(self.X, dtype=float)
         y = np.ascontiguousarray(self.y, dtype=float)
         s2 = None if self.s2 is None else np.ascontiguousarray(self.s2, dtype=float)
