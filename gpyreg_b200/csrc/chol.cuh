@@ -16,7 +16,7 @@ constexpr int DP_PITCH = T + 4;                                   // 132: 16-byt
 constexpr int SB = 32;                                            // sub-block of the tile factorisation
 constexpr int IVP = 36;                                           // pitch of the 32x32 scratch blocks
 constexpr size_t DIAG_SMEM =
-    ((size_t)T * DP_PITCH + 5 * SB * IVP + 3 * T) * sizeof(double);
+    ((size_t)T * DP_PITCH + 5 * SB * IVP + 2 * T) * sizeof(double);
 
 struct DiagArgs {
   double* Abuf; double* Wbuf;      // Wbuf may be null (nlZ-only path)
@@ -202,7 +202,6 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
   double* Tm = Iv + 4 * SB * IVP;               // [32][36] scratch, T(m,n) at Tm[n*36 + m]
   double* bsh = Tm + SB * IVP;                  // b_k
   double* lg = bsh + T;                         // log L_jj
-  double* rsq = lg + T;                         // 1 / L_jj
   __shared__ int s_failed;
   __shared__ long long stamps[32];
   int nst = 0;
@@ -231,7 +230,6 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
   }
   if (tid < T) {
     bsh[tid] = a.bvec ? a.bvec[(long long)slot * Np + k * T + tid] : 0.0;
-    rsq[tid] = 1.0;
   }
   if (tid == 0) s_failed = 0;
   asm volatile("cp.async.wait_group 0;\n" ::);

@@ -339,13 +339,43 @@ gemm_nt_kernel(const __grid_constant__ Op op) {
   }
   if (MODE & GM_ZSOLVE) {
     // z_k = D_k b_k, recomputed by every CTA of the step (D_k is L2-resident after the first):
-    // one launch per block column instead of a solve launch and an update launch
-    double* zs = gsm + 1024;                   // clear of the reduction scratch below
-    double* zbs = zs + T;
+    // one launch per block column instead of a solve launch and an update launch.  The lower
+    // triangle of D_k is staged in the (unused: K = 0) operand ring with all loads in flight at
+    // once -- columns 0..63 with all rows, columns 64..127 with rows 64..127 -- and summed in the
+    // order of zsolve_row (element c into accumulator c mod 4, increasing c): bit-identical.
+    double* zs = gsm + 256;                    // clear of the reduction scratch gsm[0..256)
+    double* zbs = gsm + 384;
+    double* D1 = gsm + 512;                    // [64][128]
+    double* D2 = D1 + 64 * T;                  // [64][64]
+    for (int e = tid; e < 64 * 64; e += GEMM_THREADS) {
+      const int col = e >> 6, r2 = (e & 63) * 2;
+      if (r2 + 1 >= col) cp_async16(D1 + col * T + r2, t.zD + col * T + r2);
+    }
+    for (int e = tid; e < 64 * 32; e += GEMM_THREADS) {
+      const int col = e >> 5, r2 = (e & 31) * 2;
+      if (r2 + 1 >= col) cp_async16(D2 + col * 64 + r2, t.zD + (64 + col) * T + 64 + r2);
+    }
+    cp_async_commit();
     if (tid < T) zbs[tid] = t.zb[tid];
+    cp_async_wait<0>();
     __syncthreads();
     if (tid < T) {
-      const double z = zsolve_row(t.zD, zbs, tid, t.znact);
+      const int rr = tid;
+      double s4[4] = {0.0, 0.0, 0.0, 0.0};
+      if (rr < t.znact) {
+        const int c1 = min(rr, 63);
+        for (int c0 = 0; c0 <= c1; c0 += 4) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (c0 + u <= c1) s4[u] = __fma_rn(D1[(c0 + u) * T + rr], zbs[c0 + u], s4[u]);
+        }
+        for (int c0 = 64; c0 <= rr; c0 += 4) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (c0 + u <= rr) s4[u] = __fma_rn(D2[(c0 + u - 64) * 64 + rr - 64], zbs[c0 + u], s4[u]);
+        }
+      }
+      const double z = __dadd_rn(__dadd_rn(s4[0], s4[1]), __dadd_rn(s4[2], s4[3]));
       zs[tid] = z;
       if (t.zout) t.zout[tid] = z;
     }
