@@ -489,3 +489,54 @@ def test_schedule_toggles_do_not_change_results(env, exact):
         assert rel_err(got[0], base[0]) <= 1e-12 and abs(got[1] - base[1]) <= 1e-12 * abs(base[1])
         assert np.max(np.abs(got[2] - base[2])) <= 1e-10 * np.max(np.abs(base[2]))
     assert base[1] == base[0][0]          # a row's value does not depend on its batch
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_seeded_fuzz_small_batches(eng, seed):
+    """Random model / size / batch (1..9 rows: the look-ahead, narrow-block and recursive-inverse paths),
+    sizes straddling tile boundaries, against the oracle: nlZ, gradient, posterior mean vector, and a
+    rank-one append followed by a prediction."""
+    from bench import benign_hyp, synth_data
+    rng = np.random.default_rng(1000 + seed)
+    N = int(rng.choice([1, 2, 31, 127, 128, 129, 255, 257, 383, 385, 511, 640]))
+    D = int(rng.integers(1, 9))
+    B = int(rng.choice([1, 2, 3, 5, 9]))
+    cov_kind = int(rng.integers(0, 3))
+    ard = bool(rng.integers(0, 2)) or cov_kind == 2
+    degree = int(rng.choice([1, 3, 5])) if cov_kind == 1 else 0
+    if degree == 1:
+        degree = 3                       # Matern-1 length-scale gradients are NaN by construction (SURVEY 8a)
+    spec = orc.ModelSpec(D=D, cov_kind=cov_kind, degree=degree, ard=ard, mean_kind=int(rng.integers(0, 3)))
+    X, y = synth_data(N + 1, D, seed=seed)
+    Xn, yn, X, y = X[-1], y[-1], X[:-1], y[:-1]
+    hyp = benign_hyp(spec, B, y, seed=seed + 1)
+    setup_engine(eng, spec, X, y, None)
+    nlz, dnlz, mult, status = eng.nlz_batch(hyp, want_grad=True)
+    ref_nlz, ref_dnlz = orc.nlz_batch(spec, hyp, X, y, None, True)
+    assert not status.any() and np.all(mult == 1)
+    assert rel_err(nlz, ref_nlz) <= TOL_NLZ
+    assert grad_err(dnlz, ref_dnlz) <= TOL_GRAD
+    np.testing.assert_array_equal(eng.nlz_batch(hyp)[0], nlz)          # nlZ-only path: same bits
+    post = eng.posterior_batch(hyp)
+    posts = orc.posterior_batch(spec, hyp, X, y, None)
+    for b in range(B):
+        a = post.fetch(b, "alpha")
+        ra = np.asarray(posts[b].alpha).reshape(-1)
+        assert np.max(np.abs(a - ra)) <= 1e-9 * np.max(np.abs(ra))
+    # append the held-out point in place, then predict: compare with the oracle on N + 1 points
+    st = eng.posterior_append(post, Xn, float(yn[0]))
+    X1, y1 = np.vstack((X, Xn[None, :])), np.concatenate((y, yn[None, :]))
+    Xs = rng.uniform(-3, 3, (17, D))
+    if st is None:                       # no free row in the padded layout (N a multiple of 128): rebuild
+        assert N % 128 == 0
+        post.free()
+        setup_engine(eng, spec, X1, y1, None)
+        post = eng.posterior_batch(hyp)
+    else:
+        assert not st.any() and post.N == N + 1
+    posts1 = orc.posterior_batch(spec, hyp, X1, y1, None)
+    mu, v = eng.predict(post, Xs, add_noise=True, separate=True)
+    rmu, rv = orc.predict(spec, posts1, X1, y1, Xs, add_noise=True, separate_samples=True)
+    assert np.max(np.abs(mu - rmu)) <= TOL_PRED * (1 + np.max(np.abs(rmu)))
+    assert np.max(np.abs(v - rv)) <= TOL_PRED * np.max(np.abs(rv))
+    post.free()
