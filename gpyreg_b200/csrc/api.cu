@@ -785,6 +785,7 @@ static int factor_with_retry(gpb_ctx* ctx, Bufs& b, const Model& md, long long N
   for (int attempt = 0; attempt < 10; ++attempt) {
     run_prep_build(ctx, b, md, N, sel, nsel);
     run_potrf(ctx, b, N, sel, nsel, write_w);
+    CK(cudaGetLastError());                    // a refused launch must not pass for a result
     CK(cudaMemcpyAsync(failh.data(), b.fail, sizeof(int) * maxslot, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     std::vector<int> next;
@@ -989,6 +990,7 @@ static int nlz_batch_impl(gpb_ctx* ctx, const double* hyp, bool hyp_on_device, i
       CK(cudaEventRecord(ctx->ev[4], ctx->stream));
     }
     CK(cudaEventRecord(ctx->ev[5], ctx->stream));
+    CK(cudaGetLastError());
     // results
     bool anyfail = false;
     for (int s = 0; s < n; ++s) anyfail |= status_h[s] != 0;
@@ -1101,8 +1103,9 @@ extern "C" int gpb_posterior_batch(gpb_ctx* ctx, const double* hyp, int64_t B, g
   }
   run_bwd(ctx, b, b.sel, (int)B);
   post->sp.resize(B);
-  cudaError_t e = cudaMemcpyAsync(post->sp.data(), b.sp, sizeof(SlotP) * B, cudaMemcpyDeviceToHost,
-                                  ctx->stream);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(post->sp.data(), b.sp, sizeof(SlotP) * B, cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return bail(GPB_ECUDA); }
   // low-noise samples store L = -(K + sn2_mult*diag(sn2))^-1 (gaussian_process.py:2440-2448):
@@ -1119,7 +1122,8 @@ extern "C" int gpb_posterior_batch(gpb_ctx* ctx, const double* hyp, int64_t B, g
       symmetrize_kernel<<<grid1d(b.smat()), 256, 0, ctx->stream>>>(b.Abuf + s * b.smat(), b.Np);
       LAUNCHED(ctx);
     }
-    e = cudaStreamSynchronize(ctx->stream);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return bail(GPB_ECUDA); }
   }
   *out = post;
@@ -1194,6 +1198,7 @@ static int ensure_w(gpb_ctx* ctx, gpb_post* post) {
   if (!high.empty()) {
     CK(cudaMemcpyAsync(b.sel2, high.data(), sizeof(int) * high.size(), cudaMemcpyHostToDevice, ctx->stream));
     run_inverse(ctx, b, post->N, b.sel2, (int)high.size(), false, false);
+    CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
   }
   post->w_ready = true;
@@ -1357,6 +1362,7 @@ static int predict_impl(gpb_ctx* ctx, const gpb_post* cpost, const double* Xs, c
     }
     pred_combine_kernel<<<(unsigned)((mc + 255) / 256), 256, 0, ctx->stream>>>(ca);
     LAUNCHED(ctx);
+    CK(cudaGetLastError());
     if (!on_device) {
       CK(cudaMemcpyAsync(mu + c0 * ocols, ca.mu, sizeof(double) * mc * ocols, cudaMemcpyDeviceToHost, ctx->stream));
       CK(cudaMemcpyAsync(s2 + c0 * ocols, ca.s2, sizeof(double) * mc * ocols, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1500,6 +1506,7 @@ extern "C" int gpb_quad(gpb_ctx* ctx, const gpb_post* cpost, const double* mu, c
     ca.lpd = nullptr;
     pred_combine_kernel<<<(unsigned)((mc + 255) / 256), 256, 0, ctx->stream>>>(ca);
     LAUNCHED(ctx);
+    CK(cudaGetLastError());
     CK(cudaMemcpyAsync(F + c0 * ocols, ca.mu, sizeof(double) * mc * ocols, cudaMemcpyDeviceToHost, ctx->stream));
     if (compute_var)
       CK(cudaMemcpyAsync(F_var + c0 * ocols, ca.s2, sizeof(double) * mc * ocols, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1594,6 +1601,7 @@ extern "C" int gpb_posterior_append(gpb_ctx* ctx, gpb_post* post, const double* 
   }
   append_finish_kernel<<<(unsigned)Ns, 256, 0, ctx->stream>>>(a);
   LAUNCHED(ctx);
+  CK(cudaGetLastError());
   CK(cudaMemcpyAsync(post->X + (size_t)N * D, dx, sizeof(double) * D, cudaMemcpyDeviceToDevice, ctx->stream));
   std::vector<int> st((size_t)Ns);
   CK(cudaMemcpyAsync(st.data(), b.fail, sizeof(int) * Ns, cudaMemcpyDeviceToHost, ctx->stream));
