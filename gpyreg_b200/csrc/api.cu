@@ -46,7 +46,8 @@ struct gpb_ctx {
   int trtri = 2;             // env GPB_TRTRI: 2 recursive halving (default; as fast as the recurrence for large
                              // batches, 4-5x faster for one matrix), 0 column recurrence, 1 recursive up to trtri_max
   int trtri_max = 8;         // env GPB_TRTRI_MAX
-  int lookahead = 1;         // env GPB_LOOKAHEAD: 0 off, 1 small batches (default), 2 always
+  int lookahead = 2;         // env GPB_LOOKAHEAD: 0 off, 1 batches <= 8 only, 2 always (default: -10 % at B=9, -4 % at B=32,
+                             // neutral at B=64)
   long long la_wide = 6000;  // env GPB_LA_WIDE: matrices x (remaining tile columns)^2 above which blocks stay wide
   int la_chunk = 1 << 30;    // logical tiles per look-ahead launch (env GPB_LA_CHUNK; measured: uncut is best)
   int la_ob = 0;             // outer block used with look-ahead (env GPB_LA_OB; 0 = 1 for <= 2 matrices, else 2)

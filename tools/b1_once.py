@@ -13,5 +13,6 @@ N = int(os.environ.get("N", "5000"))
 X, y = synth_data(N, spec.D, 0)
 eng.set_model(spec.cov_kind, spec.degree, spec.ard, spec.mean_kind, spec.noise_params)
 eng.set_data(X, y, None)
-hyp = benign_hyp(spec, 2, y, 1)
-print(eng.nlz_batch(hyp[:1], want_grad=bool(int(os.environ.get("GRAD", "0"))))[0])
+B = int(os.environ.get("B", "1"))
+hyp = benign_hyp(spec, max(B, 2), y, 1)
+print(eng.nlz_batch(hyp[:B], want_grad=bool(int(os.environ.get("GRAD", "0"))))[0])
