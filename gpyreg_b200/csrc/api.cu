@@ -456,6 +456,10 @@ static int alloc_bufs(gpb_ctx* ctx, Bufs& b, int cap, bool with_w, int Np, int D
   }
   CK(cudaMalloc(&b.Dbuf, nt * T * T * 8 * cap));
   CK(cudaMalloc(&b.DTbuf, nt * T * T * 8 * cap));
+  // diag_kernel only stores the non-zero 32x32 blocks of D_k and D_k^T
+  CK(cudaMemsetAsync(b.Dbuf, 0, nt * T * T * 8 * cap, ctx->stream));
+  CK(cudaMemsetAsync(b.DTbuf, 0, nt * T * T * 8 * cap, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaMalloc(&b.xs, (size_t)D * Np * 8 * cap));
   CK(cudaMalloc(&b.resid, (size_t)Np * 8 * cap));
   CK(cudaMalloc(&b.sn2v, (size_t)Np * 8 * cap));

@@ -273,37 +273,51 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
     }
     __syncthreads();
     STAMP();
-    // ---- 3. trailing update of the lower 8x8 blocks: S -= L21 L21^T
-    const int nblk = mblocks * (mblocks + 1) / 2;
-    for (int idx = warp; idx < nblk; idx += 16) {         // two 8x8 blocks per pass, interleaved chains
-      const int idx2 = idx + 8;
-      const bool two = idx2 < nblk;
-      int bi, bj, bi2 = 0, bj2 = 0;
-      tri_decode(idx, bi, bj);
-      if (two) tri_decode(idx2, bi2, bj2);
-      const int r0 = c0 + SB + bi * 8, q0 = c0 + SB + bj * 8;
-      const int r1 = c0 + SB + bi2 * 8, q1 = c0 + SB + bj2 * 8;
-      double av0[8], bv0[8], av1[8], bv1[8];
+    // ---- 3. trailing update S -= L21 L21^T of the lower triangle, 16x16 super-blocks (2x2 DMMA
+    // blocks) per warp: two A and two B fragments per k-step feed four DMMAs -- the loop is bound
+    // by shared-memory fragment loads, not by the tensor pipe
+    const int ms = (mblocks + 1) / 2;
+    const int nsup = ms * (ms + 1) / 2;
+    for (int idx = warp; idx < nsup; idx += 8) {
+      int si, sj;
+      tri_decode(idx, si, sj);
+      const int r0 = c0 + SB + si * 16, q0 = c0 + SB + sj * 16;
+      const bool okr = 2 * si + 1 < mblocks, okq = 2 * sj + 1 < mblocks;   // second half inside the tile
+      const bool diag = si == sj;                                          // block (0,1) is above the diagonal
+      double x00[2], x01[2], x10[2], x11[2];
+      x00[0] = S[(q0 + 2 * tq) * DP_PITCH + r0 + g];
+      x00[1] = S[(q0 + 2 * tq + 1) * DP_PITCH + r0 + g];
+      x10[0] = okr ? S[(q0 + 2 * tq) * DP_PITCH + r0 + 8 + g] : 0.0;
+      x10[1] = okr ? S[(q0 + 2 * tq + 1) * DP_PITCH + r0 + 8 + g] : 0.0;
+      x01[0] = (okq && !diag) ? S[(q0 + 8 + 2 * tq) * DP_PITCH + r0 + g] : 0.0;
+      x01[1] = (okq && !diag) ? S[(q0 + 8 + 2 * tq + 1) * DP_PITCH + r0 + g] : 0.0;
+      x11[0] = (okr && okq) ? S[(q0 + 8 + 2 * tq) * DP_PITCH + r0 + 8 + g] : 0.0;
+      x11[1] = (okr && okq) ? S[(q0 + 8 + 2 * tq + 1) * DP_PITCH + r0 + 8 + g] : 0.0;
 #pragma unroll
       for (int k4 = 0; k4 < 8; ++k4) {
         const int col = (c0 + k4 * 4 + tq) * DP_PITCH;
-        av0[k4] = -S[col + r0 + g];
-        bv0[k4] = S[col + q0 + g];
-        av1[k4] = -S[col + r1 + g];
-        bv1[k4] = S[col + q1 + g];
+        const double a0 = -S[col + r0 + g];
+        const double a1 = okr ? -S[col + r0 + 8 + g] : 0.0;
+        const double b0 = S[col + q0 + g];
+        const double b1 = okq ? S[col + q0 + 8 + g] : 0.0;
+        dmma_t(x00[0], x00[1], a0, b0);
+        dmma_t(x10[0], x10[1], a1, b0);
+        dmma_t(x11[0], x11[1], a1, b1);
+        if (!diag) dmma_t(x01[0], x01[1], a0, b1);
       }
-      double x0 = S[(q0 + 2 * tq) * DP_PITCH + r0 + g], x1 = S[(q0 + 2 * tq + 1) * DP_PITCH + r0 + g];
-      double y0 = S[(q1 + 2 * tq) * DP_PITCH + r1 + g], y1 = S[(q1 + 2 * tq + 1) * DP_PITCH + r1 + g];
-#pragma unroll
-      for (int k4 = 0; k4 < 8; ++k4) {
-        dmma_t(x0, x1, av0[k4], bv0[k4]);
-        dmma_t(y0, y1, av1[k4], bv1[k4]);
+      S[(q0 + 2 * tq) * DP_PITCH + r0 + g] = x00[0];
+      S[(q0 + 2 * tq + 1) * DP_PITCH + r0 + g] = x00[1];
+      if (okr) {
+        S[(q0 + 2 * tq) * DP_PITCH + r0 + 8 + g] = x10[0];
+        S[(q0 + 2 * tq + 1) * DP_PITCH + r0 + 8 + g] = x10[1];
       }
-      S[(q0 + 2 * tq) * DP_PITCH + r0 + g] = x0;
-      S[(q0 + 2 * tq + 1) * DP_PITCH + r0 + g] = x1;
-      if (two) {
-        S[(q1 + 2 * tq) * DP_PITCH + r1 + g] = y0;
-        S[(q1 + 2 * tq + 1) * DP_PITCH + r1 + g] = y1;
+      if (okq && !diag) {
+        S[(q0 + 8 + 2 * tq) * DP_PITCH + r0 + g] = x01[0];
+        S[(q0 + 8 + 2 * tq + 1) * DP_PITCH + r0 + g] = x01[1];
+      }
+      if (okr && okq) {
+        S[(q0 + 8 + 2 * tq) * DP_PITCH + r0 + 8 + g] = x11[0];
+        S[(q0 + 8 + 2 * tq + 1) * DP_PITCH + r0 + 8 + g] = x11[1];
       }
     }
     __syncthreads();
@@ -388,6 +402,13 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
         S[R0 * DP_PITCH + C + 1] = d1;
         S[R1 * DP_PITCH + C] = e0;
         S[R1 * DP_PITCH + C + 1] = e1;
+        // and in natural layout over L_ij, which nothing reads any more (L is already written
+        // back; later blocks use L_i,kb with kb > j only): the output pass reads D without
+        // the 8-way bank conflicts of a transposed access
+        S[C * DP_PITCH + R0] = d0;
+        S[(C + 1) * DP_PITCH + R0] = d1;
+        S[C * DP_PITCH + R1] = e0;
+        S[(C + 1) * DP_PITCH + R1] = e1;
       }
       __syncthreads();
     }
@@ -397,7 +418,7 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
   // element (rr, c) of D, rr >= c
   auto Dval = [&](int rr, int c) -> double {
     if ((rr >> 5) == (c >> 5)) return Iv[(rr >> 5) * SB * IVP + (c & 31) * IVP + (rr & 31)];
-    return (rr < nact) ? S[rr * DP_PITCH + c] : 0.0;
+    return (rr < nact) ? S[c * DP_PITCH + rr] : 0.0;      // natural copy written by pass B
   };
   // ---- outputs: D_k (column-major, zeros above the diagonal), D_k^T, W diag tile, z_k
   double* Dk = a.Dbuf + ((long long)slot * a.Nt + k) * T * T;
@@ -415,17 +436,27 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
         const int c = cb * SB + 2 * u + cpar;
         // D(rr, c), rr >= c
         v[u] = (cb == rb) ? ((rr >= c) ? Iv[cb * SB * IVP + (c & 31) * IVP + (rr & 31)] : 0.0)
-                          : ((cb < rb && rr < nact) ? S[rr * DP_PITCH + c] : 0.0);
+                          : ((cb < rb && rr < nact) ? S[c * DP_PITCH + rr] : 0.0);
         // D^T(rr, c) = D(c, rr), c >= rr
         w[u] = (cb == rb) ? ((c >= rr) ? Iv[cb * SB * IVP + (rr & 31) * IVP + (c & 31)] : 0.0)
                           : ((cb > rb && c < nact) ? S[c * DP_PITCH + rr] : 0.0);
       }
+      // blocks that are identically zero (D above, D^T below the block diagonal) are not stored:
+      // the buffers are zeroed when they are allocated and nothing else writes there
+      if (cb <= rb) {
 #pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        const int c = cb * SB + 2 * u + cpar;
-        Dk[c * T + rr] = v[u];
-        if (Wd) Wd[(long long)c * Np + rr] = v[u];
-        DTk[c * T + rr] = w[u];
+        for (int u = 0; u < 16; ++u) {
+          const int c = cb * SB + 2 * u + cpar;
+          Dk[c * T + rr] = v[u];
+          if (Wd) Wd[(long long)c * Np + rr] = v[u];
+        }
+      }
+      if (cb >= rb) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int c = cb * SB + 2 * u + cpar;
+          DTk[c * T + rr] = w[u];
+        }
       }
     }
   }
