@@ -16,7 +16,7 @@ constexpr int DP_PITCH = T + 4;                                   // 132: 16-byt
 constexpr int SB = 32;                                            // sub-block of the tile factorisation
 constexpr int IVP = 36;                                           // pitch of the 32x32 scratch blocks
 constexpr size_t DIAG_SMEM =
-    ((size_t)T * DP_PITCH + 5 * SB * IVP + 2 * T) * sizeof(double);
+    ((size_t)T * DP_PITCH + 8 * SB * IVP + 2 * T) * sizeof(double);
 
 struct DiagArgs {
   double* Abuf; double* Wbuf;      // Wbuf may be null (nlZ-only path)
@@ -199,8 +199,8 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
   extern __shared__ __align__(16) double dsm[];
   double* S = dsm;                              // [T][129]
   double* Iv = S + T * DP_PITCH;                // [4][32][36]  Inv_p(r,c) at Iv[p][c*36 + r]
-  double* Tm = Iv + 4 * SB * IVP;               // [32][36] scratch, T(m,n) at Tm[n*36 + m]
-  double* bsh = Tm + SB * IVP;                  // b_k
+  double* Tm = Iv + 4 * SB * IVP;               // [4][32][36] scratch blocks, T(m,n) at Tm[n*36 + m]
+  double* bsh = Tm + 4 * SB * IVP;              // b_k
   double* lg = bsh + T;                         // log L_jj
   __shared__ int s_failed;
   __shared__ long long stamps[32];
@@ -346,71 +346,136 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
 
   __syncthreads();
   STAMP();
-  // ---- D = L^-1, 32x32 blocks: D_jj = Inv_j ; D_ij = -Inv_i * sum_{kb=j}^{i-1} L_i,kb D_kb,j
-  // D(R,C) for R in a later block than C is stored transposed at S[R*129 + C].
-  for (int j = 0; j < T / SB; ++j) {
-    if (j * SB >= nact) break;
-    for (int i = j + 1; i < T / SB; ++i) {
-      if (i * SB >= nact) break;
-      // pass A: Tm = sum_kb L_i,kb * D_kb,j.  16 output 8x8 blocks: warp w owns (mi, ni) =
-      // (w>>2, w&3) and (w>>2 + 2, w&3): same B fragments, two interleaved DMMA chains.
-      {
-        const int mi = warp >> 2, ni = warp & 3;
-        double t0 = 0.0, t1 = 0.0, u0 = 0.0, u1 = 0.0;
-        for (int kb = j; kb < i; ++kb) {
-          double a0[8], a1[8], bb[8];
+  // ---- D = L^-1 from the 32x32 blocks, recursively: D_jj = Inv_j; then the two 64x64 diagonal
+  // halves get their off-diagonal block (round 1: blocks (1,0) and (3,2)), then the 64x64 block below
+  // (round 2: blocks (2,0) (2,1) (3,0) (3,1)):  D_21 = -D_22 (L_21 D_11).  Four stages instead of the
+  // twelve of a block-by-block sweep, with all eight warps busy in each.
+  // D(R,C) for R in a later block than C is stored transposed at S[R*132 + C] (operand layout of
+  // the next stage) AND in natural layout over L(R,C), which nothing reads any more at that point
+  // (L is already written back): the output pass then reads D without bank conflicts.
+  {
+    auto put_D = [&](int R, int C, double v0, double v1) {     // D(R, C) and D(R, C+1)
+      S[R * DP_PITCH + C] = v0;
+      S[R * DP_PITCH + C + 1] = v1;
+      S[C * DP_PITCH + R] = v0;
+      S[(C + 1) * DP_PITCH + R] = v1;
+    };
+    // round 1, stage A: T_p = L(i,j) Inv_j for the pairs p = 0: (1,0), p = 1: (3,2)
+    {
+      const int pr = warp >> 2, ni = warp & 3, i = 2 * pr + 1, j = 2 * pr;
+      if (i * SB < nact) {
+        double acc[4][2];
 #pragma unroll
-          for (int k4 = 0; k4 < 8; ++k4) {
-            const int q = k4 * 4 + tq;
-            a0[k4] = S[(kb * SB + q) * DP_PITCH + i * SB + mi * 8 + g];
-            a1[k4] = S[(kb * SB + q) * DP_PITCH + i * SB + (mi + 2) * 8 + g];
-            bb[k4] = (kb == j) ? Iv[j * SB * IVP + (ni * 8 + g) * IVP + q]
-                               : S[(kb * SB + q) * DP_PITCH + j * SB + ni * 8 + g];
-          }
-#pragma unroll
-          for (int k4 = 0; k4 < 8; ++k4) {
-            dmma_t(t0, t1, a0[k4], bb[k4]);
-            dmma_t(u0, u1, a1[k4], bb[k4]);
-          }
-        }
-        Tm[(ni * 8 + 2 * tq) * IVP + mi * 8 + g] = t0;
-        Tm[(ni * 8 + 2 * tq + 1) * IVP + mi * 8 + g] = t1;
-        Tm[(ni * 8 + 2 * tq) * IVP + (mi + 2) * 8 + g] = u0;
-        Tm[(ni * 8 + 2 * tq + 1) * IVP + (mi + 2) * 8 + g] = u1;
-      }
-      __syncthreads();
-      // pass B: D_ij = -Inv_i * Tm
-      {
-        const int mi = warp >> 2, ni = warp & 3;
-        double a0[8], a1[8], bb[8];
+        for (int mi = 0; mi < 4; ++mi) acc[mi][0] = acc[mi][1] = 0.0;
 #pragma unroll
         for (int k4 = 0; k4 < 8; ++k4) {
           const int q = k4 * 4 + tq;
-          a0[k4] = -Iv[i * SB * IVP + q * IVP + mi * 8 + g];
-          a1[k4] = -Iv[i * SB * IVP + q * IVP + (mi + 2) * 8 + g];
-          bb[k4] = Tm[(ni * 8 + g) * IVP + q];
+          const double bf = Iv[j * SB * IVP + (ni * 8 + g) * IVP + q];                    // Inv_j(q, n)
+#pragma unroll
+          for (int mi = 0; mi < 4; ++mi)
+            dmma_t(acc[mi][0], acc[mi][1], S[(j * SB + q) * DP_PITCH + i * SB + mi * 8 + g], bf);
         }
-        double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+          Tm[pr * SB * IVP + (ni * 8 + 2 * tq) * IVP + mi * 8 + g] = acc[mi][0];
+          Tm[pr * SB * IVP + (ni * 8 + 2 * tq + 1) * IVP + mi * 8 + g] = acc[mi][1];
+        }
+      }
+    }
+    __syncthreads();
+    // round 1, stage B: D(i,j) = -Inv_i T_p
+    {
+      const int pr = warp >> 2, ni = warp & 3, i = 2 * pr + 1, j = 2 * pr;
+      if (i * SB < nact) {
+        double acc[4][2];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) acc[mi][0] = acc[mi][1] = 0.0;
 #pragma unroll
         for (int k4 = 0; k4 < 8; ++k4) {
-          dmma_t(d0, d1, a0[k4], bb[k4]);
-          dmma_t(e0, e1, a1[k4], bb[k4]);
+          const int q = k4 * 4 + tq;
+          const double bf = Tm[pr * SB * IVP + (ni * 8 + g) * IVP + q];                   // T_p(q, n)
+#pragma unroll
+          for (int mi = 0; mi < 4; ++mi)
+            dmma_t(acc[mi][0], acc[mi][1], -Iv[i * SB * IVP + q * IVP + mi * 8 + g], bf);
         }
-        const int C = j * SB + ni * 8 + 2 * tq;
-        const int R0 = i * SB + mi * 8 + g, R1 = i * SB + (mi + 2) * 8 + g;
-        S[R0 * DP_PITCH + C] = d0;
-        S[R0 * DP_PITCH + C + 1] = d1;
-        S[R1 * DP_PITCH + C] = e0;
-        S[R1 * DP_PITCH + C + 1] = e1;
-        // and in natural layout over L_ij, which nothing reads any more (L is already written
-        // back; later blocks use L_i,kb with kb > j only): the output pass reads D without
-        // the 8-way bank conflicts of a transposed access
-        S[C * DP_PITCH + R0] = d0;
-        S[(C + 1) * DP_PITCH + R0] = d1;
-        S[C * DP_PITCH + R1] = e0;
-        S[(C + 1) * DP_PITCH + R1] = e1;
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+          put_D(i * SB + mi * 8 + g, j * SB + ni * 8 + 2 * tq, acc[mi][0], acc[mi][1]);
       }
-      __syncthreads();
+    }
+    __syncthreads();
+    // round 2, stage A: X(i,j) = sum_{kb=j..1} L(i,kb) D11(kb,j) for i in {2,3}, j in {0,1}
+    {
+      const int o = warp >> 1, nh = warp & 1, i = 2 + (o >> 1), j = o & 1;
+      if (i * SB < nact) {
+        double acc[2][4][2];
+#pragma unroll
+        for (int n2 = 0; n2 < 2; ++n2)
+#pragma unroll
+          for (int mi = 0; mi < 4; ++mi) acc[n2][mi][0] = acc[n2][mi][1] = 0.0;
+        for (int kb = j; kb < 2; ++kb) {
+#pragma unroll
+          for (int k4 = 0; k4 < 8; ++k4) {
+            const int q = k4 * 4 + tq;
+            double bf[2];
+#pragma unroll
+            for (int n2 = 0; n2 < 2; ++n2) {
+              const int n = (2 * nh + n2) * 8 + g;
+              bf[n2] = (kb == j) ? Iv[j * SB * IVP + n * IVP + q]                         // Inv_j(q, n)
+                                 : S[(SB + q) * DP_PITCH + n];                            // D(1,0)(q, n)
+            }
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) {
+              const double af = S[(kb * SB + q) * DP_PITCH + i * SB + mi * 8 + g];       // L(i,kb)(m, q)
+              dmma_t(acc[0][mi][0], acc[0][mi][1], af, bf[0]);
+              dmma_t(acc[1][mi][0], acc[1][mi][1], af, bf[1]);
+            }
+          }
+        }
+#pragma unroll
+        for (int n2 = 0; n2 < 2; ++n2)
+#pragma unroll
+          for (int mi = 0; mi < 4; ++mi) {
+            const int n = (2 * nh + n2) * 8 + 2 * tq;
+            Tm[o * SB * IVP + n * IVP + mi * 8 + g] = acc[n2][mi][0];
+            Tm[o * SB * IVP + (n + 1) * IVP + mi * 8 + g] = acc[n2][mi][1];
+          }
+      }
+    }
+    __syncthreads();
+    // round 2, stage B: D(i,j) = -sum_{k=2..i} D22(i,k) X(k,j)
+    {
+      const int o = warp >> 1, nh = warp & 1, i = 2 + (o >> 1), j = o & 1;
+      if (i * SB < nact) {
+        double acc[2][4][2];
+#pragma unroll
+        for (int n2 = 0; n2 < 2; ++n2)
+#pragma unroll
+          for (int mi = 0; mi < 4; ++mi) acc[n2][mi][0] = acc[n2][mi][1] = 0.0;
+        for (int k = 2; k <= i; ++k) {
+          const double* X = Tm + ((k - 2) * 2 + j) * SB * IVP;
+#pragma unroll
+          for (int k4 = 0; k4 < 8; ++k4) {
+            const int q = k4 * 4 + tq;
+            double bf[2];
+#pragma unroll
+            for (int n2 = 0; n2 < 2; ++n2) bf[n2] = X[((2 * nh + n2) * 8 + g) * IVP + q];   // X(k,j)(q, n)
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) {
+              const int m = mi * 8 + g;
+              const double af = (k == i) ? -Iv[i * SB * IVP + q * IVP + m]                // -Inv_i(m, q)
+                                         : -S[(2 * SB + q) * DP_PITCH + 3 * SB + m];     // -D(3,2)(m, q), natural copy
+              dmma_t(acc[0][mi][0], acc[0][mi][1], af, bf[0]);
+              dmma_t(acc[1][mi][0], acc[1][mi][1], af, bf[1]);
+            }
+          }
+        }
+#pragma unroll
+        for (int n2 = 0; n2 < 2; ++n2)
+#pragma unroll
+          for (int mi = 0; mi < 4; ++mi)
+            put_D(i * SB + mi * 8 + g, j * SB + (2 * nh + n2) * 8 + 2 * tq, acc[n2][mi][0], acc[n2][mi][1]);
+      }
     }
   }
   __syncthreads();

@@ -39,7 +39,7 @@ def test_gemm_nt(eng, M, N, K):
         assert np.max(np.abs(got - ref)) <= 1e-12 * K
 
 
-@pytest.mark.parametrize("n", [5, 100, 128, 129, 300, 1000])
+@pytest.mark.parametrize("n", [5, 40, 72, 100, 128, 129, 200, 300, 1000])
 def test_potrf(eng, n):
     rng = np.random.default_rng(n)
     G = rng.standard_normal((n, n))
