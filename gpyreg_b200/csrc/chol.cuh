@@ -66,10 +66,8 @@ __device__ __forceinline__ void chol32_step(double (&arow)[SB], double& dg, doub
     dg = lj;                                          // L(J, J)
     rdiag = fma(p, y0 * e, y0);                       // 1 / L(J, J)
   }
-  if (lane > J) {
-    arow[J] = lj;
-    dg = fma(-lj, lj, dg);
-  }
+  arow[J] = lj;                                       // lanes <= J: unused garbage
+  if (lane > J) dg = fma(-lj, lj, dg);
   if (J + 1 < SB) {
     piv = __shfl_sync(0xffffffffu, dg, J + 1);        // next pivot first: it heads the chain
     double* cb = colbuf + (J & 1) * SB;               // double-buffered: no WAR hazard across steps
@@ -77,10 +75,14 @@ __device__ __forceinline__ void chol32_step(double (&arow)[SB], double& dg, doub
     __syncwarp();
     constexpr int CS = (J + 1) & ~1;
 #pragma unroll
+    // unpredicated: entries on and above the diagonal of the register block (lane <= c) collect
+    // garbage that nothing reads -- the diagonal lives in dg, the write-back and the inverse use the
+    // strictly lower part only.  The loop is issue-bound: one FMA per column instead of
+    // compare + FMA + two selects
     for (int c = CS; c < SB; c += 2) {
       const double2 v = *reinterpret_cast<const double2*>(cb + c);
-      if (c > J && lane > c) arow[c] = fma(-lj, v.x, arow[c]);
-      if (lane > c + 1) arow[c + 1] = fma(-lj, v.y, arow[c + 1]);
+      if (c > J) arow[c] = fma(-lj, v.x, arow[c]);
+      arow[c + 1] = fma(-lj, v.y, arow[c + 1]);
     }
   }
 }
@@ -109,8 +111,9 @@ __device__ __forceinline__ void inv16_step(const double* Lcol, const double* rd,
 #pragma unroll
   for (int r = RS; r < HB; r += 2) {
     const double2 v = *reinterpret_cast<const double2*>(col + r);     // L(h+r, h+Q), L(h+r+1, h+Q)
-    if (r > Q && cc < r) inv[r] = fma(v.x, inv[Q], inv[r]);
-    if (cc < r + 1) inv[r + 1] = fma(v.y, inv[Q], inv[r + 1]);
+    // unpredicated: for rows r <= cc the term is L(r,Q) * x_Q with Q < cc, and x_Q = 0 there
+    if (r > Q) inv[r] = fma(v.x, inv[Q], inv[r]);
+    inv[r + 1] = fma(v.y, inv[Q], inv[r + 1]);
   }
   const double dn = rd[Q + 1];                                        // 1 / L(h+Q+1, h+Q+1)
   if (cc < Q + 1) inv[Q + 1] = -inv[Q + 1] * dn;
