@@ -62,14 +62,14 @@ __device__ __forceinline__ void chol32_step(double (&arow)[SB], double& dg, doub
   const double e = fma(-(y0 * y0), piv, 1.0);
   const double p = fma(e, 0.375, 0.5);
   const double lj = fma(p, ay0 * e, ay0);             // a / sqrt(piv)
-  if (lane == J) {
-    dg = lj;                                          // L(J, J)
-    rdiag = fma(p, y0 * e, y0);                       // 1 / L(J, J)
-  }
+  // selects, no branch: a divergent `if (lane == J)` region costs a reconvergence per step
+  const double yfull = fma(p, y0 * e, y0);            // 1 / sqrt(piv)
+  rdiag = (lane == J) ? yfull : rdiag;                // 1 / L(J, J) on the diagonal lane
+  const double dnew = fma(-lj, lj, dg);
+  dg = (lane == J) ? lj : ((lane > J) ? dnew : dg);   // L(J, J) | updated diagonal | final
   arow[J] = lj;                                       // lanes <= J: unused garbage
-  if (lane > J) dg = fma(-lj, lj, dg);
   if (J + 1 < SB) {
-    piv = __shfl_sync(0xffffffffu, dg, J + 1);        // next pivot first: it heads the chain
+    piv = __shfl_sync(0xffffffffu, dnew, J + 1);      // next pivot first (lane J+1 > J holds dnew): it heads the chain
     double* cb = colbuf + (J & 1) * SB;               // double-buffered: no WAR hazard across steps
     cb[lane] = lj;                                    // L(lane, J), valid for lanes > J
     __syncwarp();
