@@ -14,9 +14,13 @@ $CMD > gpurun_out/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_default.csv $CMD > gpurun_out/ncu_launch.log 2>&1
 echo "ncu launches exit $?"
 python tools/launch_summary.py gpurun_out/launches_default.csv
+if [ -n "$NCU_FULL" ]; then
 $CMD > gpurun_out/plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:gemm_nt_kernel -s 330 -c 8 -o gpurun_out/prof_gemm $CMD > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:gemm_nt_kernel -s 371 -c 8 -o gpurun_out/prof_gemm $CMD > gpurun_out/ncu_full.log 2>&1
 echo "ncu full exit $?"; tail -1 gpurun_out/ncu_full.log | cut -c1-120
+fi
 timeout 300 python tools/b1_latency.py 2>&1 | tail -3 | tee gpurun_out/b1_latency.txt
+timeout 100 python tools/diag_dbg.py 2>&1 | grep cycles | tail -1 | tee gpurun_out/diag_phases.txt
+timeout 300 python tools/mid_batch.py 2>&1 | tail -1 | tee gpurun_out/mid_batch.txt
 timeout 300 python tools/append_latency.py 2>&1 | tail -4 | tee gpurun_out/append_latency.txt
 timeout 600 python tools/fit_profile.py 2>&1 | tail -9 | tee gpurun_out/fit_profile.txt
