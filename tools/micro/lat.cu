@@ -1,3 +1,4 @@
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/micro/lat tools/micro/lat.cu ; run on the GPU box: tools/micro/lat
 // dependent-issue latencies on one warp: DFMA, DMUL, DADD, MUFU.RSQ64H, 64-bit shuffle, LDS
 #include <cstdio>
 #include <cuda_runtime.h>
