@@ -16,9 +16,65 @@ per coordinate) and accepts the first that clears the slice level; the RNG state
 are consumed as the sequential algorithm would have used.  The chain is identical, bit for
 bit; only the number of (batched) calls drops, from ~2 per coordinate to ~1.
 """
+import ctypes
 import logging
 
 import numpy as np
+
+
+class _RngRewind:
+    """Save / restore the global NumPy RNG (legacy ``np.random``) around a speculative draw.
+    ``np.random.get_state`` + ``set_state`` cost ~100 us per round trip, more than a small GP
+    evaluation; copying the 2.5 KB Mersenne-Twister state of the global bit generator directly takes
+    ~3 us.  Only uniform draws happen between save and restore, so the Gaussian cache of the
+    legacy generator is not involved.  The raw path is self-checked once against the public API
+    and silently replaced by it if NumPy's internals ever differ."""
+
+    _SIZE = 624 * 4 + 4          # mt19937_state: uint32 key[624]; int pos
+
+    def __init__(self):
+        self._raw = self._probe()
+        self._buf = ctypes.create_string_buffer(self._SIZE)
+        self._state = None
+
+    @staticmethod
+    def _address():
+        bg = np.random.mtrand._rand._bit_generator
+        if type(bg).__name__ != "MT19937":
+            raise TypeError("global bit generator is not MT19937")
+        return bg.ctypes.state_address
+
+    def _probe(self):
+        try:
+            public = np.random.get_state()
+            try:
+                buf = ctypes.create_string_buffer(self._SIZE)
+                ctypes.memmove(buf, self._address(), self._SIZE)
+                a = np.random.rand(700)                          # crosses a state regeneration
+                ctypes.memmove(self._address(), buf, self._SIZE)
+                b = np.random.rand(700)
+                np.random.set_state(public)
+                c = np.random.rand(700)
+                return bool(np.array_equal(a, b) and np.array_equal(a, c))
+            finally:
+                np.random.set_state(public)
+        except Exception:
+            return False
+
+    def save(self):
+        if self._raw:
+            try:
+                ctypes.memmove(self._buf, self._address(), self._SIZE)
+                return
+            except Exception:
+                self._raw = False
+        self._state = np.random.get_state()
+
+    def restore(self):
+        if self._raw:
+            ctypes.memmove(self._address(), self._buf, self._SIZE)
+        else:
+            np.random.set_state(self._state)
 
 
 class SliceSampler:
@@ -73,6 +129,7 @@ class SliceSampler:
         if np.any(self.speculate < 1):
             raise ValueError("The speculate option needs to be a positive integer (or one per coordinate).")
         self.batch_calls = 0
+        self._rewind = _RngRewind()
         self.shrink_counts = np.zeros((D, 65), dtype=np.int64)   # [coordinate][proposals needed]
         self.logger = logging.getLogger("SliceSampler")
         self.logger.setLevel({"off": logging.WARN, "summary": logging.INFO}.get(self.display, logging.DEBUG))
@@ -99,16 +156,26 @@ class SliceSampler:
             return -np.inf, f_val, lp
         return f_sum + lp, f_val, lp
 
-    def _log_density_many(self, pts):
-        """Batched log density of the rows of pts (no prior): -inf outside the bounds / for NaN."""
-        inside = np.all((pts >= self.LB) & (pts <= self.UB), axis=1)
-        out = np.full((pts.shape[0],), -np.inf)
-        if np.any(inside):
-            vals = np.asarray(self.log_f_batch(pts[inside]), dtype=float).reshape(-1)
-            self.batch_calls += 1
-            if np.any(np.isnan(vals)):
-                self.logger.warning("Target density function returned NaN. Trying to continue.")
-            out[inside] = np.where(np.isnan(vals), -np.inf, vals)
+    def _log_density_many(self, pts, d=None, inside=None):
+        """Batched log density of the rows of pts (no prior): -inf outside the bounds / for NaN.
+        When only coordinate d differs between the rows the caller passes the bounds mask it
+        already has (the other coordinates are inside by construction)."""
+        if inside is None:
+            inside = np.all((pts >= self.LB) & (pts <= self.UB), axis=1)
+        n = pts.shape[0]
+        n_in = int(np.count_nonzero(inside))
+        if n_in == 0:
+            return np.full((n,), -np.inf), inside
+        vals = np.asarray(self.log_f_batch(pts if n_in == n else pts[inside]), dtype=float).reshape(-1)
+        self.batch_calls += 1
+        nan = vals != vals
+        if nan.any():
+            self.logger.warning("Target density function returned NaN. Trying to continue.")
+            vals = np.where(nan, -np.inf, vals)
+        if n_in == n:
+            return vals, inside
+        out = np.full((n,), -np.inf)
+        out[inside] = vals
         return out, inside
 
     # -- sampling --------------------------------------------------------------------
@@ -153,9 +220,9 @@ class SliceSampler:
                 while True:                                        # shrink until accepted
                     if speculative:
                         # the next k proposals, assuming each one before is rejected
-                        state = np.random.get_state()
+                        self._rewind.save()
                         us = np.random.rand(k_spec)
-                        np.random.set_state(state)
+                        self._rewind.restore()
                         l_, h_, cands = lo[d], hi[d], []
                         for u in us:
                             c = u * (h_ - l_) + l_
@@ -166,9 +233,13 @@ class SliceSampler:
                                 l_ = c
                             else:
                                 break
-                        pts = np.tile(prop, (len(cands), 1))
+                        pts = np.empty((len(cands), D))
+                        pts[:] = prop
                         pts[:, d] = cands
-                        vals, inside = self._log_density_many(pts)
+                        # prop is inside the bounds in every other coordinate: check d only
+                        lb_d, ub_d = self.LB[d], self.UB[d]
+                        inside = np.array([lb_d <= c <= ub_d for c in cands])
+                        vals, inside = self._log_density_many(pts, d, inside)
                         stop = False
                         for c, v, ins in zip(cands, vals, inside):
                             n_shrink += 1
