@@ -333,3 +333,37 @@ def test_rank_one_declined_for_point_dependent_noise():
     ref = g.GP(2, SquaredExponential(), ConstantMean(), GaussianNoise(constant_add=True, rectified_linear_output_dependent_add=True))
     ref.update(X_new=X, y_new=y, hyp=hyp)
     np.testing.assert_array_equal(gp.posteriors[0].alpha, ref.posteriors[0].alpha)
+
+
+def test_quad_and_predict_full_after_rank_one_update():
+    """The appended point must be visible to every consumer of the posterior batch (quad and
+    predict_full read the batch's own copy of the training inputs): same results as a GP built on
+    all points at once."""
+    rng = np.random.default_rng(21)
+    N, D = 90, 3
+    X = rng.uniform(-2, 2, (N, D))
+    y = np.sin(X.sum(1, keepdims=True)) + 0.05 * rng.standard_normal((N, 1))
+    hyp = np.array([[0.2, -0.1, 0.3, 0.1, np.log(0.1), 0.2],
+                    [0.0, 0.3, -0.2, -0.1, np.log(0.2), -0.1]])
+
+    def make():
+        return g.GP(D, SquaredExponential(), ConstantMean(), GaussianNoise(constant_add=True))
+
+    gp = make()
+    gp.update(X_new=X[:-2], y_new=y[:-2], hyp=hyp)
+    for i in (N - 2, N - 1):
+        gp.update(X_new=X[i:i + 1], y_new=y[i:i + 1])
+    assert gp._post_batch.N == N
+    ref = make()
+    ref.update(X_new=X, y_new=y, hyp=hyp)
+    mu = rng.uniform(-1, 1, (5, D))
+    sigma = rng.uniform(0.3, 1.0, (5, D))
+    F, Fv = gp.quad(mu, sigma, compute_var=True, separate_samples=True)
+    Fr, Fvr = ref.quad(mu, sigma, compute_var=True, separate_samples=True)
+    np.testing.assert_allclose(F, Fr, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(Fv, Fvr, rtol=1e-7, atol=1e-14)
+    Xs = rng.uniform(-2, 2, (7, D))
+    m, c = gp.predict_full(Xs, add_noise=True)
+    mr, cr = ref.predict_full(Xs, add_noise=True)
+    np.testing.assert_allclose(m, mr, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(c, cr, rtol=1e-7, atol=1e-12)
