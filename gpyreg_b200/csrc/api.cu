@@ -571,9 +571,9 @@ static void run_prep_build(gpb_ctx* ctx, Bufs& b, const Model& md, long long N, 
     case 5: launch_build<5>(ctx, ba, grid, smem); break;
     default: launch_build<2>(ctx, ba, grid, smem); break;
   }
-  // right-hand side of the forward solve: b = y - m
-  copy_kernel<<<grid1d((long long)b.Np * b.cap), 256, 0, ctx->stream>>>(b.bvec, b.resid,
-                                                                        (long long)b.Np * b.cap);
+  // right-hand side of the forward solve: b = y - m (the listed slots only)
+  copy_sel_kernel<<<dim3((unsigned)((b.Np + 255) / 256), (unsigned)nsel), 256, 0, ctx->stream>>>(
+      b.bvec, b.resid, sel, b.Np);
   LAUNCHED(ctx);
 }
 
@@ -671,8 +671,8 @@ static void run_potrf(gpb_ctx* ctx, Bufs& b, long long N, const int* sel, int ns
 
 // alpha = L^-T z / sl
 static void run_bwd(gpb_ctx* ctx, Bufs& b, const int* sel, int nsel) {
-  copy_kernel<<<grid1d((long long)b.Np * b.cap), 256, 0, ctx->stream>>>(b.bvec, b.zvec,
-                                                                        (long long)b.Np * b.cap);
+  copy_sel_kernel<<<dim3((unsigned)((b.Np + 255) / 256), (unsigned)nsel), 256, 0, ctx->stream>>>(
+      b.bvec, b.zvec, sel, b.Np);
   LAUNCHED(ctx);
   for (int i = b.Nt - 1; i >= 0; --i) {
     VecArgs va;
