@@ -279,3 +279,43 @@ def test_rank_one_update_host_logic():
     gp, batch, rebuilt = make(np.zeros(2, dtype=np.int32))
     gp.update(X_new=np.zeros((2, 2)), y_new=np.zeros((2, 1)), hyp=np.full((1, 5), 9.0))
     assert batch.engine.calls == [] and np.array_equal(rebuilt[0], np.full((1, 5), 9.0))
+
+
+def test_rng_rewind_paths(h, monkeypatch):
+    """The speculative sampler rewinds the global RNG either by copying the Mersenne-Twister state
+    directly (fast path, self-checked) or through np.random.get_state/set_state: both reproduce the
+    reference chain, and the fast path leaves the generator exactly where the public API would."""
+    from gpyreg_b200 import slice_sample as ssm
+    rw = ssm._RngRewind()
+    np.random.seed(123)
+    ref_state = np.random.get_state()
+    rw.save()
+    a = np.random.rand(1000)
+    rw.restore()
+    b = np.random.rand(1000)
+    np.random.set_state(ref_state)
+    c = np.random.rand(1000)
+    assert np.array_equal(a, b) and np.array_equal(a, c)
+    # normal draws keep their cached second value across a save / uniform draws / restore
+    np.random.seed(7)
+    np.random.standard_normal()                  # leaves a cached Gaussian behind
+    rw.save()
+    np.random.rand(3)
+    rw.restore()
+    g1 = np.random.standard_normal(3)
+    np.random.seed(7)
+    np.random.standard_normal()
+    g2 = np.random.standard_normal(3)
+    assert np.array_equal(g1, g2)
+    logp = lambda x: float(-0.5 * (x[0] ** 2 + (x[1] - 0.5 * x[0]) ** 2 / 0.25 + x[2] ** 2 / 4))
+    logp_batch = lambda X: np.array([logp(x) for x in X])
+    for force_public in (False, True):
+        if force_public:
+            monkeypatch.setattr(ssm._RngRewind, "_probe", lambda self: False)
+        np.random.seed(9)
+        ss = SliceSampler(logp, np.array([0.1, 0.2, -0.3]), np.array([1.0, 1.0, 2.0]),
+                          np.array([-3.0, -3.0, -5.0]), np.array([3.0, 3.0, 5.0]),
+                          {"display": "off", "diagnostics": False, "log_f_batch": logp_batch, "speculate": 3})
+        assert ss._rewind._raw == (not force_public)
+        res = ss.sample(40, thin=2, burn=30)
+        np.testing.assert_array_equal(res["samples"], h["ss.samples"])
