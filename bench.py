@@ -354,6 +354,9 @@ def run_b200(args, wl):
     roofline = {"bound": "tensor", "kernel": "gemm_nt_kernel (FP64 DMMA tile GEMM)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "traffic_note": "tensor-bound, not measured live; ncu capture of the largest trailing-update launch "
+                                "(666 tiles x 64 matrices): 11.9 GB DRAM read+write vs 11.2 GB algorithmic C-tile "
+                                "bytes, operands hit in L2 (profiles/r01_ncu_full_gemm_bench_default.txt)",
                 "peak_source": "cuBLAS DGEMM 8192^3 via torch.matmul, best of 5, measured in this run "
                                "(MEASURED_PEAKS.json has no FP64 entry)",
                 "algorithmic_flops_per_step": flops_step,
