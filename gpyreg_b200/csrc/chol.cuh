@@ -1,8 +1,11 @@
 // Panel-level kernels of the batched blocked Cholesky / triangular solves.
 //   diag_kernel       factor one 128x128 diagonal tile in shared memory, invert it, write
 //                     D_k, D_k^T, log-det partial, and the forward-solve block z_k = D_k b_k
-//   diag_solve_kernel z_k = D_k b_k on an existing factor (solve-only replay, factor cache)
-//   bwd_step_kernel   w_i = D_i^T b_i ; b_j -= L_ij^T w_i (backward substitution, j < i)
+//                     (factor_block32: the 32x32 diagonal blocks in the registers of one warp)
+//   diag_solve_kernel z_k = D_k b_k on an existing factor (solve-only replay of the last block;
+//                     the other blocks are fused into the tile GEMM launch, OpFwdZ)
+//   bwd_step_kernel   w_i = D_i^T b_i ; b_j -= L_ij^T w_i (backward substitution, j < i; posterior path)
+//   alpha_gemv_kernel alpha = W^T z / sl once W = L^-1 exists (gradient path)
 //   nlz_kernel        nlZ = z^T z/(2 sl) + sum log L_ii + N log(2 pi sl)/2
 // The dense O(N^3) work between these is the tile GEMM in gemm.cuh.
 #pragma once
