@@ -508,8 +508,10 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
         // D(rr, c), rr >= c
         v[u] = (cb == rb) ? ((rr >= c) ? Iv[cb * SB * IVP + (c & 31) * IVP + (rr & 31)] : 0.0)
                           : ((cb < rb && rr < nact) ? S[c * DP_PITCH + rr] : 0.0);
-        // D^T(rr, c) = D(c, rr), c >= rr
-        w[u] = (cb == rb) ? ((c >= rr) ? Iv[cb * SB * IVP + (rr & 31) * IVP + (c & 31)] : 0.0)
+        // D^T(rr, c) = D(c, rr), c >= rr -- only the gradient / posterior paths (those that also
+        // keep W) read D_k^T: the nlZ-only path skips it
+        w[u] = !Wd ? 0.0
+             : (cb == rb) ? ((c >= rr) ? Iv[cb * SB * IVP + (rr & 31) * IVP + (c & 31)] : 0.0)
                           : ((cb > rb && c < nact) ? S[c * DP_PITCH + rr] : 0.0);
       }
       // blocks that are identically zero (D above, D^T below the block diagonal) are not stored:
@@ -522,7 +524,7 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
           if (Wd) Wd[(long long)c * Np + rr] = v[u];
         }
       }
-      if (cb >= rb) {
+      if (cb >= rb && Wd) {
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
           const int c = cb * SB + 2 * u + cpar;
