@@ -10,6 +10,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges cost nothing unless a profiler is attached
+
 #include "chol.cuh"
 #include "common.cuh"
 #include "cov.cuh"
@@ -36,6 +38,7 @@ struct Bufs {              // device storage for `cap` batch slots
   long long smat() const { return (long long)Np * Np; }
 };
 
+struct gpb_post;
 struct gpb_ctx {
   int device = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -82,6 +85,9 @@ struct gpb_ctx {
   double *pXs = nullptr, *pys = nullptr, *ps2s = nullptr, *pBt = nullptr, *pmu = nullptr,
          *pv = nullptr, *psamp = nullptr, *pout = nullptr;
   size_t pXs_n = 0, pBt_n = 0, ppart_n = 0, psamp_n = 0, pout_n = 0;
+  // live posterior batches created from this context: they hold a pointer back to it, so
+  // gpb_destroy releases the ones the caller has not freed (their handles die with the context)
+  std::vector<gpb_post*> posts;
 };
 
 struct gpb_post {
@@ -128,6 +134,15 @@ static std::string g_create_err;
   } while (0)
 
 #define LAUNCHED(ctx) ((ctx)->launches++)
+
+// NVTX range over the enclosing scope: labels the phases K1..K5 (and the jitter-retry loop) in
+// nsys / ncu timelines
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 static inline int round_up(long long v, int m) { return (int)(((v + m - 1) / m) * m); }
 static inline unsigned grid1d(long long n, int block = 256) {
@@ -289,6 +304,9 @@ extern "C" int gpb_create(int device, gpb_ctx** out) {
   return GPB_OK;
 }
 
+static void free_bufs(Bufs& b);
+static void release_post(gpb_post* post);
+
 static void free_bufs(Bufs& b) {
   double** ptrs[] = {&b.Abuf, &b.Wbuf, &b.Dbuf, &b.DTbuf, &b.xs, &b.resid, &b.sn2v, &b.bvec, &b.zvec,
                      &b.alpha, &b.logdet, &b.mult, &b.fmult, &b.hyp, &b.nlz, &b.dnlz, &b.gpart};
@@ -312,6 +330,11 @@ extern "C" void gpb_destroy(gpb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
+  {
+    std::vector<gpb_post*> live;
+    live.swap(ctx->posts);
+    for (gpb_post* p : live) release_post(p);
+  }
   free_bufs(ctx->ws);
   double* p[] = {ctx->dX, ctx->dy, ctx->ds2, ctx->pXs, ctx->pys, ctx->ps2s, ctx->pBt, ctx->pmu,
                  ctx->pv, ctx->psamp, ctx->pout};
@@ -361,7 +384,6 @@ static int fill_model(Model& md, int cov_kind, int degree, int ard, int mean_kin
                       int D) {
   if (cov_kind < 0 || cov_kind > 2) return GPB_EINVAL;
   if (cov_kind == GPB_COV_MATERN && degree != 1 && degree != 3 && degree != 5) return GPB_EINVAL;
-  if (cov_kind == GPB_COV_RQ && !ard) return GPB_EINVAL;   // the reference has no isotropic RQ
   if (mean_kind < 0 || mean_kind > 2) return GPB_EINVAL;
   if (nz[0] < 0 || nz[0] > 1 || nz[1] < 0 || nz[1] > 2 || nz[2] < 0 || nz[2] > 1) return GPB_EINVAL;
   md.cov_kind = cov_kind;
@@ -533,6 +555,7 @@ static void launch_build(gpb_ctx* ctx, const BuildArgs& a, dim3 grid, size_t sme
 
 static void run_prep_build(gpb_ctx* ctx, Bufs& b, const Model& md, long long N, const int* sel,
                            int nsel) {
+  NvtxRange nv("gpb:K1 prep+build");
   PrepArgs pa;
   pa.md = md;
   pa.N = (int)N;
@@ -581,6 +604,7 @@ static void run_prep_build(gpb_ctx* ctx, Bufs& b, const Model& md, long long N, 
 // substitution z = L^-1 (y - m) carried along.
 static void run_potrf(gpb_ctx* ctx, Bufs& b, long long N, const int* sel, int nsel, bool write_w,
                       bool with_rhs = true) {
+  NvtxRange nv("gpb:K2 potrf");
   const BatchBufs bb = batch_bufs(b, sel, N);
   const bool look0 = ctx->lookahead == 2 || (ctx->lookahead == 1 && nsel <= 8);
   const int Nt = b.Nt;                                 // outer block = OB tile columns
@@ -671,6 +695,7 @@ static void run_potrf(gpb_ctx* ctx, Bufs& b, long long N, const int* sel, int ns
 
 // alpha = L^-T z / sl
 static void run_bwd(gpb_ctx* ctx, Bufs& b, const int* sel, int nsel) {
+  NvtxRange nv("gpb:K2 backward solve");
   copy_sel_kernel<<<dim3((unsigned)((b.Np + 255) / 256), (unsigned)nsel), 256, 0, ctx->stream>>>(
       b.bvec, b.zvec, sel, b.Np);
   LAUNCHED(ctx);
@@ -696,6 +721,7 @@ static void run_bwd(gpb_ctx* ctx, Bufs& b, const int* sel, int nsel) {
 // Ainv = W^T W into the lower tiles of Abuf.
 static void run_inverse(gpb_ctx* ctx, Bufs& b, long long N, const int* sel, int nsel, bool dual,
                         bool syrk2) {
+  NvtxRange nv("gpb:K2 inverse (trtri + W^T W)");
   const BatchBufs bb = batch_bufs(b, sel, N);
   const int Nt = b.Nt;
   const bool recursive = ctx->trtri == 2 || (ctx->trtri == 1 && nsel <= ctx->trtri_max);
@@ -730,6 +756,7 @@ static void launch_grad(gpb_ctx* ctx, const GradArgs& a, dim3 grid, int ard, int
 }
 
 static void run_grad(gpb_ctx* ctx, Bufs& b, const Model& md, long long N, const int* sel, int nsel) {
+  NvtxRange nv("gpb:K3 gradient");
   GradArgs ga;
   ga.D = md.D;
   ga.N = (int)N;
@@ -788,6 +815,7 @@ static int factor_with_retry(gpb_ctx* ctx, Bufs& b, const Model& md, long long N
   int nsel = (int)slots.size();
   std::vector<int> cur = slots;
   for (int attempt = 0; attempt < 10; ++attempt) {
+    NvtxRange nv(attempt == 0 ? "gpb:factor" : "gpb:factor (jitter retry)");
     run_prep_build(ctx, b, md, N, sel, nsel);
     run_potrf(ctx, b, N, sel, nsel, write_w);
     CK(cudaGetLastError());                    // a refused launch must not pass for a result
@@ -819,6 +847,7 @@ static int factor_with_retry(gpb_ctx* ctx, Bufs& b, const Model& md, long long N
 // covariance and noise hyperparameters are unchanged): O(N^2) instead of O(N^3).
 static void run_solve_only(gpb_ctx* ctx, Bufs& b, const Model& md, long long N, const int* sel,
                            const int* fsel, int nsel) {
+  NvtxRange nv("gpb:solve replay (cached factor)");
   // the factor's jitter multiplier belongs to the row as well
   copy_mult_kernel<<<(unsigned)((nsel + 255) / 256), 256, 0, ctx->stream>>>(b.mult, b.fmult, sel, fsel, nsel);
   LAUNCHED(ctx);
@@ -872,6 +901,7 @@ static int nlz_batch_impl(gpb_ctx* ctx, const double* hyp, bool hyp_on_device, i
                           int want_grad, double* nlZ, double* dnlZ, double* sn2_mult,
                           int32_t* status, bool out_on_device) {
   if (!ctx) return GPB_EINVAL;
+  NvtxRange nv_call(want_grad ? "gpb_nlz_batch (nlZ + gradient)" : "gpb_nlz_batch (nlZ)");
   if (!ctx->has_model || !ctx->has_data) FAIL(GPB_ESTATE, "gpb_nlz_batch: set model and data first");
   if (!hyp || !nlZ || B <= 0) FAIL(GPB_EINVAL, "gpb_nlz_batch: bad arguments");
   if (want_grad && !dnlZ) FAIL(GPB_EINVAL, "gpb_nlz_batch: dnlZ is NULL");
@@ -901,6 +931,14 @@ static int nlz_batch_impl(gpb_ctx* ctx, const double* hyp, bool hyp_on_device, i
       // sampling move along a mean coordinate hit the factor of the current point.)
       const int kn = md.cov_n + md.noise_n;
       const bool cacheable = ctx->cache_enabled && !hyp_on_device && !want_grad && B <= b.cap;
+      // An invalidated cache (new model/data/workspace, a gradient or multi-chunk call, a failed
+      // call) must not leave entries behind: their slots were reallocated or overwritten, and the
+      // re-keying below only covers the rows of THIS call.
+      if (!ctx->cache.valid) {
+        ctx->cache.n = 0;
+        ctx->cache.key.clear();
+        ctx->cache.ok.clear();
+      }
       std::vector<int> miss, hit, hit_f;
       for (int sidx = 0; sidx < n; ++sidx) {
         int found = -1;
@@ -1051,6 +1089,7 @@ extern "C" int gpb_nlz_batch_dev(gpb_ctx* ctx, const double* d_hyp, int64_t B, i
 // ---------------------------------------------------------------------------------
 extern "C" int gpb_posterior_batch(gpb_ctx* ctx, const double* hyp, int64_t B, gpb_post** out) {
   if (!ctx || !out) return GPB_EINVAL;
+  NvtxRange nv_call("gpb_posterior_batch");
   *out = nullptr;
   if (!ctx->has_model || !ctx->has_data) FAIL(GPB_ESTATE, "gpb_posterior_batch: set model and data first");
   if (!hyp || B <= 0 || B > 32768) FAIL(GPB_EINVAL, "gpb_posterior_batch: bad arguments");
@@ -1131,19 +1170,27 @@ extern "C" int gpb_posterior_batch(gpb_ctx* ctx, const double* hyp, int64_t B, g
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return bail(GPB_ECUDA); }
   }
+  ctx->posts.push_back(post);
   *out = post;
   return GPB_OK;
 }
 
 extern "C" int64_t gpb_posterior_count(const gpb_post* post) { return post ? post->b.cap : 0; }
 
-extern "C" void gpb_posterior_free(gpb_post* post) {
-  if (!post) return;
-  cudaSetDevice(post->ctx->device);
-  cudaStreamSynchronize(post->ctx->stream);
+static void release_post(gpb_post* post) {
   free_bufs(post->b);
   if (post->X) cudaFree(post->X);
   delete post;
+}
+
+extern "C" void gpb_posterior_free(gpb_post* post) {
+  if (!post) return;
+  gpb_ctx* ctx = post->ctx;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  auto it = std::find(ctx->posts.begin(), ctx->posts.end(), post);
+  if (it != ctx->posts.end()) ctx->posts.erase(it);
+  release_post(post);
 }
 
 extern "C" int gpb_posterior_fetch(const gpb_post* post, int64_t s, int field, double* out) {
@@ -1220,6 +1267,7 @@ static int predict_impl(gpb_ctx* ctx, const gpb_post* cpost, const double* Xs, c
                         const double* s2s, int64_t M, int add_noise, int separate, int want_lpd,
                         double* mu, double* s2, double* lpd, bool on_device) {
   if (!ctx || !cpost) return GPB_EINVAL;
+  NvtxRange nv("gpb:K4 predict");
   gpb_post* post = const_cast<gpb_post*>(cpost);
   if (!Xs || !mu || !s2 || M <= 0) FAIL(GPB_EINVAL, "gpb_predict: bad arguments");
   if (want_lpd && (!ys || !lpd)) FAIL(GPB_EINVAL, "Cannot calculate log predictive density without y_star.");
@@ -1546,6 +1594,7 @@ static int predict_impl(gpb_ctx* ctx, const gpb_post* cpost, const double* Xs, c
 extern "C" int gpb_posterior_append(gpb_ctx* ctx, gpb_post* post, const double* x_new, double y_new,
                                     int32_t* status) {
   if (!ctx || !post || !x_new || !status) return GPB_EINVAL;
+  NvtxRange nv("gpb:K5 rank-one append");
   if (post->ctx != ctx) FAIL(GPB_EINVAL, "gpb_posterior_append: posterior belongs to another context");
   const Model md = post->md;
   if (md.nz1 != 0 || md.nz2 != 0)

@@ -33,7 +33,7 @@ struct SlotP {
 };
 
 __host__ __device__ inline int cov_count(int kind, int ard, int D) {
-  if (!ard) return 2;
+  if (!ard) return kind == 2 ? 3 : 2;     // isotropic RQ: log ell, log sf, log shape
   return D + (kind == 2 ? 2 : 1);
 }
 __host__ __device__ inline int noise_count(int nz0, int nz1, int nz2) {

@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(PrepArgs a) {
   if (threadIdx.x == 0) {
     SlotP p;
     p.sf2 = exp(2 * h[nl]);
-    p.rq_a = (md.cov_kind == 2) ? exp(h[D + 1]) : 1.0;
+    p.rq_a = (md.cov_kind == 2) ? exp(h[nl + 1]) : 1.0;
     p.sn2_min = shnan[0] ? NAN : sh[0];          // np.min propagates NaN
     p.mult = a.mult[slot];
     p.lchol = (p.sn2_min >= 1e-6) ? 1 : 0;       // gaussian_process.py:2404
@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(256) cov_plugin_kernel(CovArgs a) {
   const int D = a.D;
   const int nl = a.ard ? D : 1;
   const double sf2 = exp(2 * a.hyp[nl]);
-  const double a_rq = (a.cov_kind == 2) ? exp(a.hyp[D + 1]) : 1.0;
+  const double a_rq = (a.cov_kind == 2) ? exp(a.hyp[nl + 1]) : 1.0;
   const long long cols = a.diag ? 1 : (a.Xs ? a.M : a.N);
   const long long total = a.N * cols;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;

@@ -6,6 +6,7 @@ descriptor, the training data, and batched evaluation over hyperparameter rows.
 """
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -25,6 +26,7 @@ class PosteriorBatch:
 
     def __init__(self, engine, handle, count, N):
         self.engine, self._h, self.count, self.N = engine, handle, count, N
+        engine._batches.add(self)
 
     def fetch(self, s, field):
         n = {"alpha": self.N, "L": self.N * self.N}.get(field, 1)
@@ -35,9 +37,11 @@ class PosteriorBatch:
         return out if field == "alpha" else out[0]
 
     def free(self):
-        if self._h is not None and self.engine.lib is not None:
+        # a closed engine has already released its batches (gpb_destroy): never touch the handle then
+        if self._h is not None and self.engine.lib is not None and self.engine._h is not None:
             self.engine.lib.gpb_posterior_free(self._h)
         self._h = None
+        self.engine._batches.discard(self)
 
     def __del__(self):
         try:
@@ -57,9 +61,13 @@ class Engine:
         self._h = h
         self.model = None
         self.N = self.D = 0
+        self._batches = weakref.WeakSet()      # live PosteriorBatch objects of this context
+        self.data_owner = None                 # token of whoever uploaded the current data (GP objects share engines)
 
     def close(self):
         if getattr(self, "_h", None) is not None:
+            for b in list(self._batches):      # their device buffers die with the context
+                b.free()
             self.lib.gpb_destroy(self._h)
             self._h = None
 
@@ -262,12 +270,15 @@ class Engine:
         return int(out[0]), int(out[1])
 
 
-_default = None
+_default = {}
 
 
-def get_engine():
-    """Process-wide default engine (created on first use; raises without a GPU)."""
-    global _default
-    if _default is None:
-        _default = Engine()
-    return _default
+def get_engine(device=None):
+    """The process-wide engine of a device (created on first use; raises without a GPU).  GP objects
+    and the plugin ``compute`` methods share it: a context sizes its evaluation workspace to the
+    free device memory, so one context per GP would make several live GPs starve each other."""
+    dev = default_device() if device is None else device
+    eng = _default.get(dev)
+    if eng is None or eng._h is None:
+        eng = _default[dev] = Engine(dev)
+    return eng

@@ -89,6 +89,8 @@ def sharded_rows(evaluate, M, group=None):
             t[1:1 + len(widths)] = torch.tensor(widths, dtype=torch.int64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
         widths = [int(v) for v in t[1:1 + int(t[0])].tolist()]
+    if widths is None:                  # M == 0 on a single rank: nothing was evaluated
+        return ()
     if local is None:
         local = np.zeros((0, sum(widths)))
     full = all_gather_rows(local, M, group)

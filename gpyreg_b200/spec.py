@@ -18,7 +18,7 @@ class ModelSpec:
     @property
     def cov_n(self):
         if not self.ard:
-            return 2
+            return 3 if self.cov_kind == COV_RQ else 2
         return self.D + (2 if self.cov_kind == COV_RQ else 1)
 
     @property

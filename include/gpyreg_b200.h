@@ -49,7 +49,9 @@ enum {
 typedef struct gpb_ctx gpb_ctx;
 typedef struct gpb_post gpb_post;
 
-/* One context per process and GPU (one host thread per context). */
+/* One context per process and GPU (one host thread per context).  gpb_destroy also releases
+ * every posterior batch created from the context that is still alive: their handles must
+ * not be used (or freed) afterwards. */
 int gpb_create(int device, gpb_ctx** out);
 void gpb_destroy(gpb_ctx* ctx);
 const char* gpb_last_error(const gpb_ctx* ctx);   /* ctx may be NULL: last create error */

@@ -53,8 +53,9 @@ class ModelSpec:
     def cov_n(self) -> int:
         # covariance_functions.py:22-36 (D+1), :291-292 (RQ: D+2),
         # isotropic_covariance_functions.py:14-28 (2)
+        # isotropic rational quadratic (no reference class; north_star names it): 3
         if not self.ard:
-            return 2
+            return 3 if self.cov_kind == COV_RQ else 2
         return self.D + (2 if self.cov_kind == COV_RQ else 1)
 
     @property
@@ -109,6 +110,21 @@ def cov_compute(spec: ModelSpec, hyp, X, X_star=None, compute_diag=False,
                          "one-sample hyperparameter inputs.")
     if compute_grad and X_star is not None:
         raise ValueError("X_star should be None when compute_grad is True.")
+
+    if spec.cov_kind == COV_RQ and not spec.ard:
+        # Isotropic rational quadratic.  The reference has no such class; it is DEFINED here as
+        # RationalQuadraticARD (covariance_functions.py:301-367) with all D length scales tied,
+        # hyp = [log ell, log sf, log shape], and d/dlog(ell) = the sum of the ARD length-scale
+        # derivatives -- the relation the reference's own tests assert between its isotropic and
+        # ARD kernels (testing/test_isotropic_covariance_functions.py:164-240).
+        ard = ModelSpec(D=D, cov_kind=COV_RQ, ard=True)
+        h_ard = np.concatenate((np.full(D, hyp[0]), hyp[1:3]))
+        out = cov_compute(ard, h_ard, X, X_star, compute_diag, compute_grad)
+        if not compute_grad:
+            return out
+        K, dK = out
+        dK_iso = np.concatenate((np.sum(dK[:, :, :D], axis=2, keepdims=True), dK[:, :, D:]), axis=2)
+        return K, dK_iso
 
     nl = D if spec.ard else 1          # number of length scales
     ell = np.exp(hyp[0:nl]) if spec.ard else np.exp(hyp[0])

@@ -164,9 +164,9 @@ def test_lownoise_golden(eng, golden_lownoise, tag):
     post = eng.posterior_batch(c["hyp"])
     for b in np.nonzero(same)[0]:
         assert int(post.fetch(b, "L_chol")) == c["L_chol"][b]
-        cond_loose = 1e-5 if c["L_chol"][b] == 0 else TOL_NLZ
-        assert abs(nlz[b] - c["nlZ"][b]) <= cond_loose * abs(c["nlZ"][b])
     post.free()
+    # values (nlZ, gradient, alpha, predictions) of these rows, with a per-row bound derived from
+    # cond(A): tests/test_gpu_parity_full.py::test_lownoise_small_golden_gradient_and_predictions
 
 
 def test_wrong_hyperparameter_count_is_rejected(eng):
@@ -504,8 +504,8 @@ def test_seeded_fuzz_small_batches(eng, seed):
     cov_kind = int(rng.integers(0, 3))
     ard = bool(rng.integers(0, 2)) or cov_kind == 2
     degree = int(rng.choice([1, 3, 5])) if cov_kind == 1 else 0
-    if degree == 1:
-        degree = 3                       # Matern-1 length-scale gradients are NaN by construction
+    # Matern-1 stays Matern-1: its length-scale gradients are NaN by construction and
+    # grad_err() requires the NaN pattern to match the oracle's
     spec = orc.ModelSpec(D=D, cov_kind=cov_kind, degree=degree, ard=ard, mean_kind=int(rng.integers(0, 3)))
     X, y = synth_data(N + 1, D, seed=seed)
     Xn, yn, X, y = X[-1], y[-1], X[:-1], y[:-1]

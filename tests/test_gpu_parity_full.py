@@ -1,0 +1,312 @@
+"""Point-wise parity at the sizes BASELINE.json names ("next round" item 1):
+
+  * config 3 at its full size (N=5000, D=10, Matern-5 ARD + NegativeQuadratic) against the CPU oracle,
+  * config 2 and config 5 at N=2000, config 4 with gradient at N=8192 and nlZ-only at N=16384,
+  * a real f_min_fill design batch (reference-generated golden: both factorisation branches in one
+    call, nlZ spanning 16 decades),
+  * the low-noise branch: nlZ, gradient, alpha, L = -A^-1 and predictions against the reference, with
+    a per-row bound derived from cond(A) where the matrix is ill-conditioned,
+  * the isotropic rational quadratic kernel (= the reference's RationalQuadraticARD, length scales tied).
+
+Tolerances are north_star's: nlZ 1e-9 relative, gradient 1e-7 (max|d| / max|grad|), predictive mean
+and variance 1e-8.  The oracle runs on the host cores of the GPU box; sizes are chosen so the whole
+module stays within a few minutes there.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import gp_oracle as orc
+from tests.conftest import _load
+from tests.helpers import case, grad_err, rel_err, spec_from_array
+
+pytestmark = pytest.mark.gpu
+
+TOL_NLZ, TOL_GRAD, TOL_PRED = 1e-9, 1e-7, 1e-8
+EPS = np.finfo(float).eps
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from gpyreg_b200 import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def golden_r2():
+    return _load("round2.npz")
+
+
+def setup_engine(eng, spec, X, y, s2=None):
+    eng.set_model(spec.cov_kind, spec.degree, spec.ard, spec.mean_kind, spec.noise_params)
+    eng.set_data(X, y, s2)
+
+
+def host_mem_gb():
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable"):
+                    return int(line.split()[1]) / 2 ** 20
+    except OSError:
+        pass
+    return 0.0
+
+
+def check_predict(eng, spec, hyp, X, y, Xs, tol=TOL_PRED):
+    post = eng.posterior_batch(hyp)
+    posts = orc.posterior_batch(spec, hyp, X, y, None)
+    for b in range(hyp.shape[0]):
+        ra = np.asarray(posts[b].alpha).reshape(-1)
+        assert np.max(np.abs(post.fetch(b, "alpha") - ra)) <= 1e-9 * np.max(np.abs(ra))
+    for sep in (False, True):
+        mu, v = eng.predict(post, Xs, add_noise=True, separate=sep)
+        rmu, rv = orc.predict(spec, posts, X, y, Xs, add_noise=True, separate_samples=sep)
+        assert np.max(np.abs(mu - rmu)) <= tol * (1 + np.max(np.abs(rmu)))
+        assert np.max(np.abs(v - rv)) <= tol * np.max(np.abs(rv))
+    post.free()
+
+
+# ---------------------------------------------------------------- full-size configs vs the oracle
+def test_cfg3_headline_shape_pointwise(eng):
+    """BASELINE.json config 3 / the bench's headline shape: 40 tiles per side."""
+    from bench import benign_hyp, synth_data
+    N, D = 5000, 10
+    spec = orc.ModelSpec(D=D, cov_kind=1, degree=5, ard=True, mean_kind=2)
+    X, y = synth_data(N, D, seed=0)
+    hyp = benign_hyp(spec, 2, y, seed=1)
+    setup_engine(eng, spec, X, y)
+    nlz, dnlz, mult, status = eng.nlz_batch(hyp, want_grad=True)
+    ref_nlz, ref_dnlz = orc.nlz_batch(spec, hyp, X, y, None, True)
+    assert not status.any() and np.all(mult == 1)
+    assert rel_err(nlz, ref_nlz) <= TOL_NLZ
+    assert grad_err(dnlz, ref_dnlz) <= TOL_GRAD
+    np.testing.assert_array_equal(eng.nlz_batch(hyp)[0], nlz)
+    Xs = np.random.default_rng(2).uniform(-3, 3, (64, D))
+    check_predict(eng, spec, hyp[:1], X, y, Xs)
+
+
+@pytest.mark.parametrize("model", ["cfg2", "cfg5"])
+def test_cfg2_cfg5_n2000_pointwise(eng, model):
+    from bench import benign_hyp, synth_data
+    N = 2000
+    D, spec = {"cfg2": (6, orc.ModelSpec(D=6, cov_kind=0, ard=True, mean_kind=1)),
+               "cfg5": (10, orc.ModelSpec(D=10, cov_kind=1, degree=3, ard=False, mean_kind=1))}[model]
+    X, y = synth_data(N, D, seed=0)
+    hyp = benign_hyp(spec, 3, y, seed=1)
+    setup_engine(eng, spec, X, y)
+    nlz, dnlz, mult, status = eng.nlz_batch(hyp, want_grad=True)
+    ref_nlz, ref_dnlz = orc.nlz_batch(spec, hyp, X, y, None, True)
+    assert not status.any() and np.all(mult == 1)
+    assert rel_err(nlz, ref_nlz) <= TOL_NLZ
+    assert grad_err(dnlz, ref_dnlz) <= TOL_GRAD
+    Xs = np.random.default_rng(2).uniform(-3, 3, (2000 if model == "cfg5" else 300, D))
+    check_predict(eng, spec, hyp, X, y, Xs)
+
+
+def test_cfg4_n8192_gradient_pointwise(eng):
+    """config 4's model (one RationalQuadratic-ARD GP, D=8) with gradient at N=8192 (64 tiles per
+    side; the oracle materialises the (cov_N, N, N) derivative tensor: 5.4 GB)."""
+    from bench import benign_hyp, synth_data
+    if host_mem_gb() < 40:
+        pytest.skip("the CPU oracle needs ~20 GB of host memory at N=8192")
+    N, D = 8192, 8
+    spec = orc.ModelSpec(D=D, cov_kind=2, ard=True, mean_kind=1)
+    X, y = synth_data(N, D, seed=0)
+    hyp = benign_hyp(spec, 1, y, seed=1)
+    setup_engine(eng, spec, X, y)
+    nlz, dnlz, mult, status = eng.nlz_batch(hyp, want_grad=True)
+    ref_nlz, ref_dnlz = orc.nlz_batch(spec, hyp, X, y, None, True)
+    assert not status.any() and np.all(mult == 1)
+    assert rel_err(nlz, ref_nlz) <= TOL_NLZ
+    assert grad_err(dnlz, ref_dnlz) <= TOL_GRAD
+
+
+def test_cfg4_n16384_nlz_pointwise(eng):
+    """config 4's model, nlZ only, at half its stated size (K is 2 GB; the oracle's temporaries need
+    ~10 GB of host memory and ~20 s of LAPACK)."""
+    from bench import benign_hyp, synth_data
+    if host_mem_gb() < 40:
+        pytest.skip("the CPU oracle needs ~10 GB of host memory at N=16384")
+    N, D = 16384, 8
+    spec = orc.ModelSpec(D=D, cov_kind=2, ard=True, mean_kind=1)
+    X, y = synth_data(N, D, seed=0)
+    hyp = benign_hyp(spec, 1, y, seed=1)
+    setup_engine(eng, spec, X, y)
+    nlz, _, mult, status = eng.nlz_batch(hyp, want_grad=False)
+    ref_nlz = orc.nlz_batch(spec, hyp, X, y, None, False)
+    assert not status.any() and np.all(mult == 1)
+    assert rel_err(nlz, ref_nlz) <= TOL_NLZ
+
+
+# ---------------------------------------------------------------- real design rows (reference golden)
+def test_design_batch_both_branches(eng, golden_r2):
+    """64 rows of the f_min_fill design of the config-3 model at N=2000 (SURVEY.md 8d "design set"),
+    evaluated by the reference: rows anywhere in the LB..UB box, 12 of them in the low-noise branch,
+    all in ONE call.  sn2_mult first, then nlZ and the gradient with relative tolerances."""
+    c = case(golden_r2, "design")
+    X, y, H = c["X"], c["y"], c["hyp"]
+    D = X.shape[1]
+    spec = orc.ModelSpec(D=D, cov_kind=1, degree=5, ard=True, mean_kind=2)
+    setup_engine(eng, spec, X, y)
+    with np.errstate(all="ignore"):
+        nlz, dnlz, mult, status = eng.nlz_batch(H, want_grad=True)
+    assert not status.any()
+    np.testing.assert_array_equal(mult, c["sn2_mult"])
+    lchol = c["L_chol"].astype(bool)
+    assert (~lchol).sum() >= 8 and lchol.sum() >= 40           # both branches present
+    assert np.all(np.isfinite(nlz)) and np.all(np.isfinite(dnlz))
+    e_nlz = np.abs(nlz - c["nlZ"]) / np.abs(c["nlZ"])
+    e_grad = np.array([grad_err(dnlz[b], c["dnlZ"][b]) for b in range(H.shape[0])])
+    print("design: nlZ rel err high-noise %.2e low-noise %.2e; gradient %.2e / %.2e"
+          % (e_nlz[lchol].max(), e_nlz[~lchol].max(), e_grad[lchol].max(), e_grad[~lchol].max()))
+    assert e_nlz.max() <= TOL_NLZ
+    assert e_grad.max() <= TOL_GRAD
+    # nlZ-only evaluation of the same batch: same bits; and in two halves: same bits
+    nlz0 = eng.nlz_batch(H)[0]
+    np.testing.assert_array_equal(nlz0, nlz)
+    np.testing.assert_array_equal(np.concatenate((eng.nlz_batch(H[:31])[0], eng.nlz_batch(H[31:])[0])), nlz)
+
+
+# ---------------------------------------------------------------- low-noise branch
+def _cond_rows(spec, hyp, X, mult):
+    """cond_2 of the matrix the low-noise branch factors, K + sn2_mult * sn2 * I (:2432)."""
+    out = []
+    for h, m in zip(hyp, mult):
+        K = orc.cov_compute(spec, h[:spec.cov_n], X)
+        sn2 = orc.noise_compute(spec, h[spec.cov_n:spec.cov_n + spec.noise_n], X, None, None)
+        w = np.linalg.eigvalsh(K + m * float(np.min(sn2)) * np.eye(X.shape[0]))
+        out.append(w[-1] / max(w[0], 1e-300))
+    return np.array(out)
+
+
+def test_lownoise_multi_tile_golden(eng, golden_r2):
+    """Low-noise branch (gaussian_process.py:2424-2448) on 4 tiles per side, matrices that are NOT
+    numerically singular (cond ~1e7..1e9): everything the reference produces in that branch --
+    nlZ, gradient, alpha, L = -A^-1, predictions -- at north_star's tolerances, widened only by
+    the matrix's own conditioning where 8*eps*cond(A) exceeds them (the reference's result moves by
+    that much under a permutation of the data rows)."""
+    c = case(golden_r2, "low2")
+    spec = spec_from_array(c["spec"])
+    X, y, H = c["X"], c["y"], c["hyp"]
+    setup_engine(eng, spec, X, y)
+    nlz, dnlz, mult, status = eng.nlz_batch(H, want_grad=True)
+    assert not status.any()
+    np.testing.assert_array_equal(mult, c["sn2_mult"])
+    cond = _cond_rows(spec, H, X, mult)
+    slack = 8 * EPS * cond
+    post = eng.posterior_batch(H)
+    mu0, v0 = eng.predict(post, c["Xs"], add_noise=False, separate=True)
+    mu1, v1 = eng.predict(post, c["Xs"], add_noise=True, separate=True)
+    for b in range(H.shape[0]):
+        assert int(post.fetch(b, "L_chol")) == 0 == c["L_chol"][b]
+        e_nlz = abs(nlz[b] - c["nlZ"][b]) / abs(c["nlZ"][b])
+        e_grad = grad_err(dnlz[b], c["dnlZ"][b])
+        al = post.fetch(b, "alpha")
+        e_al = np.max(np.abs(al - c["alpha"][b])) / np.max(np.abs(c["alpha"][b]))
+        e_L = 0.0
+        if b == 0:
+            e_L = np.max(np.abs(post.fetch(b, "L") - c["L0"])) / np.max(np.abs(c["L0"]))
+        e_mu = max(np.max(np.abs(m[:, b] - c[k][:, b])) / (1 + np.max(np.abs(c[k][:, b])))
+                   for m, k in ((mu0, "pred0.mu"), (mu1, "pred1.mu")))
+        e_v = max(np.max(np.abs(v[:, b] - c[k][:, b])) / np.max(np.abs(c[k][:, b]))
+                  for v, k in ((v0, "pred0.s2"), (v1, "pred1.s2")))
+        print("low2 row %d: cond %.2e  nlZ %.1e grad %.1e alpha %.1e L %.1e mu %.1e s2 %.1e  (8 eps cond = %.1e)"
+              % (b, cond[b], e_nlz, e_grad, e_al, e_L, e_mu, e_v, slack[b]))
+        assert e_nlz <= max(TOL_NLZ, slack[b])
+        assert e_grad <= max(TOL_GRAD, slack[b])
+        assert e_al <= max(1e-9, slack[b])
+        assert e_L <= max(1e-9, slack[b])
+        assert e_mu <= max(TOL_PRED, slack[b])
+        assert e_v <= max(TOL_PRED, slack[b])
+        assert post.fetch(b, "sW") == pytest.approx(c["sW"][b], rel=1e-14)
+    post.free()
+
+
+@pytest.mark.parametrize("tag", ["eps", "thr"])
+def test_lownoise_small_golden_gradient_and_predictions(eng, golden_lownoise, tag):
+    """The round-1 low-noise goldens (N=150; `eps`: noiseless GaussianNoise(), numerically singular
+    K + 2.2e-16 I with x10 / x100 jitter; `thr`: constant noise straddling the 1e-6 threshold):
+    gradient and predictions too, each row held to max(north_star tolerance, 8*eps*cond(A))."""
+    c = case(golden_lownoise, tag)
+    spec = spec_from_array(c["spec"])
+    X, y, H = c["X"], c["y"], c["hyp"]
+    setup_engine(eng, spec, X, y)
+    with np.errstate(all="ignore"):
+        nlz, dnlz, mult, status = eng.nlz_batch(H, want_grad=True)
+    assert not status.any()
+    same = mult == c["sn2_mult"]
+    assert same[c["sn2_mult"] == 1].all()
+    cond = _cond_rows(spec, H, X, mult)
+    post = eng.posterior_batch(H)
+    mu, v = eng.predict(post, c["Xs"], add_noise=True, separate=True)
+    checked = 0
+    for b in np.flatnonzero(same):
+        lch = bool(c["L_chol"][b])
+        slack = 0.0 if lch else 8 * EPS * cond[b]
+        e_nlz = abs(nlz[b] - c["nlZ"][b]) / abs(c["nlZ"][b])
+        e_grad = grad_err(dnlz[b], c["dnlZ"][b])
+        al = post.fetch(b, "alpha")
+        e_al = np.max(np.abs(al - c["alpha"][b])) / np.max(np.abs(c["alpha"][b]))
+        e_mu = np.max(np.abs(mu[:, b] - c["pred.mu"][:, b])) / (1 + np.max(np.abs(c["pred.mu"][:, b])))
+        e_v = np.max(np.abs(v[:, b] - c["pred.s2"][:, b])) / np.max(np.abs(c["pred.s2"][:, b]))
+        print("%s row %d: L_chol %d cond %.2e  nlZ %.1e grad %.1e alpha %.1e mu %.1e s2 %.1e (8 eps cond = %.1e)"
+              % (tag, b, lch, cond[b], e_nlz, e_grad, e_al, e_mu, e_v, slack))
+        if slack > 1e-2:
+            continue                       # numerically singular: the reference itself has no correct digit
+        checked += 1
+        assert e_nlz <= max(TOL_NLZ, slack)
+        assert e_grad <= max(TOL_GRAD, slack)
+        assert e_al <= max(1e-9, slack)
+        assert e_mu <= max(TOL_PRED, slack)
+        assert e_v <= max(TOL_PRED, slack)
+    assert checked >= (3 if tag == "thr" else 0)
+    post.free()
+
+
+# ---------------------------------------------------------------- isotropic rational quadratic
+def test_rq_isotropic(eng, golden_r2):
+    """RationalQuadratic isotropic (named by north_star; no reference class): equals the reference's
+    RationalQuadraticARD with all length scales tied, the length-scale derivative being the sum of
+    the ARD ones (the reference's iso-vs-ARD test pattern, testing/test_isotropic_covariance_functions.py:164-240)."""
+    import gpyreg_b200 as g
+    from gpyreg_b200.isotropic_covariance_functions import RationalQuadraticIsotropic
+    from gpyreg_b200.mean_functions import ConstantMean
+    from gpyreg_b200.noise_functions import GaussianNoise
+    c = case(golden_r2, "rqiso")
+    cov = RationalQuadraticIsotropic()
+    D = c["X"].shape[1]
+    assert cov.hyperparameter_count(D) == 3
+    assert [n for n, _ in cov.hyperparameter_info(D)] == ["covariance_log_lengthscale", "covariance_log_outputscale",
+                                                         "covariance_log_shape"]
+    K, dK = cov.compute(c["hyp"], c["X"], compute_grad=True)
+    scale = np.max(np.abs(c["K"]))
+    assert np.max(np.abs(K - c["K"])) <= 1e-14 * scale
+    assert dK.shape == c["dK"].shape
+    assert np.max(np.abs(dK - c["dK"])) <= 1e-13 * np.max(np.abs(c["dK"]))
+    assert np.max(np.abs(cov.compute(c["hyp"], c["X"], c["Xs"]) - c["Kx"])) <= 1e-14 * scale
+    assert np.max(np.abs(cov.compute(c["hyp"], c["X"], compute_diag=True) - c["Kd"])) <= 1e-14 * scale
+    with pytest.raises(ValueError, match="Expected 3 covariance function hyperparameters"):
+        cov.compute(np.zeros(4), c["X"])
+    # through the GP: nlZ, gradient, posterior, predictions
+    X, y, H = c["gp.X"], c["gp.y"], c["gp.hyp"]
+    gp = g.GP(X.shape[1], RationalQuadraticIsotropic(), ConstantMean(), GaussianNoise(constant_add=True))
+    gp.update(X_new=X, y_new=y, hyp=H)
+    for b in range(H.shape[0]):
+        nlz, dnlz = gp._GP__compute_nlZ(H[b], True, False)
+        assert abs(nlz - c["gp.nlZ"][b]) <= TOL_NLZ * abs(c["gp.nlZ"][b])
+        assert grad_err(dnlz, c["gp.dnlZ"][b]) <= TOL_GRAD
+        al = gp.posteriors[b].alpha[:, 0]
+        assert np.max(np.abs(al - c["gp.alpha"][b])) <= 1e-9 * np.max(np.abs(c["gp.alpha"][b]))
+    for sep in (0, 1):
+        mu, s2 = gp.predict(c["gp.Xs"], add_noise=True, separate_samples=bool(sep))
+        assert np.max(np.abs(mu - c[f"gp.mu{sep}"])) <= TOL_PRED * (1 + np.max(np.abs(c[f"gp.mu{sep}"])))
+        assert np.max(np.abs(s2 - c[f"gp.s2{sep}"])) <= TOL_PRED * np.max(np.abs(c[f"gp.s2{sep}"]))
+    # the oracle's definition agrees with the reference golden bit for bit (pinned)
+    spec = orc.ModelSpec(D=X.shape[1], cov_kind=2, ard=False, mean_kind=1)
+    o_nlz, o_dnlz = orc.nlz_batch(spec, H, X, y, None, True)
+    np.testing.assert_array_equal(o_nlz, c["gp.nlZ"])
+    assert grad_err(o_dnlz, c["gp.dnlZ"]) <= 1e-13

@@ -1,0 +1,144 @@
+"""State-handling regressions of the device layer (factor cache, data upload, context and
+posterior lifetimes, several GP objects on one GPU), all through the C ABI."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import gp_oracle as orc
+from tests.helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _problem(N=300, D=3, B=12, mean_kind=2):
+    from bench import benign_hyp, synth_data
+    spec = orc.ModelSpec(D=D, cov_kind=1, degree=5, ard=True, mean_kind=mean_kind)
+    X, y = synth_data(N, D, seed=0)
+    return spec, X, y, benign_hyp(spec, B, y, seed=1)
+
+
+def _engine(spec, X, y):
+    from gpyreg_b200 import Engine
+    e = Engine(0)
+    e.set_model(spec.cov_kind, spec.degree, spec.ard, spec.mean_kind, spec.noise_params)
+    e.set_data(X, y, None)
+    return e
+
+
+_NOCACHE = r"""
+import sys, json
+import numpy as np
+sys.path.insert(0, ".")
+from gpyreg_b200 import Engine
+d = np.load(sys.argv[1])
+e = Engine(0)
+e.set_model(*[int(v) for v in d["model"][:4]], tuple(int(v) for v in d["model"][4:]))
+e.set_data(d["X"], d["y"], None)
+print(json.dumps([v.hex() for v in e.nlz_batch(d["hyp"])[0]]))
+"""
+
+
+def test_factor_cache_survives_invalidation(tmp_path):
+    """after the cache is invalidated (gradient call = workspace re-allocation
+    with W, new data, new model) a SMALLER cacheable call must not revive the entries of the
+    earlier, larger batch.  Reference values: a process with GPB_NLZ_CACHE=0."""
+    spec, X, y, hyp = _problem()
+    path = str(tmp_path / "p.npz")
+    np.savez(path, X=X, y=y, hyp=hyp,
+             model=np.array([spec.cov_kind, spec.degree, int(spec.ard), spec.mean_kind, *spec.noise_params]))
+    env = dict(os.environ, GPB_NLZ_CACHE="0")
+    out = subprocess.run([sys.executable, "-c", _NOCACHE, path], cwd=ROOT, env=env, check=True,
+                         capture_output=True, text=True, timeout=600).stdout.strip().splitlines()[-1]
+    import json
+    ref = np.array([float.fromhex(v) for v in json.loads(out)])
+
+    e = _engine(spec, X, y)
+    np.testing.assert_array_equal(e.nlz_batch(hyp)[0], ref)              # 12 rows cached
+    e.nlz_batch(hyp[5:6], want_grad=True)                                # re-allocates (W), overwrites slot 0
+    np.testing.assert_array_equal(e.nlz_batch(hyp[5:6])[0], ref[5:6])    # miss, re-keys slot 0 only
+    for r in (7, 0, 11, 5):                                              # old rows: must NOT hit dead slots
+        np.testing.assert_array_equal(e.nlz_batch(hyp[r:r + 1])[0], ref[r:r + 1])
+    # same N, different data: nothing of the old batch may survive
+    np.testing.assert_array_equal(e.nlz_batch(hyp)[0], ref)
+    e.set_data(X[::-1].copy(), y[::-1].copy(), None)
+    np.testing.assert_array_equal(e.nlz_batch(hyp[:1])[0], e.nlz_batch(hyp[:1], want_grad=True)[0])
+    got = e.nlz_batch(hyp[3:4])[0]
+    assert rel_err(got, ref[3:4]) <= 1e-11                               # permutation invariance, fresh factor
+    # mean-only design (all covariance/noise hyperparameters equal): every row has the same key
+    same = np.repeat(hyp[:1], 6, axis=0)
+    same[:, spec.cov_n + spec.noise_n] += np.arange(6) * 0.01
+    e.set_data(X, y, None)
+    a = e.nlz_batch(same)[0]
+    e.nlz_batch(same[:2], want_grad=True)
+    # slots 0 and 1 now hold inverses, not factors; a one-row call re-validates the cache, and the
+    # batched calls after it must find the factor in slot 0, not in their own (dead) slots
+    b = np.concatenate([e.nlz_batch(same[:1])[0], e.nlz_batch(same[1:4])[0], e.nlz_batch(same[4:6])[0]])
+    np.testing.assert_array_equal(a, b)
+    e.close()
+
+
+def test_inplace_data_edit_is_seen():
+    """the reference reads gp.X / gp.y afresh on every evaluation, so an
+    in-place edit of a single element must reach the GPU."""
+    import gpyreg_b200 as g
+    from gpyreg_b200.covariance_functions import Matern
+    from gpyreg_b200.mean_functions import ConstantMean
+    from gpyreg_b200.noise_functions import GaussianNoise
+    spec, X, y, hyp = _problem(N=200, B=2, mean_kind=1)
+    gp = g.GP(3, Matern(5), ConstantMean(), GaussianNoise(constant_add=True))
+    gp.X, gp.y = X.copy(), y.copy()
+    before = gp._GP__compute_nlZ(hyp[0], False, False)
+    assert rel_err(before, orc.nlz_batch(spec, hyp[:1], X, y, None, False)) <= 1e-9
+    gp.y[137, 0] += 0.5                         # one element, not at any strided probe position
+    after = gp._GP__compute_nlZ(hyp[0], False, False)
+    assert rel_err(after, orc.nlz_batch(spec, hyp[:1], gp.X, gp.y, None, False)) <= 1e-9
+    assert after != before
+    gp.X[3, 1] = np.nextafter(gp.X[3, 1], 10.0)  # a one-ulp edit
+    key = gp._data_key
+    gp._GP__compute_nlZ(hyp[0], False, False)
+    assert gp._data_key != key
+
+
+def test_several_gps_share_one_context():
+    """GP objects share the device's engine (no per-GP workspace hoarding) and
+    switching between them re-uploads the right data."""
+    import gpyreg_b200 as g
+    from gpyreg_b200.covariance_functions import Matern
+    from gpyreg_b200.mean_functions import ConstantMean
+    from gpyreg_b200.noise_functions import GaussianNoise
+    spec, X, y, hyp = _problem(N=260, B=2, mean_kind=1)
+    gps = []
+    for k in range(3):
+        gp = g.GP(3, Matern(5), ConstantMean(), GaussianNoise(constant_add=True))
+        gp.update(X_new=X[k * 40:k * 40 + 140], y_new=y[k * 40:k * 40 + 140], hyp=hyp)
+        gps.append(gp)
+    assert gps[0].engine is gps[1].engine is gps[2].engine
+    Xs = np.random.default_rng(0).uniform(-3, 3, (20, 3))
+    for k in (2, 0, 1, 0):
+        gp = gps[k]
+        Xk, yk = X[k * 40:k * 40 + 140], y[k * 40:k * 40 + 140]
+        nlz = gp._GP__compute_nlZ(hyp[1], False, False)
+        assert rel_err(nlz, orc.nlz_batch(spec, hyp[1:2], Xk, yk, None, False)) <= 1e-9
+        mu, s2 = gp.predict(Xs)
+        rmu, rs2 = orc.predict(spec, orc.posterior_batch(spec, hyp, Xk, yk, None), Xk, yk, Xs)
+        assert np.max(np.abs(mu - rmu)) <= 1e-8 * (1 + np.max(np.abs(rmu)))
+        assert np.max(np.abs(s2 - rs2)) <= 1e-8 * np.max(np.abs(rs2))
+
+
+def test_posterior_handles_die_with_their_context():
+    """closing an engine releases its posterior batches; stale Python handles
+    neither crash nor double-free."""
+    spec, X, y, hyp = _problem(N=150, B=2)
+    e = _engine(spec, X, y)
+    p1, p2 = e.posterior_batch(hyp), e.posterior_batch(hyp[:1])
+    p1.free()
+    e.close()
+    assert p2._h is None
+    p2.free()
+    p1.free()
+    del p1, p2, e

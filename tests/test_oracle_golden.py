@@ -103,3 +103,64 @@ def test_lownoise(golden_lownoise, tag):
     np.testing.assert_array_equal(v, c["pred.s2"])
     assert rel_err(np.stack([p.alpha[:, 0] for p in posts]), c["alpha"]) == 0.0
     assert grad_err(dnlz, c["dnlZ"]) == 0.0
+
+
+# ---------------------------------------------------------------- round-2 goldens
+@pytest.fixture(scope="module")
+def golden_r2():
+    from tests.conftest import _load
+    return _load("round2.npz")
+
+
+def test_low2_multi_tile_lownoise(golden_r2):
+    """Low-noise branch on 4 tiles per side: the restatement equals the reference bit for bit."""
+    c = case(golden_r2, "low2")
+    spec = spec_from_array(c["spec"])
+    nlz, dnlz = orc.nlz_batch(spec, c["hyp"], c["X"], c["y"], None, True)
+    np.testing.assert_array_equal(nlz, c["nlZ"])
+    np.testing.assert_array_equal(dnlz, c["dnlZ"])
+    posts = orc.posterior_batch(spec, c["hyp"], c["X"], c["y"], None)
+    np.testing.assert_array_equal(posts[0].L, c["L0"])
+    for b, p in enumerate(posts):
+        np.testing.assert_array_equal(p.alpha[:, 0], c["alpha"][b])
+        assert not p.L_chol and p.sn2_mult == c["sn2_mult"][b]
+    for an in (0, 1):
+        mu, s2 = orc.predict(spec, posts, c["X"], c["y"], c["Xs"], add_noise=bool(an), separate_samples=True)
+        np.testing.assert_array_equal(mu, c[f"pred{an}.mu"])
+        np.testing.assert_array_equal(s2, c[f"pred{an}.s2"])
+
+
+def test_design_rows(golden_r2):
+    """Two rows of the real f_min_fill design at N=2000 (one per factorisation branch)."""
+    c = case(golden_r2, "design")
+    spec = orc.ModelSpec(D=c["X"].shape[1], cov_kind=1, degree=5, ard=True, mean_kind=2)
+    rows = [int(np.flatnonzero(c["L_chol"] == 1)[0]), int(np.flatnonzero(c["L_chol"] == 0)[0])]
+    with np.errstate(all="ignore"):
+        nlz, dnlz = orc.nlz_batch(spec, c["hyp"][rows], c["X"], c["y"], None, True)
+    np.testing.assert_array_equal(nlz, c["nlZ"][rows])
+    np.testing.assert_array_equal(dnlz, c["dnlZ"][rows])
+
+
+def test_rq_isotropic_definition(golden_r2):
+    """Isotropic RQ is DEFINED as the reference's RationalQuadraticARD with tied length scales:
+    K, cross-covariance, prior variance and nlZ are the reference's bits, the length-scale derivative
+    is the sum of the ARD ones."""
+    c = case(golden_r2, "rqiso")
+    D = c["X"].shape[1]
+    spec = orc.ModelSpec(D=D, cov_kind=2, ard=False)
+    assert spec.cov_n == 3
+    K, dK = orc.cov_compute(spec, c["hyp"], c["X"], compute_grad=True)
+    np.testing.assert_array_equal(K, c["K"])
+    np.testing.assert_array_equal(dK, c["dK"])
+    np.testing.assert_array_equal(orc.cov_compute(spec, c["hyp"], c["X"], c["Xs"]), c["Kx"])
+    np.testing.assert_array_equal(orc.cov_compute(spec, c["hyp"], c["X"], compute_diag=True), c["Kd"])
+    X, y, H = c["gp.X"], c["gp.y"], c["gp.hyp"]
+    gspec = orc.ModelSpec(D=X.shape[1], cov_kind=2, ard=False, mean_kind=1)
+    nlz, dnlz = orc.nlz_batch(gspec, H, X, y, None, True)
+    np.testing.assert_array_equal(nlz, c["gp.nlZ"])
+    assert grad_err(dnlz, c["gp.dnlZ"]) <= 1e-13
+    posts = orc.posterior_batch(gspec, H, X, y, None)
+    for sep in (0, 1):
+        mu, s2 = orc.predict(gspec, posts, X, y, c["gp.Xs"], add_noise=True, separate_samples=bool(sep))
+        np.testing.assert_array_equal(mu, c[f"gp.mu{sep}"])
+        np.testing.assert_array_equal(s2, c[f"gp.s2{sep}"])
