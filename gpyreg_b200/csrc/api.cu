@@ -1449,7 +1449,7 @@ extern "C" int gpb_quad(gpb_ctx* ctx, const gpb_post* cpost, const double* mu, c
   gpb_post* post = const_cast<gpb_post*>(cpost);
   if (!mu || !sigma || !F || M <= 0 || (compute_var && !F_var)) FAIL(GPB_EINVAL, "gpb_quad: bad arguments");
   const Model md = post->md;
-  if (md.cov_kind != GPB_COV_SE || !md.ard)
+  if (md.cov_kind != GPB_COV_SE)
     FAIL(GPB_EINVAL, "Bayesian quadrature only supports the squared exponential kernel.");
   if (md.nz0 != 1) FAIL(GPB_EINVAL, "gpb_quad: needs the constant noise term (hyp[cov_N] = log sigma)");
   CK(cudaSetDevice(ctx->device));

@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(256) quad_build_kernel(QuadArgs a) {
     const int j = jt * T + i, gi = kt * T + i;
     double m = 0.0, itau = 0.0;
     if (j < a.mc) {
-      const double sg = a.sigma[(long long)j * D + k], ell = exp(hyp[k]);
+      const double sg = a.sigma[(long long)j * D + k], ell = exp(hyp[a.md.ard ? k : 0]);
       m = a.mu[(long long)j * D + k];
       itau = 1.0 / sqrt(sg * sg + ell * ell);
     }
@@ -270,11 +270,14 @@ __global__ void __launch_bounds__(256) quad_build_kernel(QuadArgs a) {
     if (j < a.mc) {
       double sl = 0.0, st = 0.0;            // sum log ell, sum log tau
       for (int k = 0; k < D; ++k) {
-        const double sg = a.sigma[(long long)j * D + k], ell = exp(hyp[k]);
-        sl += hyp[k];
+        // isotropic kernel: the one length scale serves every dimension (the reference indexes
+        // hyp[0:D], which is the same thing for D = 1, the only isotropic case its tests cover)
+        const double lh = hyp[a.md.ard ? k : 0];
+        const double sg = a.sigma[(long long)j * D + k], ell = exp(lh);
+        sl += lh;
         st += log(sqrt(sg * sg + ell * ell));
       }
-      v = 2 * hyp[D] + sl - st;            // :1925-1927
+      v = 2 * hyp[a.md.ard ? D : 1] + sl - st;            // :1925-1927
     }
     lnnf[threadIdx.x] = v;
     al[threadIdx.x] = alpha[kt * T + threadIdx.x];
@@ -349,11 +352,12 @@ __global__ void __launch_bounds__(256) quad_finish_kernel(QuadFinishArgs a) {
   if (a.compute_var) {
     double sl = 0.0, st = 0.0;
     for (int k = 0; k < D; ++k) {
-      const double ell = exp(hyp[k]);
-      sl += hyp[k];
+      const double lh = hyp[md.ard ? k : 0];
+      const double ell = exp(lh);
+      sl += lh;
       st += log(sqrt(2 * sg[k] * sg[k] + ell * ell));
     }
-    const double nf_kk = exp(2 * hyp[D] + sl - st);                  // :1949-1950
+    const double nf_kk = exp(2 * hyp[md.ard ? D : 1] + sl - st);     // :1949-1950
     double v = 0.0;
     for (int t = 0; t < a.nv; ++t) v += vpart[(long long)t * a.Mcp + j];
     a.V_s[o] = fmax(2.220446049250313e-16, nf_kk - v);               // :1966-1969

@@ -27,7 +27,7 @@ import scipy.stats
 from .batched_drivers import MultiChainSliceSampler, minimize_lockstep
 from .engine import Engine
 from .f_min_fill import (f_min_fill, smoothbox_cdf, smoothbox_student_t_cdf)
-from .sharding import sharded_nlz, sharded_rows
+from .sharding import sharded_nlz_device, sharded_predict_device, sharded_rows
 from .slice_sample import SliceSampler
 from .spec import ModelSpec
 
@@ -103,6 +103,22 @@ class Posterior:
     def _set(self, name, v):
         self._val[name], self._have[name] = v, True
 
+    def _detached(self):
+        """A plain host-side copy of the record (every field fetched), with no tie to the device:
+        what ``copy.deepcopy`` / ``pickle`` of a reference Posterior would hold."""
+        vals = [self._get(k) for k in self._FIELDS]
+        vals = [v.copy() if isinstance(v, np.ndarray) else v for v in vals]
+        return Posterior(np.array(self.hyp, copy=True), *vals)
+
+    def __deepcopy__(self, memo):
+        new = self._detached()
+        memo[id(self)] = new
+        return new
+
+    def __reduce__(self):
+        d = self._detached()
+        return (Posterior, (d.hyp, d.alpha, d.sW, d.L, d.sn2_mult, d.L_chol))
+
     alpha = property(lambda s: s._get("alpha"), lambda s, v: s._set("alpha", v))
     sW = property(lambda s: s._get("sW"), lambda s, v: s._set("sW", v))
     L = property(lambda s: s._get("L"), lambda s, v: s._set("L", v))
@@ -121,10 +137,36 @@ def _spec_of(D, covariance, mean, noise):
                         "(the fused CUDA kernels implement exactly those families)") from e
 
 
+def gp_from_spec(spec):
+    """A GP built from the plugin classes a ModelSpec names (benchmarks, tools)."""
+    from . import covariance_functions as cf
+    from . import isotropic_covariance_functions as icf
+    from . import mean_functions as mf
+    from .noise_functions import GaussianNoise
+    if spec.cov_kind == 0:
+        cov = cf.SquaredExponential() if spec.ard else icf.SquaredExponentialIsotropic()
+    elif spec.cov_kind == 1:
+        cov = cf.Matern(spec.degree) if spec.ard else icf.MaternIsotropic(spec.degree)
+    else:
+        cov = cf.RationalQuadraticARD() if spec.ard else icf.RationalQuadraticIsotropic()
+    mean = (mf.ZeroMean, mf.ConstantMean, mf.NegativeQuadratic)[spec.mean_kind]()
+    p = spec.noise_params
+    return GP(spec.D, cov, mean, GaussianNoise(p[0] == 1, p[1] >= 1, p[1] == 2, p[2] == 1))
+
+
 class GP:
     """A single Gaussian-process model (gaussian_process.py:15-62)."""
 
+    SHARD_MIN_N = 512      # below this a factorisation is cheaper than the all-gather's latency
+
+    MAX_D = 32             # the fused kernels keep per-dimension accumulators in registers (csrc/common.cuh MAXD)
+
     def __init__(self, D, covariance, mean, noise):
+        if D > self.MAX_D:
+            # fail at construction, not at the first upload deep inside fit()/update()
+            raise ValueError(f"gpyreg_b200.GP supports input dimension D <= {self.MAX_D} (got D = {D}): the fused "
+                             "covariance / gradient kernels hold one accumulator per dimension in registers. "
+                             "The plugin compute() methods have no such limit.")
         self.D = D
         self.covariance, self.mean, self.noise = covariance, mean, noise
         self._spec = _spec_of(D, covariance, mean, noise)
@@ -139,6 +181,47 @@ class GP:
         self.set_bounds()
         self.set_priors()
         self.temporary_data = {}
+
+    # ------------------------------------------------------------------ copying
+    _DEVICE_STATE = ("_engine", "_post_batch", "_token", "_data_key")
+
+    def __getstate__(self):
+        """Everything but the device handles (PyVBMC deep-copies and pickles its GPs): the copy's
+        posteriors are plain host records, and its factors are rebuilt on the GPU at the first
+        predict / quad / rank-one update."""
+        d = {k: v for k, v in self.__dict__.items() if k not in self._DEVICE_STATE}
+        if self.posteriors is not None:
+            posts = np.empty(self.posteriors.shape, dtype=object)
+            for i, p in enumerate(self.posteriors):
+                posts[i] = p._detached()
+            d["posteriors"] = posts
+        return d
+
+    def __setstate__(self, d):
+        self.__dict__.update(d)
+        self._engine = self._post_batch = self._data_key = None
+        self._token = object()
+
+    def __deepcopy__(self, memo):
+        import copy
+        new = type(self).__new__(type(self))
+        memo[id(self)] = new
+        new.__setstate__(copy.deepcopy(self.__getstate__(), memo))
+        return new
+
+    def _device_batch(self):
+        """The device-resident posterior batch behind ``self.posteriors``; rebuilt from the stored
+        hyperparameter samples when this GP holds host records only (a copied / unpickled GP)."""
+        batch = self._post_batch
+        if batch is not None and batch._h is not None and self.posteriors is not None and \
+                all(p._batch is batch for p in self.posteriors):
+            return batch
+        if self.posteriors is None or self.X is None or self.y is None or \
+                any(p.alpha is None for p in self.posteriors):
+            return None                      # cleaned, or never computed: the caller must update()
+        hyp = np.stack([np.asarray(p.hyp, dtype=float) for p in self.posteriors])
+        self.posteriors, self._post_batch = self._posteriors_for(hyp)
+        return self._post_batch
 
     # ------------------------------------------------------------------ layout helpers
     def _hyper_info(self):
@@ -190,17 +273,26 @@ class GP:
         return "GP:\n" + "".join("    " + ln for ln in body.splitlines(True))
 
     def __repr__(self):
-        """One ``self.<attribute> = <summary>`` line per public attribute, small arrays printed in
-        full and large ones by shape (the reference's layout, gaussian_process.py:64-80)."""
+        """``self.<attribute> = <summary>`` for the attributes the reference lists first
+        (gaussian_process.py:64-80), then every other public attribute in sorted order; arrays with
+        fewer than 10 elements are printed in full, larger ones by shape, dictionaries by identity
+        (the layout of the reference's formatting.full_repr)."""
         def brief(v):
-            if not isinstance(v, np.ndarray):
-                return repr(v)
-            if v.dtype != object and v.size < 10:
-                return np.array2string(v, precision=4, suppress_small=True, separator=", ") + " : ndarray"
-            return f"{v.shape} ndarray"
-        names = ["D", "covariance", "mean", "noise", "X", "y", "s2", "lower_bounds", "upper_bounds",
+            if isinstance(v, np.ndarray):
+                if np.prod(v.shape) < 10:
+                    text = np.array2string(v, precision=4, suppress_small=True, separator=", ")
+                    if "\n" in text:
+                        text = "\n" + "\n".join("    " + ln for ln in text.splitlines())
+                    return f"{text} : {type(v).__name__}"
+                return f"{v.shape} {type(v).__name__}"
+            if type(v) is dict:
+                return object.__repr__(v)
+            return repr(v)
+        first = ["D", "covariance", "mean", "noise", "X", "y", "s2", "lower_bounds", "upper_bounds",
                  "posteriors"]
-        return "GP:\n" + "\n".join(f"    self.{n} = {brief(getattr(self, n))}" for n in names)
+        rest = sorted(k for k in self.__dict__ if k not in first and not k.startswith("_"))
+        lines = [f"self.{n} = {brief(getattr(self, n, None))}" for n in first + rest]
+        return "GP:\n" + "\n".join("    " + ln for ln in ",\n".join(lines).splitlines())
 
     # ------------------------------------------------------------------ bounds
     def set_bounds(self, bounds=None):
@@ -512,12 +604,13 @@ class GP:
         hyp = np.atleast_2d(np.asarray(hyp, dtype=float))
         eng = self._sync_engine()
         world = _world_size()
-        if world > 1 and hyp.shape[0] >= 2 * world:
+        if world > 1 and hyp.shape[0] >= world and self.X.shape[0] >= self.SHARD_MIN_N:
             # one process per GPU, same batch on every rank (same seeds): each rank evaluates its
-            # block of rows and one all-gather returns all of them -- results are bitwise those of
-            # a single-GPU run, because a row's value does not depend on the batch it is in
-            nlz, dnlz, _, status = sharded_nlz(lambda rows, g: eng.nlz_batch(rows, want_grad=g), hyp,
-                                               compute_grad)
+            # block of rows on the device and one all-gather returns all of them -- results are
+            # bitwise those of a single-GPU run, because a row's value does not depend on the batch
+            # it is in.  Design batches, lock-step L-BFGS starts and slice-sampling chains all come
+            # through here, so they spread over the GPUs as soon as there is a row per rank.
+            nlz, dnlz, _, status = sharded_nlz_device(eng, hyp, compute_grad)
         else:
             nlz, dnlz, _, status = eng.nlz_batch(hyp, want_grad=compute_grad)
         if status.any():
@@ -622,9 +715,8 @@ class GP:
     def _rank_one_append(self, X_new, y_new):
         """The device rank-one update; False when it does not apply or was unstable (the caller
         then rebuilds all samples, which the reference does per unstable sample, :864-868)."""
-        batch = self._post_batch
-        if batch is None or batch._h is None or self.posteriors is None or \
-                any(p._batch is not batch for p in self.posteriors):
+        batch = self._device_batch()
+        if batch is None:
             return False
         status = batch.engine.posterior_append(batch, X_new[0], float(y_new[0, 0]))
         if status is None:
@@ -662,10 +754,9 @@ class GP:
             raise ValueError("Cannot calculate log predictive density without y_star.")
         if self.y is None:
             return self._predict_prior(x_star, y_star, s2_star, add_noise, separate_samples, return_lpd)
-        batch = self._post_batch
-        if batch is None or batch._h is None or self.posteriors is None or \
-                any(p._batch is not batch for p in self.posteriors):
-            raise RuntimeError("GP.predict: the posteriors hold no device factors; call "
+        batch = self._device_batch()
+        if batch is None:
+            raise RuntimeError("GP.predict: the posteriors hold no factors; call "
                                "update(compute_posterior=True) first")
         ys = None if y_star is None else y_star.reshape(-1)
         s2s = None if s2_star is None else s2_star.reshape(-1)
@@ -677,6 +768,8 @@ class GP:
         world = _world_size()
         if world > 1 and x_star.shape[0] >= 4096 * world:
             # test points sharded over the GPUs (every rank holds all posterior samples)
+            if ys is None and s2s is None and not return_lpd:
+                return sharded_predict_device(self.engine, batch, x_star, add_noise, separate_samples)
             return sharded_rows(run, x_star.shape[0])
         return run(0, x_star.shape[0])
 
@@ -888,16 +981,13 @@ class GP:
         from .covariance_functions import SquaredExponential
         if not isinstance(self.covariance, SquaredExponential):
             raise ValueError("Bayesian quadrature only supports the squared exponential kernel.")
-        if not self.covariance._ard:
-            raise ValueError("Bayesian quadrature needs the ARD squared exponential kernel "
-                             "(the reference reads D length scales, gaussian_process.py:1901)")
         D = self.D
         mu = np.tile(mu, (1, D)) if np.size(mu) == 1 else np.atleast_2d(np.asarray(mu, dtype=float))
         sigma = np.tile(sigma, (1, D)) if np.size(sigma) == 1 else np.atleast_2d(np.asarray(sigma, dtype=float))
         sigma = np.ascontiguousarray(np.broadcast_to(sigma, mu.shape))
-        batch = self._post_batch
-        if batch is None or batch._h is None:
-            raise RuntimeError("GP.quad: the posteriors hold no device factors; call "
+        batch = self._device_batch()
+        if batch is None:
+            raise RuntimeError("GP.quad: the posteriors hold no factors; call "
                                "update(compute_posterior=True) first")
         return self.engine.quad(batch, mu, sigma, compute_var=compute_var, separate=separate_samples)
 
@@ -905,13 +995,32 @@ class GP:
         """Posterior mean (M, Ns) and full covariance (M, M, Ns) at x_star for every
         hyperparameter sample (gaussian_process.py:1561-1661)."""
         x_star, y_star, s2_star = self._convert_shapes(x_star, y_star, s2_star)
-        batch = self._post_batch
-        if self.y is None or batch is None or batch._h is None:
-            raise RuntimeError("GP.predict_full needs posteriors with device factors; call "
-                               "update(compute_posterior=True) on a GP with data first")
+        if self.y is None:
+            return self._predict_full_prior(x_star, y_star, s2_star, add_noise)
+        batch = self._device_batch()
+        if batch is None:
+            raise RuntimeError("GP.predict_full: the posteriors hold no factors; call "
+                               "update(compute_posterior=True) first")
         return self.engine.predict_full(batch, x_star, None if y_star is None else y_star.reshape(-1),
                                         None if s2_star is None else s2_star.reshape(-1),
                                         add_noise=add_noise)
+
+    def _predict_full_prior(self, x_star, y_star, s2_star, add_noise):
+        """GP without training data: prior mean and covariance through the plugin kernels
+        (gaussian_process.py:1621-1624, :1649-1659)."""
+        cov_n, noise_n, mean_n = self._counts()
+        s_N, M = self.posteriors.size, x_star.shape[0]
+        mu, cov = np.zeros((M, s_N)), np.zeros((s_N, M, M))
+        for s, post in enumerate(self.posteriors):
+            h = np.asarray(post.hyp, dtype=float)
+            mu[:, s] = np.reshape(self.mean.compute(h[cov_n + noise_n:cov_n + noise_n + mean_n], x_star), -1)
+            C = self.covariance.compute(h[:cov_n], x_star)
+            cov[s] = (C + C.T) / 2
+            if add_noise:
+                mult = post.sn2_mult if post.sn2_mult is not None else 1
+                sn2 = self.noise.compute(h[cov_n:cov_n + noise_n], x_star, y_star, s2_star)
+                cov[s] += np.dot(np.eye(M), sn2) * mult
+        return mu, cov.transpose(1, 2, 0)
 
     def random_function(self, X_star, add_noise=False):
         """Draw one function from the GP (prior if there is no data, else posterior) at

@@ -4,9 +4,16 @@ own B200, and ONE all-gather returns the full result to every rank (SURVEY.md 8e
 is no exchange inside the computation, so nothing else is communicated: X, y, s2 are
 replicated (a few MB), a single factorisation never spans GPUs.
 
-The evaluation callables are injected, so the partition / gather logic is testable on CPU
-with the gloo backend (tests/test_sharding_gloo.py); on a GPU box the backend is NCCL and
-the gathered tensors live on the device.
+Two layers:
+  * ``sharded_nlz_device`` / ``sharded_predict_device`` -- the product path under NCCL.  The
+    rank's block goes to the device once, the C ABI's ``*_dev`` entry points write their results
+    straight into the send buffer of ONE ``all_gather_into_tensor``, and the gathered result
+    crosses to the host once (the GP API returns NumPy): no NumPy round trip between the
+    kernels and the collective.  The engine is duck-typed (``nlz_batch_dev`` / ``predict_dev``
+    taking raw pointers), so the same code runs under gloo on CPU tensors with a stand-in
+    engine (tests/test_sharding_gloo.py).
+  * ``sharded_nlz`` / ``sharded_rows`` -- generic versions with an injected NumPy evaluator, for
+    calls the ``*_dev`` entry points do not cover (log predictive density, per-point noise).
 """
 import numpy as np
 import torch
@@ -106,3 +113,111 @@ def sharded_predict(evaluate, Xs, group=None):
     through ``evaluate(points) -> (mu, s2)``.  Returns (mu, s2) for all M points."""
     Xs = np.ascontiguousarray(Xs, dtype=np.float64)
     return sharded_rows(lambda lo, hi: evaluate(Xs[lo:hi]), Xs.shape[0], group)
+
+
+# --------------------------------------------------------------------------------------
+# device-resident path (NCCL): results go from the kernels into the collective's send buffer
+# --------------------------------------------------------------------------------------
+def _settle(dev):
+    """The engine works on its own CUDA stream: buffers torch has just filled on ITS stream must be
+    complete before the engine writes into them (the engine synchronises its stream before it
+    returns, so the other direction is already ordered)."""
+    if dev.type == "cuda":
+        torch.cuda.current_stream(dev).synchronize()
+
+
+def _world_rank(group):
+    if dist.is_initialized():
+        return dist.get_world_size(group), dist.get_rank(group)
+    return 1, 0
+
+
+def nlz_block_to_send_buffer(engine, d_rows, n, P, want_grad, per, dev):
+    """Evaluate the ``n`` hyperparameter rows in ``d_rows`` (device tensor (n, P)) and return the
+    send buffer of the all-gather, laid out as struct-of-arrays over ``per`` slots:
+    [ nlZ (per) | sn2_mult (per) | status as int32 in the first half of (per) doubles | dnlZ (per*P) ].
+    The C ABI writes each output directly into its region."""
+    width = 3 + (P if want_grad else 0)
+    send = torch.zeros(per * width, dtype=torch.float64, device=dev)
+    if n > 0:
+        _settle(dev)
+        base, w = send.data_ptr(), 8 * per
+        engine.nlz_batch_dev(d_rows.data_ptr(), n, want_grad, base, (base + 3 * w) if want_grad else 0,
+                             base + w, base + 2 * w)
+    return send
+
+
+def unpack_nlz(recv, B, P, want_grad, world, per):
+    """Gathered (world, per*width) buffer -> (nlz, dnlz|None, sn2_mult, status) for the B rows."""
+    width = 3 + (P if want_grad else 0)
+    host = recv.reshape(world, per * width).cpu()
+    nlz, mult, status = np.empty(B), np.empty(B), np.empty(B, dtype=np.int32)
+    dnlz = np.empty((B, P)) if want_grad else None
+    for r, (lo, hi) in enumerate(shard_bounds(B, world)):
+        n = hi - lo
+        if n == 0:
+            continue
+        row = host[r]
+        nlz[lo:hi] = row[:n].numpy()
+        mult[lo:hi] = row[per:per + n].numpy()
+        status[lo:hi] = row[2 * per:3 * per].view(torch.int32)[:n].numpy()
+        if want_grad:
+            dnlz[lo:hi] = row[3 * per:3 * per + n * P].reshape(n, P).numpy()
+    return nlz, dnlz, mult, status
+
+
+def sharded_nlz_device(engine, hyp, want_grad, group=None):
+    """nlZ [, gradient] of every row of hyp (B, P) host array, identical on all ranks: rank r
+    uploads block r, ``engine.nlz_batch_dev`` fills the send buffer, one all-gather, one D2H.
+    Returns (nlz, dnlz|None, sn2_mult, status) for the whole batch on every rank."""
+    hyp = np.ascontiguousarray(np.atleast_2d(hyp), dtype=np.float64)
+    B, P = hyp.shape
+    world, rank = _world_rank(group)
+    per = -(-B // world)
+    lo, hi = shard_bounds(B, world)[rank]
+    dev = _device(group)
+    d_rows = torch.from_numpy(hyp[lo:hi]).to(dev) if hi > lo else None
+    send = nlz_block_to_send_buffer(engine, d_rows, hi - lo, P, want_grad, per, dev)
+    if world > 1:
+        recv = torch.empty(world * send.numel(), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(recv, send, group=group)
+    else:
+        recv = send
+    return unpack_nlz(recv, B, P, want_grad, world, per)
+
+
+def predict_block_to_send_buffer(engine, post, d_pts, n, cols, add_noise, separate, per, dev):
+    """[ mu (per*cols) | s2 (per*cols) ] for the rank's ``n`` test points (device tensor (n, D))."""
+    send = torch.zeros(2 * per * cols, dtype=torch.float64, device=dev)
+    if n > 0:
+        _settle(dev)
+        base = send.data_ptr()
+        engine.predict_dev(post, d_pts.data_ptr(), n, add_noise, separate, base, base + 8 * per * cols)
+    return send
+
+
+def sharded_predict_device(engine, post, Xs, add_noise=False, separate=False, group=None):
+    """Predictive mean / variance at the rows of Xs (M, D), test points sharded over the ranks and
+    every posterior sample replicated (the across-sample average stays local): block upload,
+    ``engine.predict_dev`` into the send buffer, one all-gather, one D2H.  -> (mu, s2), (M, cols)."""
+    Xs = np.ascontiguousarray(Xs, dtype=np.float64)
+    M = Xs.shape[0]
+    cols = post.count if separate else 1
+    world, rank = _world_rank(group)
+    per = -(-M // world)
+    lo, hi = shard_bounds(M, world)[rank]
+    dev = _device(group)
+    d_pts = torch.from_numpy(Xs[lo:hi]).to(dev) if hi > lo else None
+    send = predict_block_to_send_buffer(engine, post, d_pts, hi - lo, cols, add_noise, separate, per, dev)
+    if world > 1:
+        recv = torch.empty(world * send.numel(), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(recv, send, group=group)
+    else:
+        recv = send
+    host = recv.reshape(world, 2, per * cols).cpu().numpy()
+    mu, s2 = np.empty((M, cols)), np.empty((M, cols))
+    for r, (a, b) in enumerate(shard_bounds(M, world)):
+        if b > a:
+            mu[a:b] = host[r, 0, :(b - a) * cols].reshape(b - a, cols)
+            s2[a:b] = host[r, 1, :(b - a) * cols].reshape(b - a, cols)
+    return mu, s2

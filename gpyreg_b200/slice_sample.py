@@ -99,7 +99,9 @@ class SliceSampler:
             self.widths = ((self.UB - self.LB) / 2).copy()
             self.base_widths = None
         else:
-            widths = np.asarray(widths, dtype=float)
+            widths = np.asarray(widths)
+            if not np.iscomplexobj(widths):          # complex widths are rejected below, like the reference
+                widths = widths.astype(float)
             self.widths = np.tile(widths, D) if widths.size == 1 else widths.copy()
             self.base_widths = self.widths.copy()
         self.widths[np.isinf(self.widths)] = 10

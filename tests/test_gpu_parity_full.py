@@ -173,7 +173,8 @@ def test_design_batch_both_branches(eng, golden_r2):
 
 # ---------------------------------------------------------------- low-noise branch
 def _cond_rows(spec, hyp, X, mult):
-    """cond_2 of the matrix the low-noise branch factors, K + sn2_mult * sn2 * I (:2432)."""
+    """cond_2 of the matrix that is factored: K + sn2_mult * sn2 * I in the low-noise branch (:2432), the
+    same matrix divided by sn2 * sn2_mult in the high-noise one (:2416) -- constant noise in these cases."""
     out = []
     for h, m in zip(hyp, mult):
         K = orc.cov_compute(spec, h[:spec.cov_n], X)

@@ -319,3 +319,35 @@ def test_rng_rewind_paths(h, monkeypatch):
         assert ss._rewind._raw == (not force_public)
         res = ss.sample(40, thin=2, burn=30)
         np.testing.assert_array_equal(res["samples"], h["ss.samples"])
+
+
+def test_dimension_limit_is_reported_at_construction():
+    """D > 32 fails with a clear message when the GP is built, not at set_data."""
+    import gpyreg_b200 as g
+    from gpyreg_b200.covariance_functions import SquaredExponential
+    from gpyreg_b200.mean_functions import ZeroMean
+    from gpyreg_b200.noise_functions import GaussianNoise
+    with pytest.raises(ValueError, match="D <= 32"):
+        g.GP(33, SquaredExponential(), ZeroMean(), GaussianNoise(constant_add=True))
+    g.GP(32, SquaredExponential(), ZeroMean(), GaussianNoise(constant_add=True))
+
+
+def test_gp_copies_and_pickles_without_device_state():
+    """copy.deepcopy / pickle of a GP (PyVBMC does both) drop the device handles and keep the rest."""
+    import copy
+    import pickle
+    import gpyreg_b200 as g
+    from gpyreg_b200.covariance_functions import Matern
+    from gpyreg_b200.mean_functions import ConstantMean
+    from gpyreg_b200.noise_functions import GaussianNoise
+    gp = g.GP(2, Matern(3), ConstantMean(), GaussianNoise(constant_add=True))
+    gp.X, gp.y = np.zeros((4, 2)), np.zeros((4, 1))
+    gp.update(hyp=np.arange(10.0).reshape(2, 5), compute_posterior=False)
+    gp.temporary_data["k"] = 1
+    for other in (copy.deepcopy(gp), pickle.loads(pickle.dumps(gp))):
+        assert other._engine is None and other._post_batch is None and other._token is not gp._token
+        assert other.X is not gp.X and np.array_equal(other.X, gp.X)
+        assert np.array_equal(other.get_hyperparameters(as_array=True), gp.get_hyperparameters(as_array=True))
+        assert other.temporary_data == {"k": 1} and isinstance(other.covariance, Matern) and other.covariance.degree == 3
+    p = copy.deepcopy(gp.posteriors)[1]
+    assert np.array_equal(p.hyp, gp.posteriors[1].hyp) and p.alpha is None and p._batch is None
