@@ -25,6 +25,9 @@ using namespace gpb;
 // context
 // ---------------------------------------------------------------------------------
 struct Bufs {              // device storage for `cap` batch slots
+  // tensor maps of the four operand arrays [0 Abuf, 1 Wbuf, 2 Dbuf, 3 DTbuf] x [box of 132 / 68 rows]
+  CUtensorMap tm[4][2];
+  bool tm_ok = false;
   int cap = 0;
   bool has_w = false;
   bool cap_is_max = false;   // cap is limited by device memory, not by the request
@@ -35,6 +38,8 @@ struct Bufs {              // device storage for `cap` batch slots
          *dnlz = nullptr, *gpart = nullptr;
   SlotP* sp = nullptr;
   int *fail = nullptr, *sel = nullptr, *sel2 = nullptr, *sel3 = nullptr, *sel4 = nullptr;
+  double* prep_min = nullptr;        // prep_kernel scratch (per-CTA partial results)
+  int *prep_nan = nullptr, *prep_ticket = nullptr;
   long long smat() const { return (long long)Np * Np; }
 };
 
@@ -46,6 +51,17 @@ struct gpb_ctx {
   // block does not touch runs on `aux` while the main stream factors that block
   cudaStream_t aux = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // Lanes: a batch of 2..MAX_LANES matrices (the speculative proposals of a slice-sampling move)
+  // is factored one matrix per lane, each lane with its own main/aux stream pair, so one matrix's
+  // diagonal-tile kernel (one CTA, the serial part) overlaps the other matrices' tile GEMMs
+  // instead of all matrices marching through the dependent chain in lock step.
+  static constexpr int MAX_LANES = 4;
+  struct Lane {
+    cudaStream_t main = nullptr, aux = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, done = nullptr;
+  } lane[MAX_LANES];
+  cudaEvent_t ev_lanes = nullptr;
+  int lanes = MAX_LANES;     // env GPB_LANES: largest batch factored one matrix per lane (0/1 = off)
   int trtri = 2;             // env GPB_TRTRI: 2 recursive halving (default; as fast as the recurrence for large
                              // batches, 4-5x faster for one matrix), 0 column recurrence, 1 recursive up to trtri_max
   int trtri_max = 8;         // env GPB_TRTRI_MAX
@@ -62,8 +78,9 @@ struct gpb_ctx {
   double *dX = nullptr, *dy = nullptr, *ds2 = nullptr;
   size_t ws_limit = 0;
   int gemm_bn = 64;          // 64: two CTAs per SM (default); 128: one (env GPB_GEMM_BN)
-  int loader = 2;            // 0: cp.async (LDGSTS); 1: TMA bulk copies + mbarriers; 2: TMA for launches that
-                             // fill the GPU, cp.async for small ones (env GPB_LOADER=cpasync|tma|auto)
+  int loader = 4;            // 0 cp.async (LDGSTS) | 1 TMA bulk copies + mbarriers | 2 bulk for launches that fill the
+                             // GPU, cp.async for small ones | 3 tensor-map TMA | 4 (default) tensor-map TMA for launches
+                             // that fill the GPU, cp.async for small ones (env GPB_LOADER=cpasync|tma|auto_bulk|tensor|auto)
   int outer_block = 4;       // tile columns per outer block of the two-level Cholesky (env GPB_OUTER_BLOCK)
   long long* diag_dbg = nullptr;   // env GPB_DIAG_DBG: phase clock stamps of the diagonal kernel
   Bufs ws;
@@ -88,6 +105,7 @@ struct gpb_ctx {
   // live posterior batches created from this context: they hold a pointer back to it, so
   // gpb_destroy releases the ones the caller has not freed (their handles die with the context)
   std::vector<gpb_post*> posts;
+  const Bufs* cur = nullptr;     // buffers the tile GEMMs being enqueued work on (tensor maps for LOADER 2)
 };
 
 struct gpb_post {
@@ -158,7 +176,10 @@ static cudaError_t gemm_attr_shape() {
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)gemm_smem<BM_, BN_>());
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(gemm_nt_kernel<Op, BM_, BN_, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  e = cudaFuncSetAttribute(gemm_nt_kernel<Op, BM_, BN_, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)gemm_smem<BM_, BN_>());
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(gemm_nt_kernel<Op, BM_, BN_, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)gemm_smem<BM_, BN_>());
 }
 template <class Op>
@@ -168,12 +189,54 @@ static cudaError_t gemm_attr() {
   return gemm_attr_shape<Op, 128, 64>();
 }
 
+static const TmaOperands& no_tma() {
+  static TmaOperands z{};
+  return z;
+}
+
+// tensor maps of the operands of Op on the buffers the context is working on
 template <class Op, int BM_, int BN_>
-static void launch_shape(gpb_ctx* ctx, const Op& op, dim3 grid, bool tma) {
+static bool tma_operands(const gpb_ctx* ctx, TmaOperands& o) {
+  const Bufs* b = ctx->cur;
+  if (Op::TMA_A < 0 || !b || !b->tm_ok) return false;
+  double* bases[4] = {b->Abuf, b->Wbuf, b->Dbuf, b->DTbuf};
+  const long long lds[4] = {b->Np, b->Np, T, T};
+  constexpr int ia = (BM_ == BM) ? 0 : 1, ib = (BN_ == BN) ? 0 : 1;
+  const int src[4] = {Op::TMA_A, Op::TMA_B, Op::TMA_A0 >= 0 ? Op::TMA_A0 : Op::TMA_A,
+                      Op::TMA_B0 >= 0 ? Op::TMA_B0 : Op::TMA_B};
+  for (int i = 0; i < 4; ++i)
+    if (!bases[src[i]]) return false;
+  o.a = b->tm[src[0]][ia];
+  o.b = b->tm[src[1]][ib];
+  o.a0 = b->tm[src[2]][ia];
+  o.b0 = b->tm[src[3]][ib];
+  for (int i = 0; i < 4; ++i) { o.base[i] = bases[src[i]]; o.ld[i] = lds[src[i]]; }
+  return true;
+}
+
+// loader: 0 cp.async, 1 TMA bulk copies, 2 tensor-map TMA (falls back to 1 where the op has no maps)
+template <class Op, int BM_, int BN_>
+static void launch_shape(gpb_ctx* ctx, const Op& op, dim3 grid, int loader) {
   grid.x *= (BM / BM_) * (BN / BN_);
-  if (tma) gemm_nt_kernel<Op, BM_, BN_, 1><<<grid, GEMM_THREADS, gemm_smem<BM_, BN_>(), ctx->stream>>>(op);
-  else gemm_nt_kernel<Op, BM_, BN_, 0><<<grid, GEMM_THREADS, gemm_smem<BM_, BN_>(), ctx->stream>>>(op);
+  TmaOperands tmo;
+  if (loader == 2 && !tma_operands<Op, BM_, BN_>(ctx, tmo)) loader = 1;
+  if (loader == 2) gemm_nt_kernel<Op, BM_, BN_, 2><<<grid, GEMM_THREADS, gemm_smem<BM_, BN_>(), ctx->stream>>>(op, tmo);
+  else if (loader == 1) gemm_nt_kernel<Op, BM_, BN_, 1><<<grid, GEMM_THREADS, gemm_smem<BM_, BN_>(), ctx->stream>>>(op, no_tma());
+  else gemm_nt_kernel<Op, BM_, BN_, 0><<<grid, GEMM_THREADS, gemm_smem<BM_, BN_>(), ctx->stream>>>(op, no_tma());
   LAUNCHED(ctx);
+}
+
+// ctx->loader: 0 cp.async | 1 bulk | 2 auto: bulk for launches that fill the GPU | 3 tensor maps | 4 auto with
+// tensor maps (default).  TMA wins when the launch fills the machine (>= 2 CTAs per SM); a lone CTA on an SM
+// hides latency better with per-thread cp.async (measured: B=1 triangular inverse)
+static int pick_loader(const gpb_ctx* ctx, long long ctas) {
+  switch (ctx->loader) {
+    case 0: return 0;
+    case 1: return 1;
+    case 3: return 2;
+    case 2: return ctas >= 2 * 148 ? 1 : 0;
+    default: return ctas >= 2 * 148 ? 2 : 0;
+  }
 }
 
 // grid.x counts logical 128x128 tiles; the split shapes launch two CTAs per tile.
@@ -181,21 +244,19 @@ template <class Op>
 static void launch_gemm(gpb_ctx* ctx, const Op& op, dim3 grid) {
   if (Op::SLOT_MAJOR) grid = dim3(grid.y, grid.x);      // slot in x, tile in y (see gemm.cuh)
   const bool two = ctx->gemm_bn != 128;
-  // TMA bulk copies win when the launch fills the machine (>= 2 CTAs per SM); a lone CTA on an
-  // SM hides latency better with per-thread cp.async (measured: B=1 triangular inverse)
   const long long ctas = (long long)grid.x * grid.y * grid.z * (two ? 2 : 1);
-  const bool tma = ctx->loader == 1 || (ctx->loader == 2 && ctas >= 2 * 148);
-  if (two) launch_shape<Op, 128, 64>(ctx, op, grid, tma);
-  else launch_shape<Op, 128, 128>(ctx, op, grid, tma);
+  const int loader = pick_loader(ctx, ctas);
+  if (two) launch_shape<Op, 128, 64>(ctx, op, grid, loader);
+  else launch_shape<Op, 128, 128>(ctx, op, grid, loader);
 }
 
 // the in-place potrf panel: row halves (64x128) keep it race-free with two CTAs per SM
 static void launch_panel(gpb_ctx* ctx, const OpPanel& op, dim3 grid) {
   const bool two = ctx->gemm_bn != 128;
   const long long ctas = (long long)grid.x * grid.y * (two ? 2 : 1);
-  const bool tma = ctx->loader == 1 || (ctx->loader == 2 && ctas >= 2 * 148);
-  if (two) launch_shape<OpPanel, 64, 128>(ctx, op, grid, tma);
-  else launch_shape<OpPanel, 128, 128>(ctx, op, grid, tma);
+  const int loader = pick_loader(ctx, ctas);
+  if (two) launch_shape<OpPanel, 64, 128>(ctx, op, grid, loader);
+  else launch_shape<OpPanel, 128, 128>(ctx, op, grid, loader);
 }
 
 constexpr int COV_SMEM_MAX = (2 * MAXD * T + 2 * T + 8 * (MAXD + 2) + 8 * T) * 8;
@@ -281,6 +342,20 @@ extern "C" int gpb_create(int device, gpb_ctx** out) {
     delete ctx;
     return GPB_ECUDA;
   }
+  for (auto& ln : ctx->lane) {
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ln.main, cudaStreamNonBlocking, prio_hi);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ln.aux, cudaStreamNonBlocking, prio_lo);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ln.ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ln.ev_join, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming);
+  }
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_lanes, cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    g_create_err = std::string("lane streams/events: ") + cudaGetErrorString(e);
+    delete ctx;
+    return GPB_ECUDA;
+  }
+  if (const char* ln = getenv("GPB_LANES")) ctx->lanes = std::min(atoi(ln), (int)gpb_ctx::MAX_LANES);
   if (const char* la = getenv("GPB_LOOKAHEAD")) ctx->lookahead = atoi(la);
   if (const char* tr = getenv("GPB_TRTRI")) ctx->trtri = atoi(tr);
   if (const char* tm = getenv("GPB_TRTRI_MAX")) ctx->trtri_max = atoi(tm);
@@ -289,7 +364,8 @@ extern "C" int gpb_create(int device, gpb_ctx** out) {
   if (const char* lo = getenv("GPB_LA_OB")) ctx->la_ob = std::max(0, atoi(lo));
   if (const char* bn = getenv("GPB_GEMM_BN")) ctx->gemm_bn = (atoi(bn) == 128) ? 128 : 64;
   if (const char* ld = getenv("GPB_LOADER"))
-    ctx->loader = (strcmp(ld, "tma") == 0) ? 1 : (strcmp(ld, "cpasync") == 0 ? 0 : 2);
+    ctx->loader = (strcmp(ld, "tma") == 0) ? 1 : (strcmp(ld, "cpasync") == 0) ? 0 : (strcmp(ld, "auto_bulk") == 0) ? 2
+                : (strcmp(ld, "tensor") == 0) ? 3 : 4;
   if (const char* ob = getenv("GPB_OUTER_BLOCK")) ctx->outer_block = std::max(1, atoi(ob));
   if (const char* nc = getenv("GPB_NLZ_CACHE")) ctx->cache_enabled = atoi(nc) != 0;
   if (getenv("GPB_DIAG_DBG")) cudaMalloc(&ctx->diag_dbg, 40 * sizeof(long long));
@@ -316,7 +392,9 @@ static void free_bufs(Bufs& b) {
   }
   if (b.sp) cudaFree(b.sp);
   b.sp = nullptr;
-  int** ip[] = {&b.fail, &b.sel, &b.sel2, &b.sel3, &b.sel4};
+  if (b.prep_min) cudaFree(b.prep_min);
+  b.prep_min = nullptr;
+  int** ip[] = {&b.fail, &b.sel, &b.sel2, &b.sel3, &b.sel4, &b.prep_nan, &b.prep_ticket};
   for (auto p : ip) {
     if (*p) cudaFree(*p);
     *p = nullptr;
@@ -344,6 +422,14 @@ extern "C" void gpb_destroy(gpb_ctx* ctx) {
     if (ev) cudaEventDestroy(ev);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  for (auto& ln : ctx->lane) {
+    if (ln.ev_fork) cudaEventDestroy(ln.ev_fork);
+    if (ln.ev_join) cudaEventDestroy(ln.ev_join);
+    if (ln.done) cudaEventDestroy(ln.done);
+    if (ln.aux) cudaStreamDestroy(ln.aux);
+    if (ln.main) cudaStreamDestroy(ln.main);
+  }
+  if (ctx->ev_lanes) cudaEventDestroy(ctx->ev_lanes);
   if (ctx->aux) cudaStreamDestroy(ctx->aux);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
@@ -460,6 +546,50 @@ static size_t per_slot_bytes(int Np, int D, int P, int cov_n, bool with_w) {
   return b;
 }
 
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static TensorMapEncodeFn tensor_map_encoder() {
+  static TensorMapEncodeFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (TensorMapEncodeFn)p;
+  }();
+  return fn;
+}
+
+// 2-D map of a column-major array of `rows` x `cols` doubles; box = box_rows x BK
+static bool encode_map(CUtensorMap* m, double* base, long long rows, long long cols, int box_rows) {
+  TensorMapEncodeFn enc = tensor_map_encoder();
+  if (!enc || !base) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)rows, (cuuint64_t)cols};
+  const cuuint64_t strides[1] = {(cuuint64_t)rows * sizeof(double)};
+  const cuuint32_t box[2] = {(cuuint32_t)box_rows, (cuuint32_t)BK};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static void build_tensor_maps(Bufs& b) {
+  b.tm_ok = false;
+  double* bases[4] = {b.Abuf, b.Wbuf, b.Dbuf, b.DTbuf};
+  const long long rows[4] = {b.Np, b.Np, T, T};
+  const long long cols[4] = {(long long)b.cap * b.Np, (long long)b.cap * b.Np, (long long)b.cap * b.Nt * T,
+                             (long long)b.cap * b.Nt * T};
+  bool ok = true;
+  for (int i = 0; i < 4; ++i) {
+    if (!bases[i]) { memset(b.tm[i], 0, sizeof b.tm[i]); continue; }      // no W: its ops are not launched
+    ok = ok && encode_map(&b.tm[i][0], bases[i], rows[i], cols[i], BM + 4);
+    ok = ok && encode_map(&b.tm[i][1], bases[i], rows[i], cols[i], BM / 2 + 4);
+  }
+  b.tm_ok = ok;
+}
+
 static int alloc_bufs(gpb_ctx* ctx, Bufs& b, int cap, bool with_w, int Np, int D, const Model& md) {
   free_bufs(b);
   b.Np = Np;
@@ -501,8 +631,14 @@ static int alloc_bufs(gpb_ctx* ctx, Bufs& b, int cap, bool with_w, int Np, int D
   CK(cudaMalloc(&b.sel2, sizeof(int) * cap));
   CK(cudaMalloc(&b.sel3, sizeof(int) * cap));
   CK(cudaMalloc(&b.sel4, sizeof(int) * cap));
+  CK(cudaMalloc(&b.prep_min, sizeof(double) * PREP_MAX_CTAS * cap));
+  CK(cudaMalloc(&b.prep_nan, sizeof(int) * PREP_MAX_CTAS * cap));
+  CK(cudaMalloc(&b.prep_ticket, sizeof(int) * cap));
+  CK(cudaMemsetAsync(b.prep_ticket, 0, sizeof(int) * cap, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
   b.cap = cap;
   b.has_w = with_w;
+  build_tensor_maps(b);
   return GPB_OK;
 }
 
@@ -547,6 +683,13 @@ static BatchBufs batch_bufs(const Bufs& b, const int* sel, long long N) {
   return bb;
 }
 
+// CTAs per slot of prep_kernel: enough to spread one matrix's points, fewer when the batch already fills the GPU
+static dim3 prep_grid(int nsel, int Np) {
+  const int want = (Np + PREP_THREADS - 1) / PREP_THREADS;
+  const int per = std::max(1, std::min(std::min(want, (int)PREP_MAX_CTAS), (2 * 148 + nsel - 1) / nsel));
+  return dim3((unsigned)nsel, (unsigned)per);
+}
+
 template <int KIND>
 static void launch_build(gpb_ctx* ctx, const BuildArgs& a, dim3 grid, size_t smem) {
   build_kernel<KIND><<<grid, 256, smem, ctx->stream>>>(a);
@@ -570,7 +713,10 @@ static void run_prep_build(gpb_ctx* ctx, Bufs& b, const Model& md, long long N, 
   pa.resid = b.resid;
   pa.sn2v = b.sn2v;
   pa.sp = b.sp;
-  prep_kernel<<<nsel, PREP_THREADS, 0, ctx->stream>>>(pa);
+  pa.part_min = b.prep_min;
+  pa.part_nan = b.prep_nan;
+  pa.ticket = b.prep_ticket;
+  prep_kernel<<<prep_grid(nsel, b.Np), PREP_THREADS, 0, ctx->stream>>>(pa);
   LAUNCHED(ctx);
 
   BuildArgs ba;
@@ -605,6 +751,7 @@ static void run_prep_build(gpb_ctx* ctx, Bufs& b, const Model& md, long long N, 
 static void run_potrf(gpb_ctx* ctx, Bufs& b, long long N, const int* sel, int nsel, bool write_w,
                       bool with_rhs = true) {
   NvtxRange nv("gpb:K2 potrf");
+  ctx->cur = &b;
   const BatchBufs bb = batch_bufs(b, sel, N);
   const bool look0 = ctx->lookahead == 2 || (ctx->lookahead == 1 && nsel <= 8);
   const int Nt = b.Nt;                                 // outer block = OB tile columns
@@ -722,6 +869,7 @@ static void run_bwd(gpb_ctx* ctx, Bufs& b, const int* sel, int nsel) {
 static void run_inverse(gpb_ctx* ctx, Bufs& b, long long N, const int* sel, int nsel, bool dual,
                         bool syrk2) {
   NvtxRange nv("gpb:K2 inverse (trtri + W^T W)");
+  ctx->cur = &b;
   const BatchBufs bb = batch_bufs(b, sel, N);
   const int Nt = b.Nt;
   const bool recursive = ctx->trtri == 2 || (ctx->trtri == 1 && nsel <= ctx->trtri_max);
@@ -816,8 +964,26 @@ static int factor_with_retry(gpb_ctx* ctx, Bufs& b, const Model& md, long long N
   std::vector<int> cur = slots;
   for (int attempt = 0; attempt < 10; ++attempt) {
     NvtxRange nv(attempt == 0 ? "gpb:factor" : "gpb:factor (jitter retry)");
-    run_prep_build(ctx, b, md, N, sel, nsel);
-    run_potrf(ctx, b, N, sel, nsel, write_w);
+    if (nsel >= 2 && nsel <= ctx->lanes) {
+      // one matrix per lane (see gpb_ctx::lane); every matrix sees exactly the launches of a
+      // one-matrix call, so the results are bit-identical to any other batching
+      cudaStream_t s0 = ctx->stream, a0 = ctx->aux;
+      cudaEvent_t f0 = ctx->ev_fork, j0 = ctx->ev_join;
+      CK(cudaEventRecord(ctx->ev_lanes, s0));
+      for (int m = 0; m < nsel; ++m) {
+        gpb_ctx::Lane& ln = ctx->lane[m];
+        CK(cudaStreamWaitEvent(ln.main, ctx->ev_lanes, 0));
+        ctx->stream = ln.main; ctx->aux = ln.aux; ctx->ev_fork = ln.ev_fork; ctx->ev_join = ln.ev_join;
+        run_prep_build(ctx, b, md, N, sel + m, 1);
+        run_potrf(ctx, b, N, sel + m, 1, write_w);
+        cudaEventRecord(ln.done, ln.main);
+      }
+      ctx->stream = s0; ctx->aux = a0; ctx->ev_fork = f0; ctx->ev_join = j0;
+      for (int m = 0; m < nsel; ++m) CK(cudaStreamWaitEvent(s0, ctx->lane[m].done, 0));
+    } else {
+      run_prep_build(ctx, b, md, N, sel, nsel);
+      run_potrf(ctx, b, N, sel, nsel, write_w);
+    }
     CK(cudaGetLastError());                    // a refused launch must not pass for a result
     CK(cudaMemcpyAsync(failh.data(), b.fail, sizeof(int) * maxslot, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -865,7 +1031,10 @@ static void run_solve_only(gpb_ctx* ctx, Bufs& b, const Model& md, long long N, 
   pa.resid = b.resid;
   pa.sn2v = b.sn2v;
   pa.sp = b.sp;
-  prep_kernel<<<nsel, PREP_THREADS, 0, ctx->stream>>>(pa);
+  pa.part_min = b.prep_min;
+  pa.part_nan = b.prep_nan;
+  pa.ticket = b.prep_ticket;
+  prep_kernel<<<prep_grid(nsel, b.Np), PREP_THREADS, 0, ctx->stream>>>(pa);
   LAUNCHED(ctx);
   copy_sel_kernel<<<dim3((unsigned)((b.Np + 255) / 256), (unsigned)nsel), 256, 0, ctx->stream>>>(
       b.bvec, b.resid, sel, b.Np);
@@ -877,8 +1046,8 @@ static void run_solve_only(gpb_ctx* ctx, Bufs& b, const Model& md, long long N, 
   for (int k = 0; k + 1 < b.Nt; ++k) {
     dim3 grid((unsigned)(b.Nt - k - 1), (unsigned)nsel);
     const OpFwdZ op{bb, k, b.zvec, b.bvec, fsel};
-    if (ctx->gemm_bn != 128) launch_shape<OpFwdZ, 64, 128>(ctx, op, grid, false);
-    else launch_shape<OpFwdZ, 128, 128>(ctx, op, grid, false);
+    if (ctx->gemm_bn != 128) launch_shape<OpFwdZ, 64, 128>(ctx, op, grid, 0);
+    else launch_shape<OpFwdZ, 128, 128>(ctx, op, grid, 0);
   }
   DiagSolveArgs da;
   da.Dbuf = b.Dbuf;
@@ -1747,7 +1916,8 @@ extern "C" int gpb_predict_full(gpb_ctx* ctx, const gpb_post* cpost, const doubl
     }
     if (p.lchol) {
       // V^T = Bt W^T (Mcp x Np), then C2 = V^T V (Mcp x Mcp)
-      launch_gemm(ctx, OpPlain{Bt, b.Wbuf + (size_t)s * b.smat(), Vt, Mcp, Np, Mcp, Np},
+      // (W is lower triangular; the upper tiles of Wbuf hold W^T: restrict k per column tile)
+      launch_gemm(ctx, OpPlain{Bt, b.Wbuf + (size_t)s * b.smat(), Vt, Mcp, Np, Mcp, Np, /*tri=*/1},
                   dim3((unsigned)(Mcp / T), (unsigned)Nt));
       launch_gemm(ctx, OpPlain{Vt, Vt, C2, Mcp, Mcp, Mcp, Np}, dim3((unsigned)(Mcp / T), (unsigned)(Mcp / T)));
     } else {

@@ -76,12 +76,20 @@ struct PrepArgs {
   double* resid;        // [nslots][Np]     y - m
   double* sn2v;         // [nslots][Np]
   SlotP* sp;            // [nslots]
+  double* part_min;     // [nslots][PREP_MAX_CTAS] scratch: per-CTA min of sn2
+  int* part_nan;        // [nslots][PREP_MAX_CTAS]
+  int* ticket;          // [nslots] zero between launches
 };
 
-constexpr int PREP_THREADS = 1024;     // one CTA per slot: wide, the per-point work is FP64 divisions
+// Several CTAs per slot (a lone CTA over N*D divisions was 80 us of a 3.6 ms one-matrix nlZ): each
+// handles a strided share of the points and leaves its partial min / NaN flag in scratch; the CTA
+// that finishes last (per-slot ticket) combines them -- min is order-independent -- and writes SlotP.
+constexpr int PREP_THREADS = 256;
+constexpr int PREP_MAX_CTAS = 32;
 __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(PrepArgs a) {
   __shared__ double sh[PREP_THREADS];
   __shared__ int shnan[PREP_THREADS];
+  __shared__ int s_last;
   const int slot = a.sel[blockIdx.x];
   const Model& md = a.md;
   const int D = md.D, N = a.N, Np = a.Np;
@@ -93,7 +101,7 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(PrepArgs a) {
   double* resid = a.resid + (long long)slot * Np;
   double* sn2v = a.sn2v + (long long)slot * Np;
 
-  // exp() of the length scales and of the mean's scales once per slot, not once per point
+  // exp() of the length scales and of the mean's scales once per CTA, not once per point
   __shared__ double ells[MAXD], oms[MAXD];
   if (threadIdx.x < D) {
     ells[threadIdx.x] = exp(h[md.ard ? threadIdx.x : 0]);
@@ -102,7 +110,7 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(PrepArgs a) {
   __syncthreads();
   double vmin = INFINITY;
   int anynan = 0;
-  for (int i = threadIdx.x; i < Np; i += blockDim.x) {
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < Np; i += gridDim.y * blockDim.x) {
     if (i < N) {
       const double* x = a.X + (long long)i * D;
       for (int k = 0; k < D; ++k)
@@ -139,17 +147,33 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(PrepArgs a) {
     }
     __syncthreads();
   }
+  double* pmin = a.part_min + (long long)slot * PREP_MAX_CTAS;
+  int* pnan = a.part_nan + (long long)slot * PREP_MAX_CTAS;
   if (threadIdx.x == 0) {
-    SlotP p;
-    p.sf2 = exp(2 * h[nl]);
-    p.rq_a = (md.cov_kind == 2) ? exp(h[nl + 1]) : 1.0;
-    p.sn2_min = shnan[0] ? NAN : sh[0];          // np.min propagates NaN
-    p.mult = a.mult[slot];
-    p.lchol = (p.sn2_min >= 1e-6) ? 1 : 0;       // gaussian_process.py:2404
-    p.sl = p.lchol ? p.sn2_min * p.mult : 1.0;   // :2422 / :2439
-    p.pad = 0;
-    a.sp[slot] = p;
+    pmin[blockIdx.y] = sh[0];
+    pnan[blockIdx.y] = shnan[0];
+    __threadfence();
+    s_last = (atomicAdd(a.ticket + slot, 1) == (int)gridDim.y - 1);
   }
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0) return;
+  __threadfence();
+  double mn = INFINITY;
+  int nan = 0;
+  for (int c = 0; c < (int)gridDim.y; ++c) {
+    mn = fmin(mn, ((volatile double*)pmin)[c]);
+    nan |= ((volatile int*)pnan)[c];
+  }
+  a.ticket[slot] = 0;                            // ready for the next launch
+  SlotP p;
+  p.sf2 = exp(2 * h[nl]);
+  p.rq_a = (md.cov_kind == 2) ? exp(h[nl + 1]) : 1.0;
+  p.sn2_min = nan ? NAN : mn;                    // np.min propagates NaN
+  p.mult = a.mult[slot];
+  p.lchol = (p.sn2_min >= 1e-6) ? 1 : 0;         // gaussian_process.py:2404
+  p.sl = p.lchol ? p.sn2_min * p.mult : 1.0;     // :2422 / :2439
+  p.pad = 0;
+  a.sp[slot] = p;
 }
 
 // ---------------------------------------------------------------------------------

@@ -12,11 +12,25 @@
 // Shared tiles are stored [k][m] with a pitch of 132 doubles so the DMMA fragment
 // loads (lane -> (m = lane/4, k = lane%4)) hit 16 distinct 8-byte banks per half warp.
 #pragma once
+#include <cuda.h>      // CUtensorMap (the encode function is fetched at run time: no libcuda link)
+
 #include "common.cuh"
 
 namespace gpb {
 
 constexpr int BM = 128, BN = 128, BK = 16, NSTAGE = 4;
+
+// Tensor maps of the operand sources of one launch (LOADER = 2).  Every operand of the factorisation
+// lives in one of four per-batch buffers, each of which is ONE 2-D column-major array: Abuf / Wbuf
+// are Np rows x (slots*Np) columns, Dbuf / DTbuf are T rows x (slots*Nt*T) columns.  A stage of an
+// operand is then a single box of (tile rows + 4) x BK elements: the 4 extra rows are the padding
+// of the shared-memory pitch (132 / 68 doubles, conflict-free DMMA fragment loads), fetched as
+// real neighbouring rows or zero-filled beyond the array -- nothing reads them.
+struct alignas(64) TmaOperands {
+  CUtensorMap a, b, a0, b0;          // A, B and their alternate sources for k in [0, T)
+  const double* base[4];             // base address of the array behind each map
+  long long ld[4];                   // its leading dimension (elements)
+};
 constexpr int PITCH = BM + 4;
 constexpr int GEMM_THREADS = 256;
 
@@ -82,6 +96,17 @@ __device__ __forceinline__ void bulk_g2s(double* dst, const double* src, unsigne
                : "memory");
 }
 
+// one box of a 2-D tensor map -> shared memory (cp.async.bulk.tensor -> SASS UTMALDG), completion
+// counted on `bar`; c0 = coordinate along the contiguous dimension (row), c1 = column
+__device__ __forceinline__ void tma_box_2d(double* dst, const CUtensorMap* map, int c0, int c1,
+                                           unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+
 // MODE bits
 constexpr int GM_BETA = 1;     // C enters the product: accumulators start at (beta/alpha) * C
 constexpr int GM_STORE = 2;    // normal store
@@ -108,10 +133,12 @@ constexpr size_t gemm_smem() {
 // (LDGSTS).  LOADER = 1: warp 0 issues TMA bulk copies (cp.async.bulk, one lane per tile
 // column: 32 copies per stage) and the ring is synchronised with full/empty mbarriers, so the
 // other 7 warps issue no load instructions at all.
+// LOADER = 2: like 1, but a stage is TWO tensor-map TMA copies (one box per operand) issued by one
+// elected lane, instead of 32 bulk copies issued by 32 lanes.
 template <class Op, int BM_, int BN_, int LOADER>
 __global__ void __launch_bounds__(GEMM_THREADS, ((BM_ * BN_ < BM * BN) ? 2 : 1))
-gemm_nt_kernel(const __grid_constant__ Op op) {
-  extern __shared__ __align__(16) double gsm[];
+gemm_nt_kernel(const __grid_constant__ Op op, const __grid_constant__ TmaOperands tm) {
+  extern __shared__ __align__(128) double gsm[];
   constexpr int NSN = BN / BN_, NSM = BM / BM_;       // column / row parts per logical tile
   constexpr int PA = BM_ + 4, PB = BN_ + 4;           // pitches: fragment loads hit 16 distinct banks
   constexpr int MW = BM_ / 32, NW = 8 / MW;           // warp grid
@@ -200,7 +227,29 @@ gemm_nt_kernel(const __grid_constant__ Op op) {
     else
       bulk_g2s(Bs + (stage * BK + kk) * PB, Bp + (long long)(k0 + kk) * lb, BN_ * 8, full_bar + stage);
   };
-  if (LOADER == 1) {
+  // LOADER 2: box coordinates of the operands in their arrays (once per CTA)
+  int rA = 0, cA = 0, rB = 0, cB = 0, rA0 = 0, cA0 = 0, rB0 = 0, cB0 = 0;
+  if (LOADER == 2 && warp == 0 && lane == 0) {
+    long long o = t.A - tm.base[0];
+    rA = (int)(o % tm.ld[0]); cA = (int)(o / tm.ld[0]);
+    o = t.B - tm.base[1];
+    rB = (int)(o % tm.ld[1]); cB = (int)(o / tm.ld[1]);
+    if (t.A0) { o = t.A0 - tm.base[2]; rA0 = (int)(o % tm.ld[2]); cA0 = (int)(o / tm.ld[2]); }
+    if (t.B0) { o = t.B0 - tm.base[3]; rB0 = (int)(o % tm.ld[3]); cB0 = (int)(o / tm.ld[3]); }
+  }
+  constexpr unsigned STAGE_BYTES_BOX = BK * (PA + PB) * sizeof(double);
+  // called by warp 0; only lane 0 acts
+  auto tma_stage = [&](int kt, int stage) {
+    if (lane != 0) return;
+    const int k0 = kt * BK;
+    const bool alt = (k0 < T);
+    mbar_expect_tx(full_bar + stage, STAGE_BYTES_BOX);
+    if (alt && t.A0) tma_box_2d(As + stage * BK * PA, &tm.a0, rA0, cA0 + k0, full_bar + stage);
+    else tma_box_2d(As + stage * BK * PA, &tm.a, rA, cA + k0, full_bar + stage);
+    if (alt && t.B0) tma_box_2d(Bs + stage * BK * PB, &tm.b0, rB0, cB0 + k0, full_bar + stage);
+    else tma_box_2d(Bs + stage * BK * PB, &tm.b, rB, cB + k0, full_bar + stage);
+  };
+  if (LOADER >= 1) {
     if (tid == 0) {
 #pragma unroll
       for (int s = 0; s < NSTAGE; ++s) {
@@ -213,7 +262,7 @@ gemm_nt_kernel(const __grid_constant__ Op op) {
     __syncthreads();
     if (warp == 0) {
       for (int s = 0; s < NSTAGE - 1; ++s)
-        if (s < KT) bulk_stage(s, s);
+        if (s < KT) { if (LOADER == 2) tma_stage(s, s); else bulk_stage(s, s); }
     }
   } else {
 #pragma unroll
@@ -245,13 +294,13 @@ gemm_nt_kernel(const __grid_constant__ Op op) {
   }
 
   for (int kt = 0; kt < KT; ++kt) {
-    if (LOADER == 1) {
+    if (LOADER >= 1) {
       const int nk = kt + NSTAGE - 1;
       if (warp == 0 && nk < KT) {
         const int ns = nk % NSTAGE;
         // the slot was last read in iteration kt-1: wait until all 8 warps have released it
         if (nk >= NSTAGE) mbar_wait(empty_bar + ns, ((nk / NSTAGE) - 1) & 1);
-        bulk_stage(nk, ns);
+        if (LOADER == 2) tma_stage(nk, ns); else bulk_stage(nk, ns);
       }
       mbar_wait(full_bar + (kt % NSTAGE), (kt / NSTAGE) & 1);
     } else {
@@ -277,7 +326,7 @@ gemm_nt_kernel(const __grid_constant__ Op op) {
           for (int ni = 0; ni < NI; ++ni) dmma8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
       }
     }
-    if (LOADER == 1) {                       // this warp is done with the slot
+    if (LOADER >= 1) {                       // this warp is done with the slot
       __syncwarp();
       if (lane == 0) mbar_arrive(empty_bar + (kt % NSTAGE));
     }
@@ -458,6 +507,7 @@ __device__ __forceinline__ GemmTile empty_tile() {
 
 // debug / benchmark: plain C = alpha A B^T + beta C
 struct OpGeneric {
+  static constexpr int TMA_A = -1, TMA_B = -1, TMA_A0 = -1, TMA_B0 = -1;   // operand arrays: 0 Abuf, 1 Wbuf, 2 Dbuf, 3 DTbuf
   static constexpr bool SLOT_MAJOR = false;
   static constexpr int MODE = GM_BETA | GM_STORE;
   const double* A; const double* B; double* C;
@@ -474,19 +524,23 @@ struct OpGeneric {
   }
 };
 
-// plain product C = A B^T (C is not read)
+// plain product C = A B^T (C is not read).  tri = 1: B is LOWER TRIANGULAR in tile storage whose upper
+// tiles hold something else (Wbuf keeps W^T there): column tile `by` of the product only runs over
+// k < (by+1)*T, the tiles on and below B's diagonal.
 struct OpPlain {
+  static constexpr int TMA_A = -1, TMA_B = -1, TMA_A0 = -1, TMA_B0 = -1;   // operand arrays: 0 Abuf, 1 Wbuf, 2 Dbuf, 3 DTbuf
   static constexpr bool SLOT_MAJOR = false;
   static constexpr int MODE = GM_STORE;
   const double* A; const double* B; double* C;
   long long lda, ldb, ldc;
   int K;
+  int tri = 0;
   __device__ GemmTile resolve(int bx, int by) const {
     GemmTile t = empty_tile();
     t.A = A + (long long)bx * BM; t.lda = lda;
     t.B = B + (long long)by * BN; t.ldb = ldb;
     t.C = C + (long long)bx * BM + (long long)by * BN * ldc; t.ldc = ldc;
-    t.K = K;
+    t.K = tri ? min((by + 1) * BN, K) : K;
     return t;
   }
 };
@@ -494,6 +548,7 @@ struct OpPlain {
 // potrf panel, step k:  L_ik = A_ik * D_k^T  (i > k), in place; with a right-hand side the
 // forward-substitution update  b_i -= L_ik z_k  rides in the epilogue
 struct OpPanel {
+  static constexpr int TMA_A = 0, TMA_B = 2, TMA_A0 = -1, TMA_B0 = -1;   // operand arrays: 0 Abuf, 1 Wbuf, 2 Dbuf, 3 DTbuf
   static constexpr bool SLOT_MAJOR = false;
   static constexpr int MODE = GM_STORE | GM_ROWDOT;
   BatchBufs b; int k;
@@ -520,6 +575,7 @@ struct OpPanel {
 // as the fused panel (K = 0: the accumulators are just the stored L_ik), so replaying the solve
 // for a new right-hand side is bit-identical to a full evaluation
 struct OpFwd {
+  static constexpr int TMA_A = -1, TMA_B = -1, TMA_A0 = -1, TMA_B0 = -1;   // operand arrays: 0 Abuf, 1 Wbuf, 2 Dbuf, 3 DTbuf
   static constexpr bool SLOT_MAJOR = false;
   static constexpr int MODE = GM_BETA | GM_ROWDOT;
   BatchBufs b; int k;
@@ -545,6 +601,7 @@ struct OpFwd {
 // solve-only replay, one launch per block column: like OpFwd, but every CTA first computes
 // z_k = D_k b_k itself (the CTAs of the first tile row also store it)
 struct OpFwdZ {
+  static constexpr int TMA_A = -1, TMA_B = -1, TMA_A0 = -1, TMA_B0 = -1;   // operand arrays: 0 Abuf, 1 Wbuf, 2 Dbuf, 3 DTbuf
   static constexpr bool SLOT_MAJOR = false;
   static constexpr int MODE = GM_BETA | GM_ROWDOT | GM_ZSOLVE;
   BatchBufs b; int k;
@@ -576,6 +633,7 @@ struct OpFwdZ {
 // factored, ONE update with K = kw*128 brings the rest of the matrix up to date, so most of the
 // flops run with a long K loop and each C tile is read and written once per outer block.
 struct OpSyrk {
+  static constexpr int TMA_A = 0, TMA_B = 0, TMA_A0 = -1, TMA_B0 = -1;   // operand arrays: 0 Abuf, 1 Wbuf, 2 Dbuf, 3 DTbuf
   static constexpr bool SLOT_MAJOR = false;
   static constexpr int MODE = GM_BETA | GM_STORE;
   BatchBufs b; int k0, kw, jlo, jhi;
@@ -604,6 +662,7 @@ struct OpSyrk {
 
 // H pass:  upper tile (j,i) <- (L_ij * D_j)^T  for every i > j
 struct OpHpass {
+  static constexpr int TMA_A = 0, TMA_B = 3, TMA_A0 = -1, TMA_B0 = -1;   // operand arrays: 0 Abuf, 1 Wbuf, 2 Dbuf, 3 DTbuf
   static constexpr bool SLOT_MAJOR = false;
   static constexpr int MODE = GM_STORET;
   BatchBufs b;
@@ -624,6 +683,7 @@ struct OpHpass {
 
 // triangular inverse, block column j (descending):  W_ij = - sum_{k=j+1..i} W_ik H_kj
 struct OpWrec {
+  static constexpr int TMA_A = 1, TMA_B = 0, TMA_A0 = -1, TMA_B0 = -1;   // operand arrays: 0 Abuf, 1 Wbuf, 2 Dbuf, 3 DTbuf
   static constexpr bool SLOT_MAJOR = true;
   static constexpr int MODE = GM_STORE | GM_STORET;
   BatchBufs b; int j; int dual;
@@ -653,6 +713,7 @@ struct OpWrec {
 //   pass 2 (OpRecW): W_21 = -W_22 X into the lower tiles of Wbuf and transposed into the upper
 // Tile order: longest K first; bx = (kidx * P + pair) * s + other.
 struct OpRecX {
+  static constexpr int TMA_A = 0, TMA_B = 1, TMA_A0 = -1, TMA_B0 = 3;   // operand arrays: 0 Abuf, 1 Wbuf, 2 Dbuf, 3 DTbuf
   static constexpr bool SLOT_MAJOR = true;
   static constexpr int MODE = GM_STORET;
   BatchBufs b; int s, P;
@@ -675,6 +736,7 @@ struct OpRecX {
 };
 
 struct OpRecW {
+  static constexpr int TMA_A = 1, TMA_B = 0, TMA_A0 = -1, TMA_B0 = -1;   // operand arrays: 0 Abuf, 1 Wbuf, 2 Dbuf, 3 DTbuf
   static constexpr bool SLOT_MAJOR = true;
   static constexpr int MODE = GM_STORE | GM_STORET;
   BatchBufs b; int s, P;
@@ -698,6 +760,7 @@ struct OpRecW {
 
 // K^-1 = W^T W (lower tiles a >= c) written over the lower triangle of Abuf
 struct OpSyrk2 {
+  static constexpr int TMA_A = 1, TMA_B = 1, TMA_A0 = 3, TMA_B0 = 3;   // operand arrays: 0 Abuf, 1 Wbuf, 2 Dbuf, 3 DTbuf
   static constexpr bool SLOT_MAJOR = true;
   static constexpr int MODE = GM_STORE;
   BatchBufs b;
@@ -724,6 +787,7 @@ struct OpSyrk2 {
 // predictive variance:  part[nt][j] = sum_{m in tile nt} ( sum_k Bt(j,k) Wm(m,k) )^2   (L_chol)
 //                    or sum_{m in tile nt} ( sum_k Bt(j,k) X(m,k) ) * Bt(j,m)            (low noise)
 struct OpPred {
+  static constexpr int TMA_A = -1, TMA_B = -1, TMA_A0 = -1, TMA_B0 = -1;   // operand arrays: 0 Abuf, 1 Wbuf, 2 Dbuf, 3 DTbuf
   static constexpr bool SLOT_MAJOR = false;
   static constexpr int MODE = GM_REDUCE;
   // blockIdx.z = posterior sample within the group handled by this launch

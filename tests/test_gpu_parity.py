@@ -455,6 +455,7 @@ _TOGGLE_CACHE = {}
     ({"GPB_OUTER_BLOCK": "3", "GPB_LOOKAHEAD": "0"}, True),
     ({"GPB_LOADER": "tma"}, True),                         # TMA bulk-copy loader for every launch
     ({"GPB_LOADER": "cpasync"}, True),
+    ({"GPB_LANES": "0"}, True),                            # small batches in lock step instead of one matrix per lane
     ({"GPB_TRTRI": "0"}, False),                           # column-recurrence triangular inverse
     ({"GPB_GEMM_BN": "128"}, False),                       # one CTA per tile: other reduction shapes
 ])
@@ -469,7 +470,7 @@ def test_schedule_toggles_do_not_change_results(env, exact):
 
     def run(extra):
         e = dict(os.environ)
-        for k in ("GPB_LOOKAHEAD", "GPB_LA_OB", "GPB_OUTER_BLOCK", "GPB_LOADER", "GPB_TRTRI", "GPB_GEMM_BN"):
+        for k in ("GPB_LOOKAHEAD", "GPB_LA_OB", "GPB_OUTER_BLOCK", "GPB_LOADER", "GPB_TRTRI", "GPB_GEMM_BN", "GPB_LANES"):
             e.pop(k, None)
         e.update(extra)
         root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
