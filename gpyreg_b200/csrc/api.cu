@@ -61,7 +61,9 @@ struct gpb_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, done = nullptr;
   } lane[MAX_LANES];
   cudaEvent_t ev_lanes = nullptr;
-  int lanes = MAX_LANES;     // env GPB_LANES: largest batch factored one matrix per lane (0/1 = off)
+  int lanes = 0;             // env GPB_LANES: largest batch factored one matrix per lane.  Default off: measured on
+                             // B200 (profiles/r02_small_batch_latency.txt) it is neutral at N=5000 (the lock-step batch already
+                             // runs all diagonal tiles side by side) and 15-25 % slower at N <= 2000 (twice the launches)
   int trtri = 2;             // env GPB_TRTRI: 2 recursive halving (default; as fast as the recurrence for large
                              // batches, 4-5x faster for one matrix), 0 column recurrence, 1 recursive up to trtri_max
   int trtri_max = 8;         // env GPB_TRTRI_MAX
@@ -189,6 +191,8 @@ static cudaError_t gemm_attr() {
   return gemm_attr_shape<Op, 128, 64>();
 }
 
+static bool encode_map(CUtensorMap* m, double* base, long long rows, long long cols, int box_rows);
+
 static const TmaOperands& no_tma() {
   static TmaOperands z{};
   return z;
@@ -211,15 +215,17 @@ static bool tma_operands(const gpb_ctx* ctx, TmaOperands& o) {
   o.a0 = b->tm[src[2]][ia];
   o.b0 = b->tm[src[3]][ib];
   for (int i = 0; i < 4; ++i) { o.base[i] = bases[src[i]]; o.ld[i] = lds[src[i]]; }
+  o.b_alt = o.b; o.base[4] = o.base[1]; o.ld[4] = o.ld[1];
   return true;
 }
 
 // loader: 0 cp.async, 1 TMA bulk copies, 2 tensor-map TMA (falls back to 1 where the op has no maps)
 template <class Op, int BM_, int BN_>
-static void launch_shape(gpb_ctx* ctx, const Op& op, dim3 grid, int loader) {
+static void launch_shape(gpb_ctx* ctx, const Op& op, dim3 grid, int loader, const TmaOperands* custom = nullptr) {
   grid.x *= (BM / BM_) * (BN / BN_);
   TmaOperands tmo;
-  if (loader == 2 && !tma_operands<Op, BM_, BN_>(ctx, tmo)) loader = 1;
+  if (loader == 2 && custom) tmo = *custom;
+  else if (loader == 2 && !tma_operands<Op, BM_, BN_>(ctx, tmo)) loader = 1;
   if (loader == 2) gemm_nt_kernel<Op, BM_, BN_, 2><<<grid, GEMM_THREADS, gemm_smem<BM_, BN_>(), ctx->stream>>>(op, tmo);
   else if (loader == 1) gemm_nt_kernel<Op, BM_, BN_, 1><<<grid, GEMM_THREADS, gemm_smem<BM_, BN_>(), ctx->stream>>>(op, no_tma());
   else gemm_nt_kernel<Op, BM_, BN_, 0><<<grid, GEMM_THREADS, gemm_smem<BM_, BN_>(), ctx->stream>>>(op, no_tma());
@@ -241,13 +247,29 @@ static int pick_loader(const gpb_ctx* ctx, long long ctas) {
 
 // grid.x counts logical 128x128 tiles; the split shapes launch two CTAs per tile.
 template <class Op>
-static void launch_gemm(gpb_ctx* ctx, const Op& op, dim3 grid) {
+static void launch_gemm(gpb_ctx* ctx, const Op& op, dim3 grid, const TmaOperands* custom = nullptr) {
   if (Op::SLOT_MAJOR) grid = dim3(grid.y, grid.x);      // slot in x, tile in y (see gemm.cuh)
   const bool two = ctx->gemm_bn != 128;
   const long long ctas = (long long)grid.x * grid.y * grid.z * (two ? 2 : 1);
   const int loader = pick_loader(ctx, ctas);
-  if (two) launch_shape<Op, 128, 64>(ctx, op, grid, loader);
-  else launch_shape<Op, 128, 128>(ctx, op, grid, loader);
+  if (two) launch_shape<Op, 128, 64>(ctx, op, grid, loader, custom);
+  else launch_shape<Op, 128, 128>(ctx, op, grid, loader, custom);
+}
+
+// predict / quad: A = the Ks scratch (Mcp rows x (samples*Np) columns), B = W or the explicit inverse
+// of the posterior batch, chosen per sample
+static bool pred_tma(const gpb_ctx* ctx, const Bufs& b, const double* Bt, int Mcp, long long cols, TmaOperands& o) {
+  if (!b.tm_ok || !b.Wbuf) return false;
+  const int ib = (ctx->gemm_bn != 128) ? 1 : 0;
+  if (!encode_map(&o.a, const_cast<double*>(Bt), Mcp, cols, BM + 4)) return false;
+  o.a0 = o.a;
+  o.b = b.tm[1][ib];
+  o.b0 = o.b;
+  o.b_alt = b.tm[0][ib];
+  o.base[0] = o.base[2] = Bt; o.ld[0] = o.ld[2] = Mcp;
+  o.base[1] = o.base[3] = b.Wbuf; o.ld[1] = o.ld[3] = b.Np;
+  o.base[4] = b.Abuf; o.ld[4] = b.Np;
+  return true;
 }
 
 // the in-place potrf panel: row halves (64x128) keep it race-free with two CTAs per SM
@@ -1534,7 +1556,11 @@ static int predict_impl(gpb_ctx* ctx, const gpb_post* cpost, const double* Xs, c
       op.ns = ns;
       op.N = (int)post->N;
       op.mc = mc;
-      launch_gemm(ctx, op, dim3((unsigned)(Mcp / T), (unsigned)Nt, (unsigned)g));
+      {
+        TmaOperands tmo;
+        const bool have = pred_tma(ctx, b, ctx->pBt, Mcp, (long long)g * Np, tmo);
+        launch_gemm(ctx, op, dim3((unsigned)(Mcp / T), (unsigned)Nt, (unsigned)g), have ? &tmo : nullptr);
+      }
       FinishArgs fa;
       fa.md = md;
       fa.Nt = Nt;
@@ -1688,7 +1714,9 @@ extern "C" int gpb_quad(gpb_ctx* ctx, const gpb_post* cpost, const double* mu, c
         op.ns = ns;
         op.N = (int)post->N;
         op.mc = mc;
-        launch_gemm(ctx, op, dim3((unsigned)(Mcp / T), (unsigned)Nt, (unsigned)g));
+        TmaOperands tmo;
+        const bool have = pred_tma(ctx, b, ctx->pBt, Mcp, (long long)g * Np, tmo);
+        launch_gemm(ctx, op, dim3((unsigned)(Mcp / T), (unsigned)Nt, (unsigned)g), have ? &tmo : nullptr);
       }
       QuadFinishArgs fa;
       fa.md = md;

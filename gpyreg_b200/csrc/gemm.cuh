@@ -28,8 +28,9 @@ constexpr int BM = 128, BN = 128, BK = 16, NSTAGE = 4;
 // real neighbouring rows or zero-filled beyond the array -- nothing reads them.
 struct alignas(64) TmaOperands {
   CUtensorMap a, b, a0, b0;          // A, B and their alternate sources for k in [0, T)
-  const double* base[4];             // base address of the array behind each map
-  long long ld[4];                   // its leading dimension (elements)
+  CUtensorMap b_alt;                 // second B array, chosen per tile (predict: W or the explicit inverse)
+  const double* base[5];             // base address of the array behind each map
+  long long ld[5];                   // its leading dimension (elements)
 };
 constexpr int PITCH = BM + 4;
 constexpr int GEMM_THREADS = 256;
@@ -46,6 +47,7 @@ struct GemmTile {
   const double* vdot; double* vdst;   // GM_ROWDOT: vdst[m] -= sum_n C(m,n) * vdot[n]
   const double* zD; const double* zb; double* zout; int znact;   // GM_ZSOLVE: D_k, b_k, where z_k goes (or null)
   int K;
+  int b_alt;                          // LOADER 2: B lives in the launch's alternate B array (TmaOperands::b_alt)
   int mvalid, nvalid;                 // rows / columns of the 128x128 tile that hold data (rest is padding)
   double alpha, cscale;               // result = alpha * (cscale * C + A B^T); cscale = beta / alpha
   bool valid;
@@ -232,8 +234,9 @@ gemm_nt_kernel(const __grid_constant__ Op op, const __grid_constant__ TmaOperand
   if (LOADER == 2 && warp == 0 && lane == 0) {
     long long o = t.A - tm.base[0];
     rA = (int)(o % tm.ld[0]); cA = (int)(o / tm.ld[0]);
-    o = t.B - tm.base[1];
-    rB = (int)(o % tm.ld[1]); cB = (int)(o / tm.ld[1]);
+    const int ib = t.b_alt ? 4 : 1;
+    o = t.B - tm.base[ib];
+    rB = (int)(o % tm.ld[ib]); cB = (int)(o / tm.ld[ib]);
     if (t.A0) { o = t.A0 - tm.base[2]; rA0 = (int)(o % tm.ld[2]); cA0 = (int)(o / tm.ld[2]); }
     if (t.B0) { o = t.B0 - tm.base[3]; rB0 = (int)(o % tm.ld[3]); cB0 = (int)(o / tm.ld[3]); }
   }
@@ -247,7 +250,7 @@ gemm_nt_kernel(const __grid_constant__ Op op, const __grid_constant__ TmaOperand
     if (alt && t.A0) tma_box_2d(As + stage * BK * PA, &tm.a0, rA0, cA0 + k0, full_bar + stage);
     else tma_box_2d(As + stage * BK * PA, &tm.a, rA, cA + k0, full_bar + stage);
     if (alt && t.B0) tma_box_2d(Bs + stage * BK * PB, &tm.b0, rB0, cB0 + k0, full_bar + stage);
-    else tma_box_2d(Bs + stage * BK * PB, &tm.b, rB, cB + k0, full_bar + stage);
+    else tma_box_2d(Bs + stage * BK * PB, t.b_alt ? &tm.b_alt : &tm.b, rB, cB + k0, full_bar + stage);
   };
   if (LOADER >= 1) {
     if (tid == 0) {
@@ -497,6 +500,7 @@ __device__ __forceinline__ GemmTile empty_tile() {
   t.zout = nullptr;
   t.znact = 0;
   t.K = 0;
+  t.b_alt = 0;
   t.mvalid = BM;
   t.nvalid = BN;
   t.alpha = 1.0;
@@ -806,6 +810,7 @@ struct OpPred {
     const int jt = bx, nt = (int)gridDim.y - 1 - by;   // longest K first
     t.A = bt + (long long)jt * BM; t.lda = ldbt;
     t.B = (tri ? Wbuf : Abuf) + z * smat + (long long)nt * BN; t.ldb = Np;
+    t.b_alt = tri ? 0 : 1;
     const int n16 = (N + BK - 1) / BK * BK;
     t.K = tri ? min((nt + 1) * T, n16) : n16;
     t.mvalid = mc - jt * BM;

@@ -455,7 +455,9 @@ _TOGGLE_CACHE = {}
     ({"GPB_OUTER_BLOCK": "3", "GPB_LOOKAHEAD": "0"}, True),
     ({"GPB_LOADER": "tma"}, True),                         # TMA bulk-copy loader for every launch
     ({"GPB_LOADER": "cpasync"}, True),
-    ({"GPB_LANES": "0"}, True),                            # small batches in lock step instead of one matrix per lane
+    ({"GPB_LOADER": "tensor"}, True),                      # tensor-map TMA for every launch
+    ({"GPB_LOADER": "auto_bulk"}, True),                   # round-1 default
+    ({"GPB_LANES": "4"}, True),                            # small batches one matrix per lane instead of in lock step
     ({"GPB_TRTRI": "0"}, False),                           # column-recurrence triangular inverse
     ({"GPB_GEMM_BN": "128"}, False),                       # one CTA per tile: other reduction shapes
 ])
