@@ -8,6 +8,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <type_traits>
+#include <utility>
 #include <vector>
 
 #include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges cost nothing unless a profiler is attached
@@ -108,6 +110,8 @@ struct gpb_ctx {
   // gpb_destroy releases the ones the caller has not freed (their handles die with the context)
   std::vector<gpb_post*> posts;
   const Bufs* cur = nullptr;     // buffers the tile GEMMs being enqueued work on (tensor maps for LOADER 2)
+  bool quarter_tiles = true;     // env GPB_QUARTER=0: no 64x64 CTAs for small trailing updates
+  bool pdl = true;               // env GPB_PDL=0: ordinary launches for the tile GEMMs and the diagonal kernel
 };
 
 struct gpb_post {
@@ -193,6 +197,26 @@ static cudaError_t gemm_attr() {
 
 static bool encode_map(CUtensorMap* m, double* base, long long rows, long long cols, int box_rows);
 
+// Launch on ctx->stream; with ctx->pdl the kernel carries the programmatic-stream-serialization
+// attribute (common.cuh: pdl_wait / pdl_launch), so its launch latency and prologue overlap the tail
+// of its predecessor.  Only kernels that call pdl_wait() before their first dependent access may come
+// through here.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_chain(gpb_ctx* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = ctx->pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 static const TmaOperands& no_tma() {
   static TmaOperands z{};
   return z;
@@ -226,9 +250,9 @@ static void launch_shape(gpb_ctx* ctx, const Op& op, dim3 grid, int loader, cons
   TmaOperands tmo;
   if (loader == 2 && custom) tmo = *custom;
   else if (loader == 2 && !tma_operands<Op, BM_, BN_>(ctx, tmo)) loader = 1;
-  if (loader == 2) gemm_nt_kernel<Op, BM_, BN_, 2><<<grid, GEMM_THREADS, gemm_smem<BM_, BN_>(), ctx->stream>>>(op, tmo);
-  else if (loader == 1) gemm_nt_kernel<Op, BM_, BN_, 1><<<grid, GEMM_THREADS, gemm_smem<BM_, BN_>(), ctx->stream>>>(op, no_tma());
-  else gemm_nt_kernel<Op, BM_, BN_, 0><<<grid, GEMM_THREADS, gemm_smem<BM_, BN_>(), ctx->stream>>>(op, no_tma());
+  if (loader == 2) launch_chain(ctx, gemm_nt_kernel<Op, BM_, BN_, 2>, grid, dim3(GEMM_THREADS), gemm_smem<BM_, BN_>(), op, tmo);
+  else if (loader == 1) launch_chain(ctx, gemm_nt_kernel<Op, BM_, BN_, 1>, grid, dim3(GEMM_THREADS), gemm_smem<BM_, BN_>(), op, no_tma());
+  else launch_chain(ctx, gemm_nt_kernel<Op, BM_, BN_, 0>, grid, dim3(GEMM_THREADS), gemm_smem<BM_, BN_>(), op, no_tma());
   LAUNCHED(ctx);
 }
 
@@ -252,6 +276,14 @@ static void launch_gemm(gpb_ctx* ctx, const Op& op, dim3 grid, const TmaOperands
   const bool two = ctx->gemm_bn != 128;
   const long long ctas = (long long)grid.x * grid.y * grid.z * (two ? 2 : 1);
   const int loader = pick_loader(ctx, ctas);
+  if constexpr (std::is_same<Op, OpSyrk>::value) {
+    // a trailing update of a few tiles sits on the dependent chain of a small batch (diag -> panel ->
+    // next column -> diag): quarter tiles put four CTAs on each, same arithmetic per element
+    if (two && ctx->quarter_tiles && ctas * 2 <= 2 * 148) {
+      launch_shape<Op, 64, 64>(ctx, op, grid, loader, custom);
+      return;
+    }
+  }
   if (two) launch_shape<Op, 128, 64>(ctx, op, grid, loader, custom);
   else launch_shape<Op, 128, 128>(ctx, op, grid, loader, custom);
 }
@@ -312,6 +344,7 @@ static int init_attrs(gpb_ctx* ctx) {
   CK((gemm_attr_shape<OpFwd, 128, 128>()));
   CK((gemm_attr_shape<OpPanel, 64, 128>()));
   CK(gemm_attr<OpSyrk>());
+  CK((gemm_attr_shape<OpSyrk, 64, 64>()));
   CK(gemm_attr<OpHpass>());
   CK(gemm_attr<OpWrec>());
   CK(gemm_attr<OpRecX>());
@@ -378,6 +411,8 @@ extern "C" int gpb_create(int device, gpb_ctx** out) {
     return GPB_ECUDA;
   }
   if (const char* ln = getenv("GPB_LANES")) ctx->lanes = std::min(atoi(ln), (int)gpb_ctx::MAX_LANES);
+  if (const char* pd = getenv("GPB_PDL")) ctx->pdl = atoi(pd) != 0;
+  if (const char* qt = getenv("GPB_QUARTER")) ctx->quarter_tiles = atoi(qt) != 0;
   if (const char* la = getenv("GPB_LOOKAHEAD")) ctx->lookahead = atoi(la);
   if (const char* tr = getenv("GPB_TRTRI")) ctx->trtri = atoi(tr);
   if (const char* tm = getenv("GPB_TRTRI_MAX")) ctx->trtri_max = atoi(tm);
@@ -812,7 +847,7 @@ static void run_potrf(gpb_ctx* ctx, Bufs& b, long long N, const int* sel, int ns
     da.logdet = b.logdet;
     da.fail = b.fail;
     da.dbg = (k == 0) ? ctx->diag_dbg : nullptr;
-    diag_kernel<<<nsel, 256, DIAG_SMEM, ctx->stream>>>(da);
+    launch_chain(ctx, diag_kernel, dim3((unsigned)nsel), dim3(256), DIAG_SMEM, da);
     LAUNCHED(ctx);
     const int n = Nt - k - 1;
     if (n <= 0) break;

@@ -221,6 +221,14 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
   const int nact = min(T, a.N - k * T);         // rows/cols holding data (the rest is identity)
   const int nact8 = (nact + 7) & ~7;
 
+  for (int e = tid; e < 4 * SB * IVP; e += 256) {     // diagonal-block inverses start as identity
+    const int within = e % (SB * IVP);
+    Iv[e] = (within / IVP == within % IVP) ? 1.0 : 0.0;
+  }
+  if (tid == 0) s_failed = 0;
+  // the tile (and the running right-hand side) are written by the preceding trailing update
+  pdl_wait();
+  pdl_launch();
   // lower triangle of the tile with 16-byte async copies (all in flight at once); nothing reads
   // the strict upper triangle of S before it is overwritten
   for (int e = tid; e < T * T / 2; e += 256) {
@@ -230,14 +238,9 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(A + (long long)c * Np + r2));
   }
   asm volatile("cp.async.commit_group;\n" ::);
-  for (int e = tid; e < 4 * SB * IVP; e += 256) {     // diagonal-block inverses start as identity
-    const int within = e % (SB * IVP);
-    Iv[e] = (within / IVP == within % IVP) ? 1.0 : 0.0;
-  }
   if (tid < T) {
     bsh[tid] = a.bvec ? a.bvec[(long long)slot * Np + k * T + tid] : 0.0;
   }
-  if (tid == 0) s_failed = 0;
   asm volatile("cp.async.wait_group 0;\n" ::);
   __syncthreads();
   STAMP();

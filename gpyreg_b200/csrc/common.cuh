@@ -43,6 +43,16 @@ __host__ __device__ inline int mean_count(int kind, int D) {
   return kind == 0 ? 0 : (kind == 1 ? 1 : 1 + 2 * D);
 }
 
+// Programmatic dependent launch (PDL).  A kernel launched with the programmatic-stream-serialization
+// attribute may start while its predecessor in the stream is still running; it must call pdl_wait()
+// before it touches anything the predecessor writes (the wait returns when the predecessor grid has
+// completed and its writes are visible).  pdl_launch() lets the NEXT kernel in the stream begin its
+// launch; every kernel here calls it only after its own pdl_wait(), so whatever a successor does
+// before ITS wait runs with everything up to the predecessor's predecessor complete.  Both are
+// no-ops for a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // lower-triangle tile enumeration: idx -> (i, j), i >= j, idx = i(i+1)/2 + j
 __device__ inline void tri_decode(int idx, int& i, int& j) {
   int r = (int)((sqrt(8.0 * (double)idx + 1.0) - 1.0) * 0.5);

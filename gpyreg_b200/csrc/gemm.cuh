@@ -229,6 +229,10 @@ gemm_nt_kernel(const __grid_constant__ Op op, const __grid_constant__ TmaOperand
     else
       bulk_g2s(Bs + (stage * BK + kk) * PB, Bp + (long long)(k0 + kk) * lb, BN_ * 8, full_bar + stage);
   };
+  // everything above is index arithmetic on launch parameters and host-written slot lists: from here
+  // on the kernel reads what its predecessors in the stream wrote
+  pdl_wait();
+  pdl_launch();
   // LOADER 2: box coordinates of the operands in their arrays (once per CTA)
   int rA = 0, cA = 0, rB = 0, cB = 0, rA0 = 0, cA0 = 0, rB0 = 0, cB0 = 0;
   if (LOADER == 2 && warp == 0 && lane == 0) {

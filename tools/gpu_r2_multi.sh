@@ -11,13 +11,13 @@ for B in 64 1024; do
   timeout 600 $TR bench.py --gpus $N --scaling strong --batch $B --no-cpu-baseline > gpurun_out/bench_cfg3_strong_b${B}_$N.json 2> gpurun_out/bench_cfg3_strong_b${B}_$N.err; echo "exit $?"
   python -c "
 import json
-d=json.load(open('gpurun_out/bench_cfg3_strong_b${B}_$N.json'))
+d=json.loads(open('gpurun_out/bench_cfg3_strong_b${B}_$N.json').read().strip().splitlines()[-1])
 print(d['value'], d['unit'], 'ms/step', d['ms_per_step'], 'e2e', d['e2e']['value'])"
 done
 echo "== weak scaling cfg3 x$N"
 timeout 600 $TR bench.py --gpus $N --no-cpu-baseline > gpurun_out/bench_cfg3_weak_$N.json 2> gpurun_out/bench_cfg3_weak_$N.err; echo "exit $?"; python -c "
 import json
-d=json.load(open('gpurun_out/bench_cfg3_weak_$N.json'))
+d=json.loads(open('gpurun_out/bench_cfg3_weak_$N.json').read().strip().splitlines()[-1])
 print(d['value'], d['unit'], 'ms/step', d['ms_per_step'], 'e2e', d['e2e']['value'])"
 if [ "$2" == "full" ]; then
   echo "== cfg5 as stated: 256 samples, 2^24 test points over $N GPUs"
