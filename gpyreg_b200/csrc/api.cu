@@ -217,11 +217,6 @@ static cudaError_t launch_chain(gpb_ctx* ctx, void (*kernel)(KArgs...), dim3 gri
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
-static const TmaOperands& no_tma() {
-  static TmaOperands z{};
-  return z;
-}
-
 // tensor maps of the operands of Op on the buffers the context is working on
 template <class Op, int BM_, int BN_>
 static bool tma_operands(const gpb_ctx* ctx, TmaOperands& o) {
@@ -251,8 +246,8 @@ static void launch_shape(gpb_ctx* ctx, const Op& op, dim3 grid, int loader, cons
   if (loader == 2 && custom) tmo = *custom;
   else if (loader == 2 && !tma_operands<Op, BM_, BN_>(ctx, tmo)) loader = 1;
   if (loader == 2) launch_chain(ctx, gemm_nt_kernel<Op, BM_, BN_, 2>, grid, dim3(GEMM_THREADS), gemm_smem<BM_, BN_>(), op, tmo);
-  else if (loader == 1) launch_chain(ctx, gemm_nt_kernel<Op, BM_, BN_, 1>, grid, dim3(GEMM_THREADS), gemm_smem<BM_, BN_>(), op, no_tma());
-  else launch_chain(ctx, gemm_nt_kernel<Op, BM_, BN_, 0>, grid, dim3(GEMM_THREADS), gemm_smem<BM_, BN_>(), op, no_tma());
+  else if (loader == 1) launch_chain(ctx, gemm_nt_kernel<Op, BM_, BN_, 1>, grid, dim3(GEMM_THREADS), gemm_smem<BM_, BN_>(), op, NoTma{});
+  else launch_chain(ctx, gemm_nt_kernel<Op, BM_, BN_, 0>, grid, dim3(GEMM_THREADS), gemm_smem<BM_, BN_>(), op, NoTma{});
   LAUNCHED(ctx);
 }
 

@@ -98,6 +98,11 @@ __device__ __forceinline__ void bulk_g2s(double* dst, const double* src, unsigne
                : "memory");
 }
 
+// kernel parameter carrying the maps: only the LOADER = 2 instantiation pays for the 700 bytes
+struct NoTma {};
+template <int LOADER> struct TmaParam { typedef NoTma type; };
+template <> struct TmaParam<2> { typedef TmaOperands type; };
+
 // one box of a 2-D tensor map -> shared memory (cp.async.bulk.tensor -> SASS UTMALDG), completion
 // counted on `bar`; c0 = coordinate along the contiguous dimension (row), c1 = column
 __device__ __forceinline__ void tma_box_2d(double* dst, const CUtensorMap* map, int c0, int c1,
@@ -139,7 +144,7 @@ constexpr size_t gemm_smem() {
 // elected lane, instead of 32 bulk copies issued by 32 lanes.
 template <class Op, int BM_, int BN_, int LOADER>
 __global__ void __launch_bounds__(GEMM_THREADS, ((BM_ * BN_ < BM * BN) ? 2 : 1))
-gemm_nt_kernel(const __grid_constant__ Op op, const __grid_constant__ TmaOperands tm) {
+gemm_nt_kernel(const __grid_constant__ Op op, const __grid_constant__ typename TmaParam<LOADER>::type tm) {
   extern __shared__ __align__(128) double gsm[];
   constexpr int NSN = BN / BN_, NSM = BM / BM_;       // column / row parts per logical tile
   constexpr int PA = BM_ + 4, PB = BN_ + 4;           // pitches: fragment loads hit 16 distinct banks
@@ -235,26 +240,30 @@ gemm_nt_kernel(const __grid_constant__ Op op, const __grid_constant__ TmaOperand
   pdl_launch();
   // LOADER 2: box coordinates of the operands in their arrays (once per CTA)
   int rA = 0, cA = 0, rB = 0, cB = 0, rA0 = 0, cA0 = 0, rB0 = 0, cB0 = 0;
-  if (LOADER == 2 && warp == 0 && lane == 0) {
-    long long o = t.A - tm.base[0];
-    rA = (int)(o % tm.ld[0]); cA = (int)(o / tm.ld[0]);
-    const int ib = t.b_alt ? 4 : 1;
-    o = t.B - tm.base[ib];
-    rB = (int)(o % tm.ld[ib]); cB = (int)(o / tm.ld[ib]);
-    if (t.A0) { o = t.A0 - tm.base[2]; rA0 = (int)(o % tm.ld[2]); cA0 = (int)(o / tm.ld[2]); }
-    if (t.B0) { o = t.B0 - tm.base[3]; rB0 = (int)(o % tm.ld[3]); cB0 = (int)(o / tm.ld[3]); }
+  if constexpr (LOADER == 2) {
+    if (warp == 0 && lane == 0) {
+      long long o = t.A - tm.base[0];
+      rA = (int)(o % tm.ld[0]); cA = (int)(o / tm.ld[0]);
+      const int ib = t.b_alt ? 4 : 1;
+      o = t.B - tm.base[ib];
+      rB = (int)(o % tm.ld[ib]); cB = (int)(o / tm.ld[ib]);
+      if (t.A0) { o = t.A0 - tm.base[2]; rA0 = (int)(o % tm.ld[2]); cA0 = (int)(o / tm.ld[2]); }
+      if (t.B0) { o = t.B0 - tm.base[3]; rB0 = (int)(o % tm.ld[3]); cB0 = (int)(o / tm.ld[3]); }
+    }
   }
   constexpr unsigned STAGE_BYTES_BOX = BK * (PA + PB) * sizeof(double);
   // called by warp 0; only lane 0 acts
   auto tma_stage = [&](int kt, int stage) {
-    if (lane != 0) return;
-    const int k0 = kt * BK;
-    const bool alt = (k0 < T);
-    mbar_expect_tx(full_bar + stage, STAGE_BYTES_BOX);
-    if (alt && t.A0) tma_box_2d(As + stage * BK * PA, &tm.a0, rA0, cA0 + k0, full_bar + stage);
-    else tma_box_2d(As + stage * BK * PA, &tm.a, rA, cA + k0, full_bar + stage);
-    if (alt && t.B0) tma_box_2d(Bs + stage * BK * PB, &tm.b0, rB0, cB0 + k0, full_bar + stage);
-    else tma_box_2d(Bs + stage * BK * PB, t.b_alt ? &tm.b_alt : &tm.b, rB, cB + k0, full_bar + stage);
+    if constexpr (LOADER == 2) {
+      if (lane != 0) return;
+      const int k0 = kt * BK;
+      const bool alt = (k0 < T);
+      mbar_expect_tx(full_bar + stage, STAGE_BYTES_BOX);
+      if (alt && t.A0) tma_box_2d(As + stage * BK * PA, &tm.a0, rA0, cA0 + k0, full_bar + stage);
+      else tma_box_2d(As + stage * BK * PA, &tm.a, rA, cA + k0, full_bar + stage);
+      if (alt && t.B0) tma_box_2d(Bs + stage * BK * PB, &tm.b0, rB0, cB0 + k0, full_bar + stage);
+      else tma_box_2d(Bs + stage * BK * PB, t.b_alt ? &tm.b_alt : &tm.b, rB, cB + k0, full_bar + stage);
+    }
   };
   if (LOADER >= 1) {
     if (tid == 0) {
