@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgpyreg_b200.so")
+# GPYREG_B200_LIB: another build of the library (A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("GPYREG_B200_LIB") or os.path.join(HERE, "libgpyreg_b200.so")
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)

@@ -245,93 +245,123 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
   __syncthreads();
   STAMP();
 
+  // Warp-specialised block loop.  The serial part is the 32x32 block factorisation in warp 0
+  // (factor_block32, ~7.4 k cycles); everything else of a step is DMMA work that only the NEXT
+  // step's panel needs.  So per step p:
+  //   X  warps 0-3: panel rows of block p+1 (one 8-row block each), then the update of the diagonal
+  //      block (p+1, p+1) -- all the next factorisation needs;
+  //   Y  warps 4-7: the panel rows below block p+1;
+  //   warp 0 goes straight on to factor block p+1 while warps 1-7 apply the rest of the trailing
+  //   update (every 16x16 super-block except the three of block (p+1, p+1)).
+  // Named barriers: 1, 2 = warps 0-3 (128 threads); 3 = all panel rows written (warp 0 only
+  // arrives); 4 = end of step.  Every element sees the same operations in the same order as in a
+  // plain sequential sweep.
+  auto bar_sync = [](int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); };
+  auto bar_arrive = [](int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); };
+  auto panel_rows = [&](int c0, const double* Ivp, int mb) {
+    // rows m0..m0+7 below the block: L21 = P * Inv^T   (C(m,n) = sum_k P(m,k) Inv(n,k))
+    const int m0 = c0 + SB + mb * 8;
+    double af[8];
+#pragma unroll
+    for (int k4 = 0; k4 < 8; ++k4) af[k4] = S[(c0 + k4 * 4 + tq) * DP_PITCH + m0 + g];
+    double acc[4][2];
+#pragma unroll
+    for (int n8 = 0; n8 < 4; ++n8) acc[n8][0] = acc[n8][1] = 0.0;
+#pragma unroll
+    for (int k4 = 0; k4 < 8; ++k4) {
+      double bf[4];
+#pragma unroll
+      for (int n8 = 0; n8 < 4; ++n8) bf[n8] = Ivp[(k4 * 4 + tq) * IVP + n8 * 8 + g];
+#pragma unroll
+      for (int n8 = 0; n8 < 4; ++n8) dmma_t(acc[n8][0], acc[n8][1], af[k4], bf[n8]);   // 4 chains
+    }
+#pragma unroll
+    for (int n8 = 0; n8 < 4; ++n8) {
+      S[(c0 + n8 * 8 + 2 * tq) * DP_PITCH + m0 + g] = acc[n8][0];
+      S[(c0 + n8 * 8 + 2 * tq + 1) * DP_PITCH + m0 + g] = acc[n8][1];
+    }
+  };
+  auto update_super = [&](int c0, int mblocks, int idx) {
+    // S -= L21 L21^T on one 16x16 super-block (2x2 DMMA blocks) of the lower triangle: two A and
+    // two B fragments per k-step feed four DMMAs
+    int si, sj;
+    tri_decode(idx, si, sj);
+    const int r0 = c0 + SB + si * 16, q0 = c0 + SB + sj * 16;
+    const bool okr = 2 * si + 1 < mblocks, okq = 2 * sj + 1 < mblocks;   // second half inside the tile
+    const bool diag = si == sj;                                          // block (0,1) is above the diagonal
+    double x00[2], x01[2], x10[2], x11[2];
+    x00[0] = S[(q0 + 2 * tq) * DP_PITCH + r0 + g];
+    x00[1] = S[(q0 + 2 * tq + 1) * DP_PITCH + r0 + g];
+    x10[0] = okr ? S[(q0 + 2 * tq) * DP_PITCH + r0 + 8 + g] : 0.0;
+    x10[1] = okr ? S[(q0 + 2 * tq + 1) * DP_PITCH + r0 + 8 + g] : 0.0;
+    x01[0] = (okq && !diag) ? S[(q0 + 8 + 2 * tq) * DP_PITCH + r0 + g] : 0.0;
+    x01[1] = (okq && !diag) ? S[(q0 + 8 + 2 * tq + 1) * DP_PITCH + r0 + g] : 0.0;
+    x11[0] = (okr && okq) ? S[(q0 + 8 + 2 * tq) * DP_PITCH + r0 + 8 + g] : 0.0;
+    x11[1] = (okr && okq) ? S[(q0 + 8 + 2 * tq + 1) * DP_PITCH + r0 + 8 + g] : 0.0;
+#pragma unroll
+    for (int k4 = 0; k4 < 8; ++k4) {
+      const int col = (c0 + k4 * 4 + tq) * DP_PITCH;
+      const double a0 = -S[col + r0 + g];
+      const double a1 = okr ? -S[col + r0 + 8 + g] : 0.0;
+      const double b0 = S[col + q0 + g];
+      const double b1 = okq ? S[col + q0 + 8 + g] : 0.0;
+      dmma_t(x00[0], x00[1], a0, b0);
+      dmma_t(x10[0], x10[1], a1, b0);
+      dmma_t(x11[0], x11[1], a1, b1);
+      if (!diag) dmma_t(x01[0], x01[1], a0, b1);
+    }
+    S[(q0 + 2 * tq) * DP_PITCH + r0 + g] = x00[0];
+    S[(q0 + 2 * tq + 1) * DP_PITCH + r0 + g] = x00[1];
+    if (okr) {
+      S[(q0 + 2 * tq) * DP_PITCH + r0 + 8 + g] = x10[0];
+      S[(q0 + 2 * tq + 1) * DP_PITCH + r0 + 8 + g] = x10[1];
+    }
+    if (okq && !diag) {
+      S[(q0 + 8 + 2 * tq) * DP_PITCH + r0 + g] = x01[0];
+      S[(q0 + 8 + 2 * tq + 1) * DP_PITCH + r0 + g] = x01[1];
+    }
+    if (okr && okq) {
+      S[(q0 + 8 + 2 * tq) * DP_PITCH + r0 + 8 + g] = x11[0];
+      S[(q0 + 8 + 2 * tq + 1) * DP_PITCH + r0 + 8 + g] = x11[1];
+    }
+  };
+
+  if (warp == 0) {
+    if (factor_block32(S, Iv, Tm, 0, lane)) s_failed = 1;
+  }
+  __syncthreads();
+  STAMP();
   for (int p = 0; p < T / SB; ++p) {
     const int c0 = p * SB;
     if (c0 >= nact) break;
-    double* Ivp = Iv + p * SB * IVP;
-    // ---- 1. diagonal block in registers (warp 0 only: the SM's shuffle unit is shared, so
-    // redundant copies in the other warps would slow this one down): lane r owns row r
-    if (warp == 0) {
-      if (factor_block32(S, Ivp, Tm, c0, lane)) s_failed = 1;
-    }
-    __syncthreads();
-    STAMP();
-    // ---- 2. panel: rows below the block, L21 = P * Inv^T   (C(m,n) = sum_k P(m,k) Inv(n,k))
-    const int mblocks = max(0, (nact8 - c0 - SB) / 8);
-    for (int mb = warp; mb < mblocks; mb += 8) {
-      const int m0 = c0 + SB + mb * 8;
-      double af[8];
-#pragma unroll
-      for (int k4 = 0; k4 < 8; ++k4) af[k4] = S[(c0 + k4 * 4 + tq) * DP_PITCH + m0 + g];
-      double acc[4][2];
-#pragma unroll
-      for (int n8 = 0; n8 < 4; ++n8) acc[n8][0] = acc[n8][1] = 0.0;
-#pragma unroll
-      for (int k4 = 0; k4 < 8; ++k4) {
-        double bf[4];
-#pragma unroll
-        for (int n8 = 0; n8 < 4; ++n8) bf[n8] = Ivp[(k4 * 4 + tq) * IVP + n8 * 8 + g];
-#pragma unroll
-        for (int n8 = 0; n8 < 4; ++n8) dmma_t(acc[n8][0], acc[n8][1], af[k4], bf[n8]);   // 4 chains
-      }
-#pragma unroll
-      for (int n8 = 0; n8 < 4; ++n8) {
-        S[(c0 + n8 * 8 + 2 * tq) * DP_PITCH + m0 + g] = acc[n8][0];
-        S[(c0 + n8 * 8 + 2 * tq + 1) * DP_PITCH + m0 + g] = acc[n8][1];
-      }
-    }
-    __syncthreads();
-    STAMP();
-    // ---- 3. trailing update S -= L21 L21^T of the lower triangle, 16x16 super-blocks (2x2 DMMA
-    // blocks) per warp: two A and two B fragments per k-step feed four DMMAs -- the loop is bound
-    // by shared-memory fragment loads, not by the tensor pipe
+    const double* Ivp = Iv + p * SB * IVP;
+    const int mblocks = max(0, (nact8 - c0 - SB) / 8);   // 8-row blocks below block p
     const int ms = (mblocks + 1) / 2;
-    const int nsup = ms * (ms + 1) / 2;
-    for (int idx = warp; idx < nsup; idx += 8) {
-      int si, sj;
-      tri_decode(idx, si, sj);
-      const int r0 = c0 + SB + si * 16, q0 = c0 + SB + sj * 16;
-      const bool okr = 2 * si + 1 < mblocks, okq = 2 * sj + 1 < mblocks;   // second half inside the tile
-      const bool diag = si == sj;                                          // block (0,1) is above the diagonal
-      double x00[2], x01[2], x10[2], x11[2];
-      x00[0] = S[(q0 + 2 * tq) * DP_PITCH + r0 + g];
-      x00[1] = S[(q0 + 2 * tq + 1) * DP_PITCH + r0 + g];
-      x10[0] = okr ? S[(q0 + 2 * tq) * DP_PITCH + r0 + 8 + g] : 0.0;
-      x10[1] = okr ? S[(q0 + 2 * tq + 1) * DP_PITCH + r0 + 8 + g] : 0.0;
-      x01[0] = (okq && !diag) ? S[(q0 + 8 + 2 * tq) * DP_PITCH + r0 + g] : 0.0;
-      x01[1] = (okq && !diag) ? S[(q0 + 8 + 2 * tq + 1) * DP_PITCH + r0 + g] : 0.0;
-      x11[0] = (okr && okq) ? S[(q0 + 8 + 2 * tq) * DP_PITCH + r0 + 8 + g] : 0.0;
-      x11[1] = (okr && okq) ? S[(q0 + 8 + 2 * tq + 1) * DP_PITCH + r0 + 8 + g] : 0.0;
-#pragma unroll
-      for (int k4 = 0; k4 < 8; ++k4) {
-        const int col = (c0 + k4 * 4 + tq) * DP_PITCH;
-        const double a0 = -S[col + r0 + g];
-        const double a1 = okr ? -S[col + r0 + 8 + g] : 0.0;
-        const double b0 = S[col + q0 + g];
-        const double b1 = okq ? S[col + q0 + 8 + g] : 0.0;
-        dmma_t(x00[0], x00[1], a0, b0);
-        dmma_t(x10[0], x10[1], a1, b0);
-        dmma_t(x11[0], x11[1], a1, b1);
-        if (!diag) dmma_t(x01[0], x01[1], a0, b1);
-      }
-      S[(q0 + 2 * tq) * DP_PITCH + r0 + g] = x00[0];
-      S[(q0 + 2 * tq + 1) * DP_PITCH + r0 + g] = x00[1];
-      if (okr) {
-        S[(q0 + 2 * tq) * DP_PITCH + r0 + 8 + g] = x10[0];
-        S[(q0 + 2 * tq + 1) * DP_PITCH + r0 + 8 + g] = x10[1];
-      }
-      if (okq && !diag) {
-        S[(q0 + 8 + 2 * tq) * DP_PITCH + r0 + g] = x01[0];
-        S[(q0 + 8 + 2 * tq + 1) * DP_PITCH + r0 + g] = x01[1];
-      }
-      if (okr && okq) {
-        S[(q0 + 8 + 2 * tq) * DP_PITCH + r0 + 8 + g] = x11[0];
-        S[(q0 + 8 + 2 * tq + 1) * DP_PITCH + r0 + 8 + g] = x11[1];
-      }
+    const int nsup = ms * (ms + 1) / 2;                  // 16x16 super-blocks of the trailing lower triangle
+    if (mblocks == 0) break;                             // block p was the last one
+    // ---- X / Y: the panel
+    if (warp < 4) {
+      if (warp < mblocks) panel_rows(c0, Ivp, warp);
+      bar_sync(1, 128);                                  // rows of block p+1 complete
+      if (warp < 3 && warp < nsup) update_super(c0, mblocks, warp);      // block (p+1, p+1)
+      bar_sync(2, 128);                                  // block (p+1, p+1) up to date
+    } else {
+      for (int mb = warp; mb < mblocks; mb += 4) panel_rows(c0, Ivp, mb);
     }
-    __syncthreads();
+    if (warp == 0) {
+      bar_arrive(3, 256);
+      STAMP();
+      // ---- the serial part: next diagonal block in registers, lane r owns row r
+      if (factor_block32(S, Iv + (p + 1) * SB * IVP, Tm, c0 + SB, lane)) s_failed = 1;
+      STAMP();
+    } else {
+      bar_sync(3, 256);                                  // every panel row of this step is written
+      for (int idx = 3 + (warp - 1); idx < nsup; idx += 7) update_super(c0, mblocks, idx);
+    }
+    bar_sync(4, 256);
     STAMP();
   }
+  __syncthreads();
 
   if (tid < T) lg[tid] = (tid < nact) ? log(S[tid * DP_PITCH + tid]) : 0.0;
   __syncthreads();
