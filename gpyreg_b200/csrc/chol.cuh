@@ -191,6 +191,78 @@ __device__ __noinline__ int factor_block32(double* S, double* Ivp, double* Tm, i
   return failed;
 }
 
+// Out of line (one copy each): the kernel's code must stay inside the SM's instruction cache -- with
+// these bodies inlined at every call site the block factorisation's unrolled code was evicted between
+// launches and its first call ran five times slower.
+// rows m0..m0+7 below block c0: L21 = P * Inv^T   (C(m,n) = sum_k P(m,k) Inv(n,k))
+__device__ __noinline__ void diag_panel_rows(double* S, const double* Ivp, int c0, int mb, int g, int tq) {
+  const int m0 = c0 + SB + mb * 8;
+  double af[8];
+#pragma unroll
+  for (int k4 = 0; k4 < 8; ++k4) af[k4] = S[(c0 + k4 * 4 + tq) * DP_PITCH + m0 + g];
+  double acc[4][2];
+#pragma unroll
+  for (int n8 = 0; n8 < 4; ++n8) acc[n8][0] = acc[n8][1] = 0.0;
+#pragma unroll
+  for (int k4 = 0; k4 < 8; ++k4) {
+    double bf[4];
+#pragma unroll
+    for (int n8 = 0; n8 < 4; ++n8) bf[n8] = Ivp[(k4 * 4 + tq) * IVP + n8 * 8 + g];
+#pragma unroll
+    for (int n8 = 0; n8 < 4; ++n8) dmma_t(acc[n8][0], acc[n8][1], af[k4], bf[n8]);   // 4 chains
+  }
+#pragma unroll
+  for (int n8 = 0; n8 < 4; ++n8) {
+    S[(c0 + n8 * 8 + 2 * tq) * DP_PITCH + m0 + g] = acc[n8][0];
+    S[(c0 + n8 * 8 + 2 * tq + 1) * DP_PITCH + m0 + g] = acc[n8][1];
+  }
+}
+
+// S -= L21 L21^T on one 16x16 super-block (2x2 DMMA blocks) of the trailing lower triangle: two A and
+// two B fragments per k-step feed four DMMAs
+__device__ __noinline__ void diag_update_super(double* S, int c0, int mblocks, int idx, int g, int tq) {
+  int si, sj;
+  tri_decode(idx, si, sj);
+  const int r0 = c0 + SB + si * 16, q0 = c0 + SB + sj * 16;
+  const bool okr = 2 * si + 1 < mblocks, okq = 2 * sj + 1 < mblocks;   // second half inside the tile
+  const bool diag = si == sj;                                          // block (0,1) is above the diagonal
+  double x00[2], x01[2], x10[2], x11[2];
+  x00[0] = S[(q0 + 2 * tq) * DP_PITCH + r0 + g];
+  x00[1] = S[(q0 + 2 * tq + 1) * DP_PITCH + r0 + g];
+  x10[0] = okr ? S[(q0 + 2 * tq) * DP_PITCH + r0 + 8 + g] : 0.0;
+  x10[1] = okr ? S[(q0 + 2 * tq + 1) * DP_PITCH + r0 + 8 + g] : 0.0;
+  x01[0] = (okq && !diag) ? S[(q0 + 8 + 2 * tq) * DP_PITCH + r0 + g] : 0.0;
+  x01[1] = (okq && !diag) ? S[(q0 + 8 + 2 * tq + 1) * DP_PITCH + r0 + g] : 0.0;
+  x11[0] = (okr && okq) ? S[(q0 + 8 + 2 * tq) * DP_PITCH + r0 + 8 + g] : 0.0;
+  x11[1] = (okr && okq) ? S[(q0 + 8 + 2 * tq + 1) * DP_PITCH + r0 + 8 + g] : 0.0;
+#pragma unroll
+  for (int k4 = 0; k4 < 8; ++k4) {
+    const int col = (c0 + k4 * 4 + tq) * DP_PITCH;
+    const double a0 = -S[col + r0 + g];
+    const double a1 = okr ? -S[col + r0 + 8 + g] : 0.0;
+    const double b0 = S[col + q0 + g];
+    const double b1 = okq ? S[col + q0 + 8 + g] : 0.0;
+    dmma_t(x00[0], x00[1], a0, b0);
+    dmma_t(x10[0], x10[1], a1, b0);
+    dmma_t(x11[0], x11[1], a1, b1);
+    if (!diag) dmma_t(x01[0], x01[1], a0, b1);
+  }
+  S[(q0 + 2 * tq) * DP_PITCH + r0 + g] = x00[0];
+  S[(q0 + 2 * tq + 1) * DP_PITCH + r0 + g] = x00[1];
+  if (okr) {
+    S[(q0 + 2 * tq) * DP_PITCH + r0 + 8 + g] = x10[0];
+    S[(q0 + 2 * tq + 1) * DP_PITCH + r0 + 8 + g] = x10[1];
+  }
+  if (okq && !diag) {
+    S[(q0 + 8 + 2 * tq) * DP_PITCH + r0 + g] = x01[0];
+    S[(q0 + 8 + 2 * tq + 1) * DP_PITCH + r0 + g] = x01[1];
+  }
+  if (okr && okq) {
+    S[(q0 + 8 + 2 * tq) * DP_PITCH + r0 + 8 + g] = x11[0];
+    S[(q0 + 8 + 2 * tq + 1) * DP_PITCH + r0 + 8 + g] = x11[1];
+  }
+}
+
 // One CTA factors a 128x128 diagonal tile and inverts the factor.
 //   S(r,c) lives at S[c*132 + r] (column-major, conflict-free along r, 16-byte aligned columns).
 //   The tile is processed in four 32-wide block columns.  Per block column:
@@ -258,110 +330,43 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
   // plain sequential sweep.
   auto bar_sync = [](int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); };
   auto bar_arrive = [](int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); };
-  auto panel_rows = [&](int c0, const double* Ivp, int mb) {
-    // rows m0..m0+7 below the block: L21 = P * Inv^T   (C(m,n) = sum_k P(m,k) Inv(n,k))
-    const int m0 = c0 + SB + mb * 8;
-    double af[8];
-#pragma unroll
-    for (int k4 = 0; k4 < 8; ++k4) af[k4] = S[(c0 + k4 * 4 + tq) * DP_PITCH + m0 + g];
-    double acc[4][2];
-#pragma unroll
-    for (int n8 = 0; n8 < 4; ++n8) acc[n8][0] = acc[n8][1] = 0.0;
-#pragma unroll
-    for (int k4 = 0; k4 < 8; ++k4) {
-      double bf[4];
-#pragma unroll
-      for (int n8 = 0; n8 < 4; ++n8) bf[n8] = Ivp[(k4 * 4 + tq) * IVP + n8 * 8 + g];
-#pragma unroll
-      for (int n8 = 0; n8 < 4; ++n8) dmma_t(acc[n8][0], acc[n8][1], af[k4], bf[n8]);   // 4 chains
+  for (int p = 0; p < T / SB; ++p) {
+    const int c0 = p * SB;                               // block factored in this round
+    if (c0 >= nact) break;
+    const int cp = c0 - SB;                              // block whose panel / trailing update is due (p > 0)
+    const int mblocks = (p > 0) ? (nact8 - c0) / 8 : 0;  // 8-row blocks below block p-1 (>= 1: block p exists)
+    const int ms = (mblocks + 1) / 2;
+    const int nsup = ms * (ms + 1) / 2;                  // 16x16 super-blocks of the trailing lower triangle
+    if (p > 0) {
+      const double* Ivp = Iv + (p - 1) * SB * IVP;
+      // ---- X / Y: the panel of block p-1
+      if (warp < 4) {
+        if (warp < mblocks) diag_panel_rows(S, Ivp, cp, warp, g, tq);
+        bar_sync(1, 128);                                // rows of block p complete
+        if (warp < 3 && warp < nsup) diag_update_super(S, cp, mblocks, warp, g, tq);      // block (p, p)
+        bar_sync(2, 128);                                // block (p, p) up to date
+      } else {
+        for (int mb = warp; mb < mblocks; mb += 4) diag_panel_rows(S, Ivp, cp, mb, g, tq);
+      }
     }
-#pragma unroll
-    for (int n8 = 0; n8 < 4; ++n8) {
-      S[(c0 + n8 * 8 + 2 * tq) * DP_PITCH + m0 + g] = acc[n8][0];
-      S[(c0 + n8 * 8 + 2 * tq + 1) * DP_PITCH + m0 + g] = acc[n8][1];
+    if (warp == 0) {
+      if (p > 0) bar_arrive(3, 256);
+      // ---- the serial part: diagonal block p in registers, lane r owns row r (single call site: the
+      // function is 40 KB of unrolled code)
+      if (factor_block32(S, Iv + p * SB * IVP, Tm, c0, lane)) s_failed = 1;
+    } else if (p > 0) {
+      bar_sync(3, 256);                                  // every panel row of block p-1 is written
+      // warp 4 shares its scheduler with warp 0: it sits the overlap out so that the (issue-bound)
+      // factorisation keeps its issue slots; the other six warps carry the trailing update
+      if (warp != 4) {
+        const int w = (warp < 4) ? warp - 1 : warp - 2;  // 0..5
+        for (int idx = 3 + w; idx < nsup; idx += 6) diag_update_super(S, cp, mblocks, idx, g, tq);
+      }
     }
-  };
-  auto update_super = [&](int c0, int mblocks, int idx) {
-    // S -= L21 L21^T on one 16x16 super-block (2x2 DMMA blocks) of the lower triangle: two A and
-    // two B fragments per k-step feed four DMMAs
-    int si, sj;
-    tri_decode(idx, si, sj);
-    const int r0 = c0 + SB + si * 16, q0 = c0 + SB + sj * 16;
-    const bool okr = 2 * si + 1 < mblocks, okq = 2 * sj + 1 < mblocks;   // second half inside the tile
-    const bool diag = si == sj;                                          // block (0,1) is above the diagonal
-    double x00[2], x01[2], x10[2], x11[2];
-    x00[0] = S[(q0 + 2 * tq) * DP_PITCH + r0 + g];
-    x00[1] = S[(q0 + 2 * tq + 1) * DP_PITCH + r0 + g];
-    x10[0] = okr ? S[(q0 + 2 * tq) * DP_PITCH + r0 + 8 + g] : 0.0;
-    x10[1] = okr ? S[(q0 + 2 * tq + 1) * DP_PITCH + r0 + 8 + g] : 0.0;
-    x01[0] = (okq && !diag) ? S[(q0 + 8 + 2 * tq) * DP_PITCH + r0 + g] : 0.0;
-    x01[1] = (okq && !diag) ? S[(q0 + 8 + 2 * tq + 1) * DP_PITCH + r0 + g] : 0.0;
-    x11[0] = (okr && okq) ? S[(q0 + 8 + 2 * tq) * DP_PITCH + r0 + 8 + g] : 0.0;
-    x11[1] = (okr && okq) ? S[(q0 + 8 + 2 * tq + 1) * DP_PITCH + r0 + 8 + g] : 0.0;
-#pragma unroll
-    for (int k4 = 0; k4 < 8; ++k4) {
-      const int col = (c0 + k4 * 4 + tq) * DP_PITCH;
-      const double a0 = -S[col + r0 + g];
-      const double a1 = okr ? -S[col + r0 + 8 + g] : 0.0;
-      const double b0 = S[col + q0 + g];
-      const double b1 = okq ? S[col + q0 + 8 + g] : 0.0;
-      dmma_t(x00[0], x00[1], a0, b0);
-      dmma_t(x10[0], x10[1], a1, b0);
-      dmma_t(x11[0], x11[1], a1, b1);
-      if (!diag) dmma_t(x01[0], x01[1], a0, b1);
-    }
-    S[(q0 + 2 * tq) * DP_PITCH + r0 + g] = x00[0];
-    S[(q0 + 2 * tq + 1) * DP_PITCH + r0 + g] = x00[1];
-    if (okr) {
-      S[(q0 + 2 * tq) * DP_PITCH + r0 + 8 + g] = x10[0];
-      S[(q0 + 2 * tq + 1) * DP_PITCH + r0 + 8 + g] = x10[1];
-    }
-    if (okq && !diag) {
-      S[(q0 + 8 + 2 * tq) * DP_PITCH + r0 + g] = x01[0];
-      S[(q0 + 8 + 2 * tq + 1) * DP_PITCH + r0 + g] = x01[1];
-    }
-    if (okr && okq) {
-      S[(q0 + 8 + 2 * tq) * DP_PITCH + r0 + 8 + g] = x11[0];
-      S[(q0 + 8 + 2 * tq + 1) * DP_PITCH + r0 + 8 + g] = x11[1];
-    }
-  };
-
-  if (warp == 0) {
-    if (factor_block32(S, Iv, Tm, 0, lane)) s_failed = 1;
+    bar_sync(4, 256);
   }
   __syncthreads();
   STAMP();
-  for (int p = 0; p < T / SB; ++p) {
-    const int c0 = p * SB;
-    if (c0 >= nact) break;
-    const double* Ivp = Iv + p * SB * IVP;
-    const int mblocks = max(0, (nact8 - c0 - SB) / 8);   // 8-row blocks below block p
-    const int ms = (mblocks + 1) / 2;
-    const int nsup = ms * (ms + 1) / 2;                  // 16x16 super-blocks of the trailing lower triangle
-    if (mblocks == 0) break;                             // block p was the last one
-    // ---- X / Y: the panel
-    if (warp < 4) {
-      if (warp < mblocks) panel_rows(c0, Ivp, warp);
-      bar_sync(1, 128);                                  // rows of block p+1 complete
-      if (warp < 3 && warp < nsup) update_super(c0, mblocks, warp);      // block (p+1, p+1)
-      bar_sync(2, 128);                                  // block (p+1, p+1) up to date
-    } else {
-      for (int mb = warp; mb < mblocks; mb += 4) panel_rows(c0, Ivp, mb);
-    }
-    if (warp == 0) {
-      bar_arrive(3, 256);
-      STAMP();
-      // ---- the serial part: next diagonal block in registers, lane r owns row r
-      if (factor_block32(S, Iv + (p + 1) * SB * IVP, Tm, c0 + SB, lane)) s_failed = 1;
-      STAMP();
-    } else {
-      bar_sync(3, 256);                                  // every panel row of this step is written
-      for (int idx = 3 + (warp - 1); idx < nsup; idx += 7) update_super(c0, mblocks, idx);
-    }
-    bar_sync(4, 256);
-    STAMP();
-  }
-  __syncthreads();
 
   if (tid < T) lg[tid] = (tid < nact) ? log(S[tid * DP_PITCH + tid]) : 0.0;
   __syncthreads();
