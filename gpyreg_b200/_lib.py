@@ -34,6 +34,7 @@ SYMBOLS = {
     "gpb_posterior_free": (None, [_vp]),
     "gpb_posterior_size": (C.c_int64, [_vp]),
     "gpb_posterior_append": (C.c_int, [_vp, _vp, _vp, C.c_double, _vp]),
+    "gpb_posterior_rebuild": (C.c_int, [_vp, _vp, _vp, C.c_int64]),
     "gpb_predict": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_int,
                               _vp, _vp, _vp]),
     "gpb_predict_dev": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int, C.c_int, _vp, _vp]),

@@ -1892,10 +1892,58 @@ extern "C" int gpb_posterior_append(gpb_ctx* ctx, gpb_post* post, const double* 
     status[s] = st[s];
     ok = ok && st[s] == 0;
   }
-  // with an unstable sample the batch is inconsistent (some samples hold N+1 points): the caller
-  // rebuilds it; mark it unusable for predict until then
-  if (ok) post->N = N + 1;
-  else for (int s = 0; s < Ns; ++s) post->status[s] = 1;
+  // The stable samples now hold N+1 points.  An unstable one was left untouched: it is marked
+  // unusable until the caller recomputes it on the extended data (gpb_posterior_rebuild), which is
+  // what the reference does for exactly those samples (gaussian_process.py:864-868)
+  (void)ok;
+  post->N = N + 1;
+  for (int s = 0; s < Ns; ++s)
+    if (st[s]) post->status[s] = 1;
+  return GPB_OK;
+}
+
+extern "C" int gpb_posterior_rebuild(gpb_ctx* ctx, gpb_post* post, const int32_t* slots, int64_t n) {
+  if (!ctx || !post || !slots || n <= 0) return GPB_EINVAL;
+  NvtxRange nv_call("gpb_posterior_rebuild");
+  if (post->ctx != ctx) FAIL(GPB_EINVAL, "gpb_posterior_rebuild: posterior belongs to another context");
+  Bufs& b = post->b;
+  const Model md = post->md;
+  if (!ctx->has_data || ctx->N != post->N || ctx->Np != b.Np || ctx->D != md.D)
+    FAIL(GPB_ESTATE, "gpb_posterior_rebuild: the context must hold the data the posteriors cover (gpb_set_data first)");
+  CK(cudaSetDevice(ctx->device));
+  std::vector<int> list;
+  for (int64_t i = 0; i < n; ++i) {
+    if (slots[i] < 0 || slots[i] >= b.cap) FAIL(GPB_EINVAL, "gpb_posterior_rebuild: sample index out of range");
+    list.push_back(slots[i]);
+  }
+  int rc = factor_with_retry(ctx, b, md, post->N, list, true, post->status);
+  if (rc != GPB_OK) return rc;
+  CK(cudaMemcpyAsync(b.sel3, list.data(), sizeof(int) * list.size(), cudaMemcpyHostToDevice, ctx->stream));
+  run_bwd(ctx, b, b.sel3, (int)list.size());
+  std::vector<SlotP> all((size_t)b.cap);
+  CK(cudaMemcpyAsync(all.data(), b.sp, sizeof(SlotP) * b.cap, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  std::vector<int> low, high;
+  for (int s : list) {
+    post->sp[s] = all[s];
+    if (post->status[s]) continue;
+    (all[s].lchol ? high : low).push_back(s);
+  }
+  if (!low.empty()) {               // L = -(K + sn2_mult*diag(sn2))^-1, both triangles (gaussian_process.py:2440-2448)
+    CK(cudaMemcpyAsync(b.sel2, low.data(), sizeof(int) * low.size(), cudaMemcpyHostToDevice, ctx->stream));
+    run_inverse(ctx, b, post->N, b.sel2, (int)low.size(), true, true);
+    for (int s : low) {
+      symmetrize_kernel<<<grid1d(b.smat()), 256, 0, ctx->stream>>>(b.Abuf + s * b.smat(), b.Np);
+      LAUNCHED(ctx);
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  if (!high.empty() && post->w_ready) {   // the other samples' W = L^-1 exists: keep the batch uniform
+    CK(cudaMemcpyAsync(b.sel2, high.data(), sizeof(int) * high.size(), cudaMemcpyHostToDevice, ctx->stream));
+    run_inverse(ctx, b, post->N, b.sel2, (int)high.size(), false, false);
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  CK(cudaGetLastError());
   return GPB_OK;
 }
 

@@ -157,6 +157,12 @@ class Engine:
         post.N = int(self.lib.gpb_posterior_size(post._h))
         return status
 
+    def posterior_rebuild(self, post, slots):
+        """Recompute the listed samples of ``post`` from scratch on the data this engine holds (the
+        reference's "full update where rank-1 failed", gaussian_process.py:864-868)."""
+        slots = np.ascontiguousarray(slots, dtype=np.int32).reshape(-1)
+        self._check(self.lib.gpb_posterior_rebuild(self._h, post._h, ptr(slots), slots.size))
+
     def predict(self, post, Xs, ys=None, s2s=None, add_noise=False, separate=False, want_lpd=False):
         Xs = f64(Xs)
         M = Xs.shape[0]

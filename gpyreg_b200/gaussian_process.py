@@ -686,9 +686,9 @@ class GP:
         rank_one = (X_new is not None and y_new is not None and compute_posterior
                     and self.X is not None and self.y is not None
                     and X_new.shape[0] == 1 and y_new.shape[0] == 1 and s2_new is None)   # :738-748
-        appended = False
+        appended, unstable = False, ()
         if rank_one:
-            appended = self._rank_one_append(X_new, y_new)
+            appended, unstable = self._rank_one_append(X_new, y_new)
         if X_new is not None:
             self.X = X_new.copy() if self.X is None else np.concatenate((self.X, X_new))
         if y_new is not None:
@@ -696,6 +696,15 @@ class GP:
         if s2_new is not None:
             self.s2 = s2_new.copy() if self.s2 is None else np.concatenate((self.s2, s2_new))
         if appended:
+            if len(unstable):
+                # "Compute full update where rank-1 failed" (:864-868): only those samples, on the extended
+                # data; the others keep their rank-one factors and jitter multipliers
+                self._sync_engine().posterior_rebuild(self._post_batch, unstable)
+                for s in unstable:
+                    p = self.posteriors[s]
+                    for k in Posterior._FIELDS:
+                        p._have[k] = False
+                        p._val[k] = None
             return
         if rank_one and self.posteriors is not None:
             # the rank-one branch keeps the current samples and ignores ``hyp`` (:864-868)
@@ -713,24 +722,25 @@ class GP:
                 self.posteriors[i] = Posterior(hyp[i, :], None, None, None, None, None)
 
     def _rank_one_append(self, X_new, y_new):
-        """The device rank-one update; False when it does not apply or was unstable (the caller
-        then rebuilds all samples, which the reference does per unstable sample, :864-868)."""
+        """The device rank-one update -> (applied, unstable samples).  ``applied`` is False when the
+        in-place update does not apply (the caller then rebuilds all samples in one batched call);
+        samples whose update failed the reference's stability test (:784-798) were left untouched and
+        are recomputed by the caller once the data is extended (:864-868)."""
         batch = self._device_batch()
         if batch is None:
-            return False
+            return False, ()
         status = batch.engine.posterior_append(batch, X_new[0], float(y_new[0, 0]))
         if status is None:
-            return False
-        if status.any():
-            for s in np.flatnonzero(status):
-                warnings.warn("Rank-one update of Cholesky factor unstable "
-                              + f"for posterior {s}. Reverting to full update.", stacklevel=3)
-            return False
+            return False, ()
+        unstable = np.flatnonzero(status)
+        for s in unstable:
+            warnings.warn("Rank-one update of Cholesky factor unstable "
+                          + f"for posterior {s}. Reverting to full update.", stacklevel=3)
         for p in self.posteriors:                 # alpha, sW, L changed on the device
             for k in ("alpha", "sW", "L"):
                 p._have[k] = False
                 p._val[k] = None
-        return True
+        return True, unstable
 
     def clean(self):
         """Drop the factors (gaussian_process.py:886-905); ``update()`` rebuilds them."""

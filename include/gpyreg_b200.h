@@ -99,12 +99,17 @@ int64_t gpb_posterior_size(const gpb_post* post);
  * (x_new (D), y_new, no s2) to every sample of `post`, in place on the device.
  *   status[s] = 1  <=>  the reference's stability test fails for sample s
  *   (sqrt_arg <= 0, :784-798, "Rank-one update of Cholesky factor unstable"): that sample
- *   is left untouched and the caller rebuilds the batch with gpb_posterior_batch.
+ *   is left untouched and unusable until the caller recomputes it with gpb_posterior_rebuild.
  * Returns GPB_EAGAIN (nothing changed) when the in-place update does not apply: the noise
  * variance depends on the point (user-provided or output-dependent terms), or the padded
  * device layout has no free row left (every 128 points) -- rebuild with gpb_posterior_batch. */
 int gpb_posterior_append(gpb_ctx* ctx, gpb_post* post, const double* x_new, double y_new,
                          int32_t* status);
+/* "Compute full update where rank-1 failed", gaussian_process.py:864-868: recompute the listed
+ * samples of `post` from scratch (sn2_mult restarts at 1) on the data the context holds, which
+ * must be the data the other samples cover (call gpb_set_data with the extended X, y first).
+ * The other samples keep their rank-one factors. */
+int gpb_posterior_rebuild(gpb_ctx* ctx, gpb_post* post, const int32_t* slots, int64_t n);
 
 /* GP.predict, gaussian_process.py:1663-1816, over all samples of `post`.
  *   Xs (M,D); ys (M) or NULL; s2s (M) or NULL; outputs mu, s2 [, lpd]:

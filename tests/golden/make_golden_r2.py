@@ -1,6 +1,7 @@
 """Round-2 golden vectors, produced by running the REAL reference (build container only):
 
-    python tests/golden/make_golden_r2.py
+    python tests/golden/make_golden_r2.py          # round2.npz (about 5 minutes)
+    python tests/golden/make_golden_r2.py pfull    # pfull.npz: predict_full / quad on several tiles per side
 
 Writes tests/golden/round2.npz:
   * rqiso.*    isotropic rational quadratic = the reference's RationalQuadraticARD with all length
@@ -118,7 +119,47 @@ def gen_low2(out):
     print("low2: L_chol", out["low2.L_chol"], "sn2_mult", out["low2.sn2_mult"])
 
 
+def gen_pfull():
+    """predict_full / quad on SEVERAL tiles per side (N=300: three 128-tiles; M=150: two): the device
+    layout keeps W = L^-1 lower-triangular in tile storage with W^T in the upper tiles, which a
+    one-tile case cannot tell apart from a dense W.  Both factorisation branches."""
+    out = {}
+    rng = np.random.default_rng(900)
+    for tag, cov, mk, npar, lownoise in [("se", COVS[0], 2, (1, 0, 0), False), ("mat5", COVS[3], 1, (1, 2, 1), False),
+                                         ("lown", COVS[0], 1, (1, 0, 0), True)]:
+        N, D, B, M = 300, 2, 2, 150
+        X, y = synth(rng, N, D)
+        s2 = rng.uniform(0.005, 0.05, (N, 1)) if npar[1] else None
+        gp = make_gp(D, cov, mk, npar)
+        hyps = benign_hyp(rng, B, D, cov, mk, npar, y)
+        if lownoise:
+            hyps[:, D + 1] = np.log(3e-4)
+            hyps[:, :D] = np.log(0.3)
+        gp.update(X_new=X, y_new=y, s2_new=s2, hyp=hyps)
+        Xs = rng.uniform(-3, 3, (M, D))
+        out[f"{tag}.spec"] = np.array([D, cov[1], cov[2], cov[3], mk, *npar])
+        out[f"{tag}.X"], out[f"{tag}.y"], out[f"{tag}.hyp"], out[f"{tag}.Xs"] = X, y, hyps, Xs
+        if s2 is not None:
+            out[f"{tag}.s2"] = s2
+        out[f"{tag}.L_chol"] = np.array([int(p.L_chol) for p in gp.posteriors])
+        kw = dict(s2_star=0.01) if npar[1] else {}
+        for an in (0, 1):
+            m, c = gp.predict_full(Xs, add_noise=bool(an), **kw)
+            out[f"{tag}.full{an}.mu"], out[f"{tag}.full{an}.cov"] = m, np.ascontiguousarray(c)
+        if cov[1] == 0:
+            mu = rng.uniform(-2, 2, (5, D))
+            sigma = rng.uniform(0.2, 1.5, (5, D))
+            out[f"{tag}.qmu"], out[f"{tag}.qsigma"] = mu, sigma
+            F, Fv = gp.quad(mu, sigma, compute_var=True, separate_samples=True)
+            out[f"{tag}.quad.F"], out[f"{tag}.quad.Fv"] = F, Fv
+    np.savez_compressed(os.path.join(HERE, "pfull.npz"), **out)
+    print("pfull.npz", len(out), "arrays; L_chol", [out[t + ".L_chol"].tolist() for t in ("se", "mat5", "lown")])
+
+
 if __name__ == "__main__":
+    if "pfull" in sys.argv[1:]:
+        gen_pfull()
+        sys.exit(0)
     out = {}
     gen_rqiso(out)
     gen_low2(out)

@@ -367,3 +367,30 @@ def test_quad_and_predict_full_after_rank_one_update():
     mr, cr = ref.predict_full(Xs, add_noise=True)
     np.testing.assert_allclose(m, mr, rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(c, cr, rtol=1e-7, atol=1e-12)
+
+
+@pytest.mark.parametrize("tag", ["se", "mat5", "lown"])
+def test_predict_full_and_quad_on_several_tiles(tag):
+    """predict_full (and quad) with N=300 training points = three 128-tiles per side and M=150 test points,
+    against the reference (tests/golden/pfull.npz).  W = L^-1 is lower triangular in tile storage and the
+    upper tiles of the device buffer hold W^T: a product that runs over whole rows of that buffer is wrong
+    as soon as there is more than one tile (round-2 regression; the one-tile goldens could not see it)."""
+    g_ = _load("pfull.npz")
+    c = case(g_, tag)
+    gp = build_gp(c["spec"])
+    gp.update(X_new=c["X"], y_new=c["y"], s2_new=c.get("s2"), hyp=c["hyp"])
+    assert [int(p.L_chol) for p in gp.posteriors] == list(c["L_chol"])
+    kw = dict(s2_star=0.01) if "s2" in c else {}
+    for an in (0, 1):
+        mu, cov = gp.predict_full(c["Xs"], add_noise=bool(an), **kw)
+        assert mu.shape == c[f"full{an}.mu"].shape and cov.shape == c[f"full{an}.cov"].shape
+        assert np.max(np.abs(mu - c[f"full{an}.mu"])) <= 1e-8 * (1 + np.max(np.abs(c[f"full{an}.mu"])))
+        tol = 1e-8 if tag != "lown" else 1e-6       # low-noise branch: K* + Ks^T L Ks cancels (cond ~ 1e8)
+        assert np.max(np.abs(cov - c[f"full{an}.cov"])) <= tol * np.max(np.abs(c[f"full{an}.cov"]))
+        # the diagonal is what predict() returns
+        m1, v1 = gp.predict(c["Xs"], add_noise=bool(an), separate_samples=True, **kw)
+        assert np.max(np.abs(np.einsum("iis->is", cov) - v1)) <= tol * np.max(np.abs(v1))
+    if "qmu" in c:
+        F, Fv = gp.quad(c["qmu"], c["qsigma"], compute_var=True, separate_samples=True)
+        assert np.max(np.abs(F - c["quad.F"])) <= 1e-8 * (1 + np.max(np.abs(c["quad.F"])))
+        assert np.max(np.abs(Fv - c["quad.Fv"])) <= (1e-8 if tag != "lown" else 1e-6) * np.max(np.abs(c["quad.Fv"])) + 1e-15

@@ -142,3 +142,39 @@ def test_posterior_handles_die_with_their_context():
     p2.free()
     p1.free()
     del p1, p2, e
+
+
+def test_posterior_rebuild_of_selected_samples():
+    """gaussian_process.py:864-868: after a rank-one update only the samples whose update was unstable are
+    recomputed (on the extended data); the others keep their rank-one factors.  Natural instability is rare,
+    so the recompute is exercised on a chosen sample: it must equal a fresh posterior of that row on N+1
+    points bit for bit, the untouched sample must equal the rank-one result bit for bit, and predictions
+    through the mixed batch must match the oracle."""
+    from gpyreg_b200 import Engine
+    spec, X, y, hyp = _problem(N=201, B=3, mean_kind=1)
+    Xn, yn, X0, y0 = X[-1], y[-1], X[:-1], y[:-1]
+    e = _engine(spec, X0, y0)
+    post = e.posterior_batch(hyp)
+    e.predict(post, X0[:4])                               # W = L^-1 exists before the append
+    st = e.posterior_append(post, Xn, float(yn[0]))
+    assert st is not None and not st.any() and post.N == 201
+    kept = [post.fetch(b, "alpha").copy() for b in range(3)]
+    e.set_data(X, y, None)                                # the context now holds the N+1 points
+    e.posterior_rebuild(post, [1])
+    fresh = e.posterior_batch(hyp)
+    np.testing.assert_array_equal(post.fetch(1, "alpha"), fresh.fetch(1, "alpha"))
+    np.testing.assert_array_equal(post.fetch(1, "L"), fresh.fetch(1, "L"))
+    for b in (0, 2):
+        np.testing.assert_array_equal(post.fetch(b, "alpha"), kept[b])
+    Xs = np.random.default_rng(1).uniform(-3, 3, (40, 3))
+    mu, s2 = e.predict(post, Xs, add_noise=True, separate=True)
+    rmu, rs2 = orc.predict(spec, orc.posterior_batch(spec, hyp, X, y, None), X, y, Xs, add_noise=True,
+                           separate_samples=True)
+    assert np.max(np.abs(mu - rmu)) <= 1e-8 * (1 + np.max(np.abs(rmu)))
+    assert np.max(np.abs(s2 - rs2)) <= 1e-8 * np.max(np.abs(rs2))
+    with pytest.raises(Exception, match="data the posteriors cover"):
+        e.set_data(X0, y0, None)
+        e.posterior_rebuild(post, [0])
+    post.free()
+    fresh.free()
+    e.close()

@@ -222,20 +222,24 @@ def test_convert_shapes_and_posterior_record():
 
 
 def test_rank_one_update_host_logic():
-    """update() with one new point: device append when it applies, otherwise (declined, or the
-    reference's stability test failed, gaussian_process.py:790-798) a rebuild of all samples with the
-    CURRENT hyperparameter samples -- the ``hyp`` argument is ignored on this branch (:864-868)."""
+    """update() with one new point: device append when it applies; samples that fail the reference's
+    stability test (gaussian_process.py:790-798) are recomputed alone on the extended data (:864-868);
+    when the library declines, all samples are rebuilt with their CURRENT hyperparameters -- the ``hyp``
+    argument is ignored on this branch."""
     from gpyreg_b200.gaussian_process import Posterior
 
     class FakeEngine:
         def __init__(self, status):
-            self.status, self.calls = status, []
+            self.status, self.calls, self.rebuilt = status, [], []
 
         def posterior_append(self, post, x_new, y_new):
             self.calls.append((np.array(x_new), y_new))
-            if self.status is not None and not np.any(self.status):
+            if self.status is not None:
                 post.N += 1
             return self.status
+
+        def posterior_rebuild(self, post, slots):
+            self.rebuilt.append(list(slots))
 
     class FakeBatch:
         def __init__(self, engine):
@@ -257,6 +261,7 @@ def test_rank_one_update_host_logic():
             return gp.posteriors, batch
 
         gp._posteriors_for = fake_posteriors_for
+        gp._sync_engine = lambda: batch.engine
         return gp, batch, rebuilt
 
     x, y = np.array([[1.0, 2.0]]), np.array([[3.0]])
@@ -266,11 +271,13 @@ def test_rank_one_update_host_logic():
     assert rebuilt == [] and batch.N == 6 and gp.X.shape == (6, 2) and gp.y.shape == (6, 1)
     assert not gp.posteriors[0]._have["alpha"] and len(batch.engine.calls) == 1
     assert batch.engine.calls[0][1] == 3.0 and np.array_equal(batch.engine.calls[0][0], [1.0, 2.0])
-    # unstable sample: warning with the reference's text, rebuild with the samples' own hyp
+    # unstable sample: warning with the reference's text, THAT sample recomputed on the extended data
     gp, batch, rebuilt = make(np.array([0, 1], dtype=np.int32))
+    gp.posteriors[1]._set("sn2_mult", 10)
     with pytest.warns(UserWarning, match="Rank-one update of Cholesky factor unstable for posterior 1"):
         gp.update(X_new=x, y_new=y, hyp=np.full((1, 5), 9.0))
-    assert len(rebuilt) == 1 and np.array_equal(rebuilt[0], [[0.0] * 5, [1.0] * 5]) and gp.X.shape == (6, 2)
+    assert rebuilt == [] and batch.engine.rebuilt == [[1]] and gp.X.shape == (6, 2) and batch.N == 6
+    assert not gp.posteriors[1]._have["sn2_mult"] and not gp.posteriors[0]._have["alpha"]
     # declined by the library (GPB_EAGAIN): silent rebuild
     gp, batch, rebuilt = make(None)
     gp.update(X_new=x, y_new=y)
