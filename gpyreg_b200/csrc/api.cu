@@ -222,6 +222,7 @@ template <class Op, int BM_, int BN_>
 static bool tma_operands(const gpb_ctx* ctx, TmaOperands& o) {
   const Bufs* b = ctx->cur;
   if (Op::TMA_A < 0 || !b || !b->tm_ok) return false;
+  if ((BM_ != BM && BM_ != BM / 2) || (BN_ != BN && BN_ != BN / 2)) return false;   // boxes exist for 128 and 64 rows
   double* bases[4] = {b->Abuf, b->Wbuf, b->Dbuf, b->DTbuf};
   const long long lds[4] = {b->Np, b->Np, T, T};
   constexpr int ia = (BM_ == BM) ? 0 : 1, ib = (BN_ == BN) ? 0 : 1;
@@ -304,7 +305,10 @@ static void launch_panel(gpb_ctx* ctx, const OpPanel& op, dim3 grid) {
   const bool two = ctx->gemm_bn != 128;
   const long long ctas = (long long)grid.x * grid.y * (two ? 2 : 1);
   const int loader = pick_loader(ctx, ctas);
-  if (two) launch_shape<OpPanel, 64, 128>(ctx, op, grid, loader);
+  // a panel of a few tiles sits on the dependent chain of a small batch: row quarters put four CTAs
+  // on each tile (the fused forward-substitution sum is shape-independent, see gemm.cuh)
+  if (two && ctx->quarter_tiles && ctas * 2 <= 2 * 148) launch_shape<OpPanel, 32, 128>(ctx, op, grid, loader);
+  else if (two) launch_shape<OpPanel, 64, 128>(ctx, op, grid, loader);
   else launch_shape<OpPanel, 128, 128>(ctx, op, grid, loader);
 }
 
@@ -338,6 +342,7 @@ static int init_attrs(gpb_ctx* ctx) {
   CK((gemm_attr_shape<OpFwdZ, 64, 128>()));
   CK((gemm_attr_shape<OpFwd, 128, 128>()));
   CK((gemm_attr_shape<OpPanel, 64, 128>()));
+  CK((gemm_attr_shape<OpPanel, 32, 128>()));
   CK(gemm_attr<OpSyrk>());
   CK((gemm_attr_shape<OpSyrk, 64, 64>()));
   CK(gemm_attr<OpHpass>());

@@ -449,32 +449,39 @@ gemm_nt_kernel(const __grid_constant__ Op op, const __grid_constant__ typename T
   }
   if (MODE & GM_ROWDOT) {
     // fused forward substitution: vdst[m] -= sum_n C(m,n) * vdot[n]  (needs all columns of the
-    // tile in this CTA: BN_ == BN), reduced in a fixed order
+    // tile in this CTA: BN_ == BN).  The order of the sum does not depend on the CTA shape: the 128
+    // columns are taken in eight groups of 16 (two 8-column DMMA blocks: FMA chain over the thread's
+    // four values, then the xor tree over the four threads of a row), and the groups are added in
+    // increasing order -- so a 32x128, 64x128 or 128x128 CTA gives the same bits.
     if (t.vdot == nullptr) return;
     __syncthreads();
-    double* red = gsm;          // [NW][BM_]
+    double* red = (MODE & GM_ZSOLVE) ? gsm + 512 : gsm;    // [8][BM_]; after the z solve D_k's staging area is free
+    static_assert(NI % 2 == 0, "row-dot epilogue works on groups of two 8-column blocks");
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi) {
       const int m = wm + mi * 8 + g;
-      double s = 0.0;
-      if (wact) {
 #pragma unroll
-        for (int ni = 0; ni < NI; ++ni) {
-          const int n = wn + ni * 8 + 2 * tq;
-          // explicit FMAs: every instantiation (fused panel, solve-only replay) rounds identically
-          s = __fma_rn(t.alpha * acc[mi][ni][0], t.vdot[n], s);
-          s = __fma_rn(t.alpha * acc[mi][ni][1], t.vdot[n + 1], s);
+      for (int gq = 0; gq < NI / 2; ++gq) {
+        double s = 0.0;
+        if (wact) {
+#pragma unroll
+          for (int ni = 2 * gq; ni < 2 * gq + 2; ++ni) {
+            const int n = wn + ni * 8 + 2 * tq;
+            // explicit FMAs: every instantiation (fused panel, solve-only replay) rounds identically
+            s = __fma_rn(t.alpha * acc[mi][ni][0], t.vdot[n], s);
+            s = __fma_rn(t.alpha * acc[mi][ni][1], t.vdot[n + 1], s);
+          }
         }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (tq == 0) red[((wn >> 4) + gq) * BM_ + m] = s;
       }
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      if (tq == 0) red[(warp / MW) * BM_ + m] = s;
     }
     __syncthreads();
     if (tid < BM_ && tid < mv) {
       double s = 0.0;
 #pragma unroll
-      for (int w = 0; w < NW; ++w) s += red[w * BM_ + tid];
+      for (int w = 0; w < BN / 16; ++w) s += red[w * BM_ + tid];
       t.vdst[tid] -= s;
     }
   }

@@ -86,6 +86,13 @@ class Posterior:
     def _get(self, name):
         if not self._have[name]:
             b, s = self._batch, self._index
+            if b is None:
+                # a record of a copied / unpickled GP whose factor was not carried along: the owning
+                # GP re-creates the device factors of all its samples and this field is read from them
+                gp = self._owner() if getattr(self, "_owner", None) is not None else None
+                b = gp._device_batch() if gp is not None else None
+                if b is None:
+                    raise RuntimeError("Posterior: the factor of this record is gone (its GP was deleted)")
             if name == "alpha":
                 v = b.fetch(s, "alpha").reshape(-1, 1)
             elif name == "sW":
@@ -103,12 +110,19 @@ class Posterior:
     def _set(self, name, v):
         self._val[name], self._have[name] = v, True
 
-    def _detached(self):
-        """A plain host-side copy of the record (every field fetched), with no tie to the device:
-        what ``copy.deepcopy`` / ``pickle`` of a reference Posterior would hold."""
-        vals = [self._get(k) for k in self._FIELDS]
-        vals = [v.copy() if isinstance(v, np.ndarray) else v for v in vals]
-        return Posterior(np.array(self.hyp, copy=True), *vals)
+    def _detached(self, with_factor=True):
+        """A plain host-side copy of the record with no tie to the device: what ``copy.deepcopy`` /
+        ``pickle`` of a reference Posterior would hold.  ``with_factor=False`` (copies of a whole GP)
+        leaves the (N, N) factor behind unless it has already been fetched: the copied GP rebuilds its
+        device factors on first use and the field is read from them then."""
+        skip = () if with_factor or self._have["L"] else ("L",)
+        vals = {k: (None if k in skip else self._get(k)) for k in self._FIELDS}
+        vals = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in vals.items()}
+        new = Posterior(np.array(self.hyp, copy=True), vals["alpha"], vals["sW"], vals["L"], vals["sn2_mult"],
+                        vals["L_chol"], _index=self._index)
+        for k in skip:
+            new._have[k] = False
+        return new
 
     def __deepcopy__(self, memo):
         new = self._detached()
@@ -116,14 +130,20 @@ class Posterior:
         return new
 
     def __reduce__(self):
-        d = self._detached()
-        return (Posterior, (d.hyp, d.alpha, d.sW, d.L, d.sn2_mult, d.L_chol))
+        d = self if (self._batch is None and getattr(self, "_owner", None) is None) else self._detached()
+        return (_posterior_from_state, (d.hyp, dict(d._val), dict(d._have), d._index))
 
     alpha = property(lambda s: s._get("alpha"), lambda s, v: s._set("alpha", v))
     sW = property(lambda s: s._get("sW"), lambda s, v: s._set("sW", v))
     L = property(lambda s: s._get("L"), lambda s, v: s._set("L", v))
     sn2_mult = property(lambda s: s._get("sn2_mult"), lambda s, v: s._set("sn2_mult", v))
     L_chol = property(lambda s: s._get("L_chol"), lambda s, v: s._set("L_chol", v))
+
+
+def _posterior_from_state(hyp, val, have, index):
+    p = Posterior(hyp, val["alpha"], val["sW"], val["L"], val["sn2_mult"], val["L_chol"], _index=index)
+    p._have = dict(have)
+    return p
 
 
 def _spec_of(D, covariance, mean, noise):
@@ -193,14 +213,18 @@ class GP:
         if self.posteriors is not None:
             posts = np.empty(self.posteriors.shape, dtype=object)
             for i, p in enumerate(self.posteriors):
-                posts[i] = p._detached()
+                posts[i] = p._detached(with_factor=False)     # 8 N^2 bytes per sample stay on the device
             d["posteriors"] = posts
         return d
 
     def __setstate__(self, d):
+        import weakref
         self.__dict__.update(d)
         self._engine = self._post_batch = self._data_key = None
         self._token = object()
+        if self.posteriors is not None:
+            for p in self.posteriors:
+                p._owner = weakref.ref(self)
 
     def __deepcopy__(self, memo):
         import copy
@@ -217,7 +241,7 @@ class GP:
                 all(p._batch is batch for p in self.posteriors):
             return batch
         if self.posteriors is None or self.X is None or self.y is None or \
-                any(p.alpha is None for p in self.posteriors):
+                any(p._have["alpha"] and p._val["alpha"] is None for p in self.posteriors):
             return None                      # cleaned, or never computed: the caller must update()
         hyp = np.stack([np.asarray(p.hyp, dtype=float) for p in self.posteriors])
         self.posteriors, self._post_batch = self._posteriors_for(hyp)

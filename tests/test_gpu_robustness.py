@@ -178,3 +178,36 @@ def test_posterior_rebuild_of_selected_samples():
     post.free()
     fresh.free()
     e.close()
+
+
+def test_gp_deepcopy_and_pickle_rebuild_their_factors():
+    """PyVBMC deep-copies and pickles its GPs.  A copy carries host records (alpha, sW, flags; the (N, N)
+    factor stays behind), shares nothing with the original, predicts identically after re-creating its
+    factors on the device, and still serves ``posteriors[i].L``."""
+    import copy
+    import pickle
+    import gpyreg_b200 as g
+    from gpyreg_b200.covariance_functions import Matern
+    from gpyreg_b200.mean_functions import ConstantMean
+    from gpyreg_b200.noise_functions import GaussianNoise
+    spec, X, y, hyp = _problem(N=180, B=3, mean_kind=1)
+    gp = g.GP(3, Matern(5), ConstantMean(), GaussianNoise(constant_add=True))
+    gp.update(X_new=X, y_new=y, hyp=hyp)
+    Xs = np.random.default_rng(0).uniform(-3, 3, (25, 3))
+    ref = gp.predict(Xs, add_noise=True)
+    L0 = gp.posteriors[1].L.copy()
+    for other in (copy.deepcopy(gp), pickle.loads(pickle.dumps(gp))):
+        assert other._post_batch is None and other.posteriors[0]._batch is None
+        assert not other.posteriors[0]._have["L"] and other.posteriors[0]._have["alpha"]
+        np.testing.assert_array_equal(other.posteriors[2].alpha, gp.posteriors[2].alpha)
+        got = other.predict(Xs, add_noise=True)
+        np.testing.assert_array_equal(got[0], ref[0])
+        np.testing.assert_array_equal(got[1], ref[1])
+        np.testing.assert_array_equal(other.posteriors[1].L, L0)
+        other.update(X_new=Xs[:1], y_new=np.zeros((1, 1)))          # rank-one update on the copy only
+        assert other.X.shape[0] == 181 and gp.X.shape[0] == 180
+    np.testing.assert_array_equal(gp.predict(Xs, add_noise=True)[0], ref[0])
+    # a bare copy of the records is complete (what the reference's test_cleaning does)
+    posts = copy.deepcopy(gp.posteriors)
+    np.testing.assert_array_equal(posts[1].L, L0)
+    assert posts[1]._batch is None
