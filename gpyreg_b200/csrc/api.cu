@@ -274,8 +274,10 @@ static void launch_gemm(gpb_ctx* ctx, const Op& op, dim3 grid, const TmaOperands
   const int loader = pick_loader(ctx, ctas);
   if constexpr (std::is_same<Op, OpSyrk>::value) {
     // a trailing update of a few tiles sits on the dependent chain of a small batch (diag -> panel ->
-    // next column -> diag): quarter tiles put four CTAs on each, same arithmetic per element
-    if (two && ctx->quarter_tiles && ctas * 2 <= 2 * 148) {
+    // next column -> diag): quarter tiles put four CTAs on each, same arithmetic per element.  Only while
+    // the quarters still fit one per SM: with two matrices the early steps are bound by the trailing
+    // updates on the second stream, and more, smaller chain CTAs only queue behind them (measured)
+    if (two && ctx->quarter_tiles && ctas * 2 <= 148) {
       launch_shape<Op, 64, 64>(ctx, op, grid, loader, custom);
       return;
     }
@@ -307,7 +309,7 @@ static void launch_panel(gpb_ctx* ctx, const OpPanel& op, dim3 grid) {
   const int loader = pick_loader(ctx, ctas);
   // a panel of a few tiles sits on the dependent chain of a small batch: row quarters put four CTAs
   // on each tile (the fused forward-substitution sum is shape-independent, see gemm.cuh)
-  if (two && ctx->quarter_tiles && ctas * 2 <= 2 * 148) launch_shape<OpPanel, 32, 128>(ctx, op, grid, loader);
+  if (two && ctx->quarter_tiles && ctas * 2 <= 148) launch_shape<OpPanel, 32, 128>(ctx, op, grid, loader);
   else if (two) launch_shape<OpPanel, 64, 128>(ctx, op, grid, loader);
   else launch_shape<OpPanel, 128, 128>(ctx, op, grid, loader);
 }

@@ -125,7 +125,14 @@ class Posterior:
         return new
 
     def __deepcopy__(self, memo):
-        new = self._detached()
+        if self._batch is None and getattr(self, "_owner", None) is None:
+            # already a plain host record (possibly one of GP.__getstate__'s, with its factor left
+            # behind): copy it as it is
+            new = _posterior_from_state(np.array(self.hyp, copy=True),
+                                        {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in self._val.items()},
+                                        self._have, self._index)
+        else:
+            new = self._detached()
         memo[id(self)] = new
         return new
 
