@@ -71,9 +71,10 @@ struct gpb_ctx {
   int trtri_max = 8;         // env GPB_TRTRI_MAX
   int lookahead = 2;         // env GPB_LOOKAHEAD: 0 off, 1 batches <= 8 only, 2 always (default: -10 % at B=9, -4 % at B=32,
                              // neutral at B=64)
-  long long la_wide = 6000;  // env GPB_LA_WIDE: matrices x (remaining tile columns)^2 above which blocks stay wide
+  long long la_wide = 1500;  // env GPB_LA_WIDE: matrices x (remaining tile columns)^2 above which blocks stay wide
+                             // (re-swept in round 2 with the faster chain: profiles/r02_small_batch_latency.txt)
   int la_chunk = 1 << 30;    // logical tiles per look-ahead launch (env GPB_LA_CHUNK; measured: uncut is best)
-  int la_ob = 0;             // outer block used with look-ahead (env GPB_LA_OB; 0 = 1 for <= 2 matrices, else 2)
+  int la_ob = 2;             // narrow outer block used with look-ahead (env GPB_LA_OB; 0 = 1 for <= 2 matrices, else 2)
   std::string err;
   Model md{};
   bool has_model = false, has_data = false;

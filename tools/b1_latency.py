@@ -17,7 +17,7 @@ from gpyreg_b200.spec import ModelSpec  # noqa: E402
 
 eng = Engine(0)
 spec = ModelSpec(D=10, cov_kind=1, degree=5, ard=True, mean_kind=2)
-for N in (1000, 2000, 5000):
+for N in [int(v) for v in os.environ.get("NS", "1000,2000,5000").split(",")]:
     X, y = synth_data(N, spec.D, 0)
     eng.set_model(spec.cov_kind, spec.degree, spec.ard, spec.mean_kind, spec.noise_params)
     eng.set_data(X, y, None)
