@@ -47,6 +47,7 @@ SYMBOLS = {
     "gpb_debug_gemm_nt": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_double,
                                     C.c_double]),
     "gpb_debug_potrf": (C.c_int, [_vp, _vp, C.c_int, _vp]),
+    "gpb_debug_diag_bench": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "gpb_debug_gemm_bench": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     "gpb_last_timings": (C.c_int, [_vp, _vp]),
     "gpb_launch_count": (C.c_int64, [_vp]),

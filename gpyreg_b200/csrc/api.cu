@@ -428,7 +428,7 @@ extern "C" int gpb_create(int device, gpb_ctx** out) {
                 : (strcmp(ld, "tensor") == 0) ? 3 : 4;
   if (const char* ob = getenv("GPB_OUTER_BLOCK")) ctx->outer_block = std::max(1, atoi(ob));
   if (const char* nc = getenv("GPB_NLZ_CACHE")) ctx->cache_enabled = atoi(nc) != 0;
-  if (getenv("GPB_DIAG_DBG")) cudaMalloc(&ctx->diag_dbg, 40 * sizeof(long long));
+  if (getenv("GPB_DIAG_DBG")) cudaMalloc(&ctx->diag_dbg, 64 * sizeof(long long));
   for (auto& ev : ctx->ev) cudaEventCreate(&ev);
   int rc = init_attrs(ctx);
   if (rc != GPB_OK) {
@@ -2314,5 +2314,67 @@ extern "C" int gpb_debug_potrf(gpb_ctx* ctx, double* A, int n, int32_t* info) {
   for (int c = 0; c < n; ++c)
     for (int r = 0; r < n; ++r) A[(size_t)c * n + r] = (r >= c) ? pad[(size_t)c * Np + r] : 0.0;
   *info = failh;
+  return GPB_OK;
+}
+
+// Latency of the diagonal-tile kernel in a dependent chain: `reps` launches in stream order (no PDL), each
+// on its own copy of one SPD 128x128 tile.  us = average microseconds per launch (CUDA events).
+extern "C" int gpb_debug_diag_bench(gpb_ctx* ctx, int reps, int with_rhs, double* us) {
+  if (!ctx || !us || reps <= 0 || reps > 4096) return GPB_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  Model md{};
+  const int nz[3] = {1, 0, 0};
+  fill_model(md, 0, 0, 1, 0, nz, 1);
+  Bufs b;
+  int rc = alloc_bufs(ctx, b, reps, false, T, 1, md);
+  if (rc != GPB_OK) { free_bufs(b); return rc; }
+  std::vector<double> tile((size_t)T * T);
+  for (int c = 0; c < T; ++c)
+    for (int r = 0; r < T; ++r) tile[(size_t)c * T + r] = (r == c ? 2.0 : 0.0) + 0.5 / (1.0 + (r > c ? r - c : c - r));
+  std::vector<int> ident((size_t)reps);
+  for (int i = 0; i < reps; ++i) ident[i] = i;
+  cudaError_t e = cudaMemcpy(b.sel, ident.data(), sizeof(int) * reps, cudaMemcpyHostToDevice);
+  for (int i = 0; i < reps && e == cudaSuccess; ++i)
+    e = cudaMemcpy(b.Abuf + (size_t)i * T * T, tile.data(), sizeof(double) * T * T, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemset(b.fail, 0, sizeof(int) * reps);
+  if (e == cudaSuccess) e = cudaMemset(b.bvec, 0, sizeof(double) * T * reps);
+  const bool pdl0 = ctx->pdl;
+  ctx->pdl = false;
+  auto launch = [&](int s) {
+    DiagArgs da{};
+    da.Abuf = b.Abuf; da.Wbuf = nullptr; da.Dbuf = b.Dbuf; da.DTbuf = b.DTbuf;
+    da.sel = b.sel + s; da.smat = b.smat(); da.Np = T; da.Nt = 1; da.N = T; da.k = 0;
+    da.bvec = with_rhs ? b.bvec : nullptr; da.zvec = with_rhs ? b.zvec : nullptr;
+    da.logdet = b.logdet; da.fail = b.fail; da.dbg = ctx->diag_dbg;
+    launch_chain(ctx, diag_kernel, dim3(1), dim3(256), DIAG_SMEM, da);
+  };
+  if (e == cudaSuccess) {
+    for (int s = 0; s < std::min(reps, 4); ++s) launch(s);
+    cudaEventRecord(ctx->ev[6], ctx->stream);
+    for (int s = 0; s < reps; ++s) launch(s);
+    cudaEventRecord(ctx->ev[7], ctx->stream);
+    e = cudaStreamSynchronize(ctx->stream);
+  }
+  ctx->pdl = pdl0;
+  float ms = 0;
+  if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]);
+  int failh = 0;
+  if (e == cudaSuccess) e = cudaMemcpy(&failh, b.fail, sizeof(int), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && ctx->diag_dbg) {
+    long long st[33];
+    cudaMemcpy(st, ctx->diag_dbg, sizeof st, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "diag_kernel phase cycles:");
+    for (int i = 1; i < (int)st[0]; ++i) fprintf(stderr, " %lld", st[1 + i] - st[i]);
+    fprintf(stderr, "  total %lld\n", st[st[0]] - st[1]);
+    long long s0[24];
+    cudaMemcpy(s0, ctx->diag_dbg + 40, sizeof s0, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "factor warp (cycles since kernel start; begin/end of each block factorisation):");
+    for (int i = 0; i < (int)s0[0] && i < 16; ++i) fprintf(stderr, " %lld", s0[1 + i] - st[1]);
+    fprintf(stderr, "\n");
+  }
+  free_bufs(b);
+  if (e != cudaSuccess) FAIL(GPB_ECUDA, cudaGetErrorString(e));
+  if (failh) FAIL(GPB_ESTATE, "gpb_debug_diag_bench: the test tile did not factor");
+  *us = 1e3 * ms / reps;
   return GPB_OK;
 }

@@ -283,7 +283,13 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
   __shared__ int s_failed;
   __shared__ long long stamps[32];
   int nst = 0;
-#define STAMP() do { if (a.dbg && threadIdx.x == 0 && nst < 32) stamps[nst++] = clock64(); } while (0)
+  // stamped by warp 7 (not by the factor warp: a divergent branch in front of factor_block32 would send it
+  // down its slow not-converged path and distort what is being measured)
+#define STAMP() do { if (a.dbg && threadIdx.x == 224 && nst < 32) stamps[nst++] = clock64(); } while (0)
+  // second timeline, kept by the factor warp itself (explicitly re-converged before it goes on)
+  __shared__ long long stamps0[16];
+  int nst0 = 0;
+#define STAMP0() do { if (a.dbg) { if (threadIdx.x == 0 && nst0 < 16) stamps0[nst0++] = clock64(); __syncwarp(); } } while (0)
   STAMP();
   const int slot = a.sel[blockIdx.x];
   const int k = a.k, Np = a.Np;
@@ -351,9 +357,11 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
     }
     if (warp == 0) {
       if (p > 0) bar_arrive(3, 256);
+      STAMP0();
       // ---- the serial part: diagonal block p in registers, lane r owns row r (single call site: the
       // function is 40 KB of unrolled code)
       if (factor_block32(S, Iv + p * SB * IVP, Tm, c0, lane)) s_failed = 1;
+      STAMP0();
     } else if (p > 0) {
       bar_sync(3, 256);                                  // every panel row of block p-1 is written
       // warp 4 shares its scheduler with warp 0: it sits the overlap out so that the (issue-bound)
@@ -364,6 +372,7 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
       }
     }
     bar_sync(4, 256);
+    STAMP();
   }
   __syncthreads();
   STAMP();
@@ -590,10 +599,15 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
   __syncthreads();
   STAMP();
   if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) {
+    a.dbg[40] = nst0;
+    for (int i = 0; i < nst0; ++i) a.dbg[41 + i] = stamps0[i];
+  }
+  if (a.dbg && blockIdx.x == 0 && threadIdx.x == 224) {
     a.dbg[0] = nst;
     for (int i = 0; i < nst; ++i) a.dbg[1 + i] = stamps[i];
   }
 #undef STAMP
+#undef STAMP0
 }
 
 // z_k = D_k b_k on an existing factor (solve-only replay; same arithmetic as diag_kernel's tail)

@@ -256,6 +256,12 @@ class Engine:
         self._check(self.lib.gpb_debug_potrf(self._h, Af.ctypes.data, Af.shape[0], ptr(info)))
         return np.ascontiguousarray(Af), int(info[0])
 
+    def debug_diag_bench(self, reps=200, with_rhs=True):
+        """Microseconds per launch of the diagonal-tile kernel in a dependent chain."""
+        us = np.zeros(1)
+        self._check(self.lib.gpb_debug_diag_bench(self._h, int(reps), int(with_rhs), ptr(us)))
+        return float(us[0])
+
     def debug_gemm_bench(self, M, N, K, reps=10):
         ms = np.zeros(1)
         self._check(self.lib.gpb_debug_gemm_bench(self._h, M, N, K, reps, ptr(ms)))

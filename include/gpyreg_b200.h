@@ -161,6 +161,8 @@ int gpb_debug_gemm_nt(gpb_ctx* ctx, const double* A, const double* B, double* C,
 /* In-place lower Cholesky of a column-major (n,n) host matrix through the blocked
  * batched path (padding handled inside); info = 1 if a pivot was <= 0 or NaN. */
 int gpb_debug_potrf(gpb_ctx* ctx, double* A, int n, int32_t* info);
+/* Latency of the diagonal-tile kernel in a dependent chain of `reps` launches (microseconds per launch). */
+int gpb_debug_diag_bench(gpb_ctx* ctx, int reps, int with_rhs, double* us);
 /* Time `reps` launches of the tile GEMM on device-resident random data and return
  * the average ms per launch (CUDA events). */
 int gpb_debug_gemm_bench(gpb_ctx* ctx, int M, int N, int K, int reps, double* ms);
