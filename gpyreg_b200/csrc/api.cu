@@ -53,19 +53,6 @@ struct gpb_ctx {
   // block does not touch runs on `aux` while the main stream factors that block
   cudaStream_t aux = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  // Lanes: a batch of 2..MAX_LANES matrices (the speculative proposals of a slice-sampling move)
-  // is factored one matrix per lane, each lane with its own main/aux stream pair, so one matrix's
-  // diagonal-tile kernel (one CTA, the serial part) overlaps the other matrices' tile GEMMs
-  // instead of all matrices marching through the dependent chain in lock step.
-  static constexpr int MAX_LANES = 4;
-  struct Lane {
-    cudaStream_t main = nullptr, aux = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, done = nullptr;
-  } lane[MAX_LANES];
-  cudaEvent_t ev_lanes = nullptr;
-  int lanes = 0;             // env GPB_LANES: largest batch factored one matrix per lane.  Default off: measured on
-                             // B200 (profiles/r02_small_batch_latency.txt) it is neutral at N=5000 (the lock-step batch already
-                             // runs all diagonal tiles side by side) and 15-25 % slower at N <= 2000 (twice the launches)
   int trtri = 2;             // env GPB_TRTRI: 2 recursive halving (default; as fast as the recurrence for large
                              // batches, 4-5x faster for one matrix), 0 column recurrence, 1 recursive up to trtri_max
   int trtri_max = 8;         // env GPB_TRTRI_MAX
@@ -400,20 +387,6 @@ extern "C" int gpb_create(int device, gpb_ctx** out) {
     delete ctx;
     return GPB_ECUDA;
   }
-  for (auto& ln : ctx->lane) {
-    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ln.main, cudaStreamNonBlocking, prio_hi);
-    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ln.aux, cudaStreamNonBlocking, prio_lo);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ln.ev_fork, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ln.ev_join, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming);
-  }
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_lanes, cudaEventDisableTiming);
-  if (e != cudaSuccess) {
-    g_create_err = std::string("lane streams/events: ") + cudaGetErrorString(e);
-    delete ctx;
-    return GPB_ECUDA;
-  }
-  if (const char* ln = getenv("GPB_LANES")) ctx->lanes = std::min(atoi(ln), (int)gpb_ctx::MAX_LANES);
   if (const char* pd = getenv("GPB_PDL")) ctx->pdl = atoi(pd) != 0;
   if (const char* qt = getenv("GPB_QUARTER")) ctx->quarter_tiles = atoi(qt) != 0;
   if (const char* la = getenv("GPB_LOOKAHEAD")) ctx->lookahead = atoi(la);
@@ -482,14 +455,6 @@ extern "C" void gpb_destroy(gpb_ctx* ctx) {
     if (ev) cudaEventDestroy(ev);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
-  for (auto& ln : ctx->lane) {
-    if (ln.ev_fork) cudaEventDestroy(ln.ev_fork);
-    if (ln.ev_join) cudaEventDestroy(ln.ev_join);
-    if (ln.done) cudaEventDestroy(ln.done);
-    if (ln.aux) cudaStreamDestroy(ln.aux);
-    if (ln.main) cudaStreamDestroy(ln.main);
-  }
-  if (ctx->ev_lanes) cudaEventDestroy(ctx->ev_lanes);
   if (ctx->aux) cudaStreamDestroy(ctx->aux);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
@@ -1024,26 +989,8 @@ static int factor_with_retry(gpb_ctx* ctx, Bufs& b, const Model& md, long long N
   std::vector<int> cur = slots;
   for (int attempt = 0; attempt < 10; ++attempt) {
     NvtxRange nv(attempt == 0 ? "gpb:factor" : "gpb:factor (jitter retry)");
-    if (nsel >= 2 && nsel <= ctx->lanes) {
-      // one matrix per lane (see gpb_ctx::lane); every matrix sees exactly the launches of a
-      // one-matrix call, so the results are bit-identical to any other batching
-      cudaStream_t s0 = ctx->stream, a0 = ctx->aux;
-      cudaEvent_t f0 = ctx->ev_fork, j0 = ctx->ev_join;
-      CK(cudaEventRecord(ctx->ev_lanes, s0));
-      for (int m = 0; m < nsel; ++m) {
-        gpb_ctx::Lane& ln = ctx->lane[m];
-        CK(cudaStreamWaitEvent(ln.main, ctx->ev_lanes, 0));
-        ctx->stream = ln.main; ctx->aux = ln.aux; ctx->ev_fork = ln.ev_fork; ctx->ev_join = ln.ev_join;
-        run_prep_build(ctx, b, md, N, sel + m, 1);
-        run_potrf(ctx, b, N, sel + m, 1, write_w);
-        cudaEventRecord(ln.done, ln.main);
-      }
-      ctx->stream = s0; ctx->aux = a0; ctx->ev_fork = f0; ctx->ev_join = j0;
-      for (int m = 0; m < nsel; ++m) CK(cudaStreamWaitEvent(s0, ctx->lane[m].done, 0));
-    } else {
-      run_prep_build(ctx, b, md, N, sel, nsel);
-      run_potrf(ctx, b, N, sel, nsel, write_w);
-    }
+    run_prep_build(ctx, b, md, N, sel, nsel);
+    run_potrf(ctx, b, N, sel, nsel, write_w);
     CK(cudaGetLastError());                    // a refused launch must not pass for a result
     CK(cudaMemcpyAsync(failh.data(), b.fail, sizeof(int) * maxslot, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));

@@ -459,7 +459,6 @@ _TOGGLE_CACHE = {}
     ({"GPB_LOADER": "auto_bulk"}, True),                   # round-1 default
     ({"GPB_QUARTER": "0"}, True),                          # no 64x64 CTAs for the small trailing updates
     ({"GPB_PDL": "0"}, True),                              # ordinary launches instead of programmatic dependent launch
-    ({"GPB_LANES": "4"}, True),                            # small batches one matrix per lane instead of in lock step
     ({"GPB_TRTRI": "0"}, False),                           # column-recurrence triangular inverse
     ({"GPB_GEMM_BN": "128"}, False),                       # one CTA per tile: other reduction shapes
 ])
@@ -474,7 +473,7 @@ def test_schedule_toggles_do_not_change_results(env, exact):
 
     def run(extra):
         e = dict(os.environ)
-        for k in ("GPB_LOOKAHEAD", "GPB_LA_OB", "GPB_OUTER_BLOCK", "GPB_LOADER", "GPB_TRTRI", "GPB_GEMM_BN", "GPB_LANES", "GPB_PDL", "GPB_QUARTER"):
+        for k in ("GPB_LOOKAHEAD", "GPB_LA_OB", "GPB_OUTER_BLOCK", "GPB_LOADER", "GPB_TRTRI", "GPB_GEMM_BN", "GPB_PDL", "GPB_QUARTER"):
             e.pop(k, None)
         e.update(extra)
         root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
