@@ -320,6 +320,8 @@ static cudaError_t kind_attrs() {
   e = cudaFuncSetAttribute(grad_kernel<KIND, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, COV_SMEM_MAX);
   if (e) return e;
   e = cudaFuncSetAttribute(grad_kernel<KIND, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, COV_SMEM_MAX);
+  if (e) return e;
+  e = cudaFuncSetAttribute(grad_kernel<KIND, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, COV_SMEM_MAX);
   return e;
 }
 
@@ -527,7 +529,7 @@ extern "C" int gpb_set_model(gpb_ctx* ctx, int cov_kind, int matern_degree, int 
 extern "C" int gpb_set_data(gpb_ctx* ctx, const double* X, const double* y, const double* s2,
                             int64_t N, int D) {
   if (!ctx || !X || !y || N <= 0 || D <= 0) return GPB_EINVAL;
-  if (D > MAXD) FAIL(GPB_EINVAL, "gpb_set_data: D > 32 is not supported by the fused kernels");
+  if (D > MAXD) FAIL(GPB_EINVAL, "gpb_set_data: D > 64 is not supported by the fused kernels");
   if (N > 1000000) FAIL(GPB_EINVAL, "gpb_set_data: N too large");
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -916,14 +918,15 @@ static void run_inverse(gpb_ctx* ctx, Bufs& b, long long N, const int* sel, int 
 
 template <int KIND>
 static void launch_grad(gpb_ctx* ctx, const GradArgs& a, dim3 grid, int ard, int D) {
-  const int dp = !ard ? 0 : (D <= 8 ? 8 : (D <= 12 ? 12 : (D <= 16 ? 16 : 32)));
+  const int dp = !ard ? 0 : (D <= 8 ? 8 : (D <= 12 ? 12 : (D <= 16 ? 16 : (D <= 32 ? 32 : 64))));
   const size_t smem = ((size_t)2 * D * T + 2 * T + 8 * (size_t)((dp ? dp : 1) + 2)) * 8;
   switch (dp) {
     case 0: grad_kernel<KIND, 0><<<grid, 256, smem, ctx->stream>>>(a); break;
     case 8: grad_kernel<KIND, 8><<<grid, 256, smem, ctx->stream>>>(a); break;
     case 12: grad_kernel<KIND, 12><<<grid, 256, smem, ctx->stream>>>(a); break;
     case 16: grad_kernel<KIND, 16><<<grid, 256, smem, ctx->stream>>>(a); break;
-    default: grad_kernel<KIND, 32><<<grid, 256, smem, ctx->stream>>>(a); break;
+    case 32: grad_kernel<KIND, 32><<<grid, 256, smem, ctx->stream>>>(a); break;
+    default: grad_kernel<KIND, 64><<<grid, 256, smem, ctx->stream>>>(a); break;
   }
   LAUNCHED(ctx);
 }

@@ -7,7 +7,8 @@
 namespace gpb {
 
 constexpr int T = 128;          // tile edge of the blocked factorisation
-constexpr int MAXD = 32;        // max input dimension supported by the fused kernels
+constexpr int MAXD = 64;        // max input dimension supported by the fused kernels (staging tiles of 2*D*128
+                                // doubles in shared memory, one gradient accumulator per ARD length scale in registers)
 
 // Model descriptor: which plugin objects the GP was built from
 // (reference: gaussian_process.py:43-62).

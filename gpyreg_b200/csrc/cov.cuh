@@ -280,7 +280,7 @@ struct GradArgs {
 
 // four CTAs per SM up to 12 length scales (64 registers; measured against three: see DESIGN.md)
 template <int KIND, int DP>
-__global__ void __launch_bounds__(256, (DP <= 12 ? 4 : (DP <= 16 ? 3 : 2))) grad_kernel(GradArgs a) {
+__global__ void __launch_bounds__(256, (DP <= 12 ? 4 : (DP <= 16 ? 3 : (DP <= 32 ? 2 : 1)))) grad_kernel(GradArgs a) {
   extern __shared__ double bsm[];
   constexpr int NACC = (DP > 0 ? DP : 1) + 2;      // length scales | sf | rq shape
   const int slot = a.sel[blockIdx.y];

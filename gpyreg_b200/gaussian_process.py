@@ -186,7 +186,8 @@ class GP:
 
     SHARD_MIN_N = 512      # below this a factorisation is cheaper than the all-gather's latency
 
-    MAX_D = 32             # the fused kernels keep per-dimension accumulators in registers (csrc/common.cuh MAXD)
+    MAX_D = 64             # the fused kernels stage 2*D*128 doubles in shared memory and keep one gradient accumulator
+                           # per ARD length scale in registers (csrc/common.cuh MAXD)
 
     def __init__(self, D, covariance, mean, noise):
         if D > self.MAX_D:

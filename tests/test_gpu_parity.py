@@ -296,7 +296,7 @@ def test_batch_chunking_and_workspace_limit(eng):
 
 
 def test_predict_many_points_and_wide_inputs(eng):
-    """More test points than one chunk (8192) and the widest supported input (D = 32)."""
+    """More test points than one chunk (8192) and a wide input (D = 32)."""
     rng = np.random.default_rng(9)
     N, D = 150, 32
     X = rng.uniform(-1, 1, (N, D))
@@ -316,8 +316,8 @@ def test_predict_many_points_and_wide_inputs(eng):
     assert np.max(np.abs(mu - rmu)) <= TOL_PRED * (1 + np.max(np.abs(rmu)))
     assert np.max(np.abs(v - rv)) <= TOL_PRED * np.max(np.abs(rv))
     post.free()
-    with pytest.raises(Exception, match="D > 32"):
-        eng.set_data(np.zeros((4, 33)), np.zeros(4), None)
+    with pytest.raises(Exception, match="D > 64"):
+        eng.set_data(np.zeros((4, 65)), np.zeros(4), None)
 
 
 def test_runs_on_a_torch_stream(eng):
@@ -541,6 +541,43 @@ def test_seeded_fuzz_small_batches(eng, seed):
     posts1 = orc.posterior_batch(spec, hyp, X1, y1, None)
     mu, v = eng.predict(post, Xs, add_noise=True, separate=True)
     rmu, rv = orc.predict(spec, posts1, X1, y1, Xs, add_noise=True, separate_samples=True)
+    assert np.max(np.abs(mu - rmu)) <= TOL_PRED * (1 + np.max(np.abs(rmu)))
+    assert np.max(np.abs(v - rv)) <= TOL_PRED * np.max(np.abs(rv))
+    post.free()
+
+
+@pytest.mark.parametrize("D,cov_kind,mean_kind", [(40, 0, 2), (64, 1, 1), (64, 2, 0)])
+def test_wide_inputs_up_to_64_dimensions(eng, D, cov_kind, mean_kind):
+    """D > 32 (round-1 limit) up to the fused kernels' 64: nlZ, gradient (64 ARD length scales), posterior,
+    predictions, rank-one append and quadrature-free paths against the oracle."""
+    rng = np.random.default_rng(D + cov_kind)
+    N = 260
+    X = rng.uniform(-1, 1, (N, D))
+    y = (np.sin(X[:, :4].sum(1)) + 0.05 * rng.standard_normal(N)).reshape(-1, 1)
+    spec = orc.ModelSpec(D=D, cov_kind=cov_kind, degree=5 if cov_kind == 1 else 0, ard=True, mean_kind=mean_kind)
+    B = 2
+    cols = [np.log(3.0) + 0.2 * rng.standard_normal((B, D)), 0.1 * rng.standard_normal((B, 1))]
+    if cov_kind == 2:
+        cols.append(0.2 * rng.standard_normal((B, 1)))
+    cols.append(np.full((B, 1), np.log(0.1)))
+    if mean_kind >= 1:
+        cols.append(0.1 * rng.standard_normal((B, 1)))
+    if mean_kind == 2:
+        cols += [0.1 * rng.standard_normal((B, D)), np.log(3.0) + 0.1 * rng.standard_normal((B, D))]
+    hyp = np.concatenate(cols, axis=1)
+    assert hyp.shape[1] == spec.hyp_n
+    setup_engine(eng, spec, X[:-1], y[:-1], None)
+    nlz, dnlz, mult, status = eng.nlz_batch(hyp, want_grad=True)
+    ref_nlz, ref_dnlz = orc.nlz_batch(spec, hyp, X[:-1], y[:-1], None, True)
+    assert not status.any() and np.all(mult == 1)
+    assert rel_err(nlz, ref_nlz) <= TOL_NLZ and grad_err(dnlz, ref_dnlz) <= TOL_GRAD
+    post = eng.posterior_batch(hyp)
+    st = eng.posterior_append(post, X[-1], float(y[-1, 0]))
+    assert st is not None and not st.any()
+    Xs = rng.uniform(-1, 1, (300, D))
+    mu, v = eng.predict(post, Xs, add_noise=True, separate=True)
+    rmu, rv = orc.predict(spec, orc.posterior_batch(spec, hyp, X, y, None), X, y, Xs, add_noise=True,
+                          separate_samples=True)
     assert np.max(np.abs(mu - rmu)) <= TOL_PRED * (1 + np.max(np.abs(rmu)))
     assert np.max(np.abs(v - rv)) <= TOL_PRED * np.max(np.abs(rv))
     post.free()

@@ -329,14 +329,15 @@ def test_rng_rewind_paths(h, monkeypatch):
 
 
 def test_dimension_limit_is_reported_at_construction():
-    """D > 32 fails with a clear message when the GP is built, not at set_data."""
+    """a D beyond the fused kernels' limit (64) fails with a clear message when the GP is built,
+    not at set_data."""
     import gpyreg_b200 as g
     from gpyreg_b200.covariance_functions import SquaredExponential
     from gpyreg_b200.mean_functions import ZeroMean
     from gpyreg_b200.noise_functions import GaussianNoise
-    with pytest.raises(ValueError, match="D <= 32"):
-        g.GP(33, SquaredExponential(), ZeroMean(), GaussianNoise(constant_add=True))
-    g.GP(32, SquaredExponential(), ZeroMean(), GaussianNoise(constant_add=True))
+    with pytest.raises(ValueError, match="D <= 64"):
+        g.GP(65, SquaredExponential(), ZeroMean(), GaussianNoise(constant_add=True))
+    g.GP(64, SquaredExponential(), ZeroMean(), GaussianNoise(constant_add=True))
 
 
 def test_gp_copies_and_pickles_without_device_state():

@@ -1,8 +1,12 @@
 #!/bin/bash
-# quick validation: numerics subset + small-batch latency
+# quick validation: numerics subset + gradient kernel A/B
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q --timeout 600 -x -k "potrf or gemm_nt or core_golden or medium or tile_boundaries or fuzz or lownoise or toggles or factor_cache or robustness or design or fit_examples" 2>&1 | tail -4
-timeout 200 python tools/b1_latency.py 2>&1 | tee gpurun_out/b1_latency.log
-echo "GPB_GRAPH=0:"; GPB_GRAPH=0 NS=1000,5000 timeout 200 python tools/b1_latency.py 2>&1
-REPS=8 timeout 120 python tools/hit_once.py 2>&1 | tail -1
-timeout 300 python tools/mid_batch.py | tail -1
+timeout 900 python -m pytest tests -m gpu -q --timeout 600 -x -k "core_golden or medium or tile_boundaries or fuzz or lownoise or toggles or design or cfg2 or rq_iso" 2>&1 | tail -3
+for wl in cfg3 cfg2; do
+  timeout 300 python bench.py --workload $wl --no-cpu-baseline --steps 2 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('new', d['value'], d['roofline']['phase_ms_per_step']['gradient'])"
+  GPYREG_B200_LIB=$PWD/build/lib_grad4.so timeout 300 python bench.py --workload $wl --no-cpu-baseline --steps 2 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('old', d['value'], d['roofline']['phase_ms_per_step']['gradient'])"
+done
