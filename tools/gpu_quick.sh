@@ -1,12 +1,10 @@
 #!/bin/bash
-# quick validation: numerics subset + gradient kernel A/B
+# quick validation of a numerics subset + small/mid batch latency on one B200
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q --timeout 600 -x -k "core_golden or medium or tile_boundaries or fuzz or lownoise or toggles or design or cfg2 or rq_iso" 2>&1 | tail -3
-for wl in cfg3 cfg2; do
-  timeout 300 python bench.py --workload $wl --no-cpu-baseline --steps 2 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('new', d['value'], d['roofline']['phase_ms_per_step']['gradient'])"
-  GPYREG_B200_LIB=$PWD/build/lib_grad4.so timeout 300 python bench.py --workload $wl --no-cpu-baseline --steps 2 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('old', d['value'], d['roofline']['phase_ms_per_step']['gradient'])"
-done
+timeout 900 python -m pytest tests -m gpu -q --timeout 600 -x -k "potrf or core_golden or medium or tile_boundaries or fuzz or toggles or design or factor_cache or large_rq" 2>&1 | tail -4
+echo "banded (default):"; NS=2000,5000 timeout 200 python tools/b1_latency.py 2>&1
+timeout 300 python tools/mid_batch.py | tail -1
+echo "GPB_LA_BAND=0:"; GPB_LA_BAND=0 NS=2000,5000 timeout 200 python tools/b1_latency.py 2>&1
+GPB_LA_BAND=0 timeout 300 python tools/mid_batch.py | tail -1
+echo "GPB_LA_BAND=12:"; GPB_LA_BAND=12 NS=5000 timeout 200 python tools/b1_latency.py 2>&1
+echo "GPB_LA_BAND=16:"; GPB_LA_BAND=16 NS=5000 timeout 200 python tools/b1_latency.py 2>&1
