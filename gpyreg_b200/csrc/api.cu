@@ -87,6 +87,7 @@ struct gpb_ctx {
     long long hits = 0, misses = 0;
   } cache;
   bool cache_enabled = true;    // env GPB_NLZ_CACHE=0 disables
+  bool grad_rows = true;        // env GPB_GRAD_ROWS=0: gradient by grad_kernel for every shape (A/B)
   double timings[6] = {0, 0, 0, 0, 0, 0};
   long long launches = 0;
   cudaEvent_t ev[8] = {};
@@ -403,6 +404,7 @@ extern "C" int gpb_create(int device, gpb_ctx** out) {
                 : (strcmp(ld, "tensor") == 0) ? 3 : 4;
   if (const char* ob = getenv("GPB_OUTER_BLOCK")) ctx->outer_block = std::max(1, atoi(ob));
   if (const char* nc = getenv("GPB_NLZ_CACHE")) ctx->cache_enabled = atoi(nc) != 0;
+  if (const char* gr = getenv("GPB_GRAD_ROWS")) ctx->grad_rows = atoi(gr) != 0;
   if (getenv("GPB_DIAG_DBG")) cudaMalloc(&ctx->diag_dbg, 64 * sizeof(long long));
   for (auto& ev : ctx->ev) cudaEventCreate(&ev);
   int rc = init_attrs(ctx);
@@ -916,8 +918,23 @@ static void run_inverse(gpb_ctx* ctx, Bufs& b, long long N, const int* sel, int 
   if (syrk2) launch_gemm(ctx, OpSyrk2{bb}, dim3((unsigned)(Nt * (Nt + 1) / 2), (unsigned)nsel));
 }
 
+template <int KIND, int DP>
+static void launch_grad_rows(gpb_ctx* ctx, const GradArgs& a, dim3 grid) {
+  const size_t smem = ((size_t)T * (DP + 2) + 8 * (size_t)(DP + 2)) * 8;
+  grad_rows_kernel<KIND, DP><<<grid, 256, smem, ctx->stream>>>(a);
+  LAUNCHED(ctx);
+}
+
 template <int KIND>
 static void launch_grad(gpb_ctx* ctx, const GradArgs& a, dim3 grid, int ard, int D) {
+  if (ard && D <= 16 && ctx->grad_rows) {          // row-per-thread form (cov.cuh)
+    if (D <= 4) return launch_grad_rows<KIND, 4>(ctx, a, grid);
+    if (D <= 6) return launch_grad_rows<KIND, 6>(ctx, a, grid);
+    if (D <= 8) return launch_grad_rows<KIND, 8>(ctx, a, grid);
+    if (D <= 10) return launch_grad_rows<KIND, 10>(ctx, a, grid);
+    if (D <= 12) return launch_grad_rows<KIND, 12>(ctx, a, grid);
+    return launch_grad_rows<KIND, 16>(ctx, a, grid);
+  }
   const int dp = !ard ? 0 : (D <= 8 ? 8 : (D <= 12 ? 12 : (D <= 16 ? 16 : (D <= 32 ? 32 : 64))));
   const size_t smem = ((size_t)2 * D * T + 2 * T + 8 * (size_t)((dp ? dp : 1) + 2)) * 8;
   switch (dp) {

@@ -386,6 +386,186 @@ __global__ void __launch_bounds__(256, (DP <= 12 ? 4 : (DP <= 16 ? 3 : (DP <= 32
   }
 }
 
+// ---------------------------------------------------------------------------------
+// K3, row-per-thread form (ARD with D <= 16: the shapes a fit spends its time in).
+// grad_kernel above re-reads its 4 rows' coordinates from shared memory for every column and
+// evaluates the radial function inside divergent regions (the library sqrt/exp carry slow-path
+// branches, so the four pairs of a round never overlap): 25 shared loads and ~95 FP64 instructions
+// per pair, FP64 pipe 48-52 % busy.  Here a thread owns ONE row of the tile: its D coordinates live
+// in registers, a column's coordinates (and alpha_j) are one contiguous, warp-uniform run in shared
+// memory (broadcast 128-bit loads: D/2+1 per pair), the squared differences are kept from the
+// distance sum for the length-scale accumulators (4 FP64 instructions per dimension instead of 5),
+// and the radial functions are branch-free (below), so the whole pair is one basic block.
+// Masked pairs (upper triangle of a diagonal tile, padding) run with Q = 0.  sf^2 and the factor 2
+// of dK/dlog(sf) are applied once per tile after the reduction.
+// ---------------------------------------------------------------------------------
+
+// exp(x) for x <= 0 without a slow path: Cody-Waite reduction by ln2 (hi/lo), degree-12 Taylor
+// polynomial on |r| <= ln2/2 (truncation 1.7e-16), 2^n added into the exponent field.  Arguments below
+// -708 are evaluated at -708 (3e-308 instead of a denormal or 0: nothing downstream can tell at the
+// gradient tolerance); NaN stays NaN.
+__constant__ double EXP_C[16] = {
+    1.4426950408889634, 6755399441055744.0 /* 1.5 * 2^52 */, -6.93147180559945286e-01, -2.31904681384629956e-17,
+    2.08767569878680990e-09 /* 1/12! */, 2.50521083854417188e-08, 2.75573192239858907e-07,
+    2.75573192239858907e-06, 2.48015873015873016e-05, 1.98412698412698413e-04, 1.38888888888888889e-03,
+    8.33333333333333333e-03, 4.16666666666666667e-02, 1.66666666666666667e-01, 0.5, 1.0};
+// (the constants sit in constant memory so that each is an operand of its FMA: as immediates the
+// compiler rebuilt them with two uniform moves per use, 22 extra issue slots per pair)
+__device__ __forceinline__ double exp_nonpos(double x) {
+  x = (x < -708.0) ? -708.0 : x;
+  const double t = fma(x, EXP_C[0], EXP_C[1]);
+  const int n = __double2loint(t);
+  const double nf = t - EXP_C[1];
+  double r = fma(nf, EXP_C[2], x);
+  r = fma(nf, EXP_C[3], r);
+  double p = EXP_C[4];
+#pragma unroll
+  for (int q = 5; q < 16; ++q) p = fma(p, r, EXP_C[q]);
+  p = fma(p, r, EXP_C[15]);
+  return __hiloint2double(__double2hiint(p) + (int)((unsigned)n << 20), __double2loint(p));
+}
+
+// s = sqrt(x), rinv = 1/sqrt(x) for x >= 0 without a slow path: hardware seed (2^-22), two coupled
+// Goldschmidt steps.  x = 0 gives s = 0, rinv = +inf.
+__device__ __forceinline__ void sqrt_rsqrt_nonneg(double x, double& s, double& rinv) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double g = x * y, h = 0.5 * y;
+  double r = fma(-g, h, 0.5);
+  g = fma(g, r, g);
+  h = fma(h, r, h);
+  r = fma(-g, h, 0.5);
+  g = fma(g, r, g);
+  h = fma(h, r, h);
+  const bool zero = (__double2hiint(x) | __double2loint(x)) == 0;
+  s = zero ? 0.0 : g;
+  rinv = zero ? __longlong_as_double(0x7ff0000000000000LL) : 2.0 * h;
+}
+
+// radial factors WITHOUT sf^2:  K = sf2*kf,  dK/dlog(ell_k) = sf2*cf*Delta_k^2,  dK/dlog(shape) = sf2*sh
+template <int KIND>
+__device__ __forceinline__ void radial_factors(double r2, double a_rq, double half_over_a,
+                                               double& kf, double& cf, double& sh) {
+  sh = 0.0;
+  if (KIND == 0) {
+    kf = exp_nonpos(-0.5 * r2);
+    cf = kf;
+  } else if (KIND == 2) {
+    const double Mq = fma(r2, half_over_a, 1.0);
+    const double lg = log(Mq);
+    kf = exp(-a_rq * lg);
+    cf = kf / Mq;
+    sh = kf * (0.5 * r2 / Mq - a_rq * lg);
+  } else {
+    double r, rinv;
+    sqrt_rsqrt_nonneg(r2, r, rinv);
+    const double e = exp_nonpos(-r);
+    if (KIND == 1) { kf = e; cf = rinv * e; }                       // inf at r = 0, as the reference
+    else if (KIND == 3) { kf = fma(r, e, e); cf = e; }
+    else {
+      const double third = 1.0 / 3;
+      kf = fma(r, fma(r, third, 1.0), 1.0) * e;
+      cf = fma(r, third, third) * e;
+    }
+  }
+}
+
+template <int KIND, int DP>
+__global__ void __launch_bounds__(256, (DP <= 6 ? 3 : 2)) grad_rows_kernel(GradArgs a) {
+  extern __shared__ double bsm[];
+  constexpr int NACC = DP + 2;                     // length scales | sf | rq shape
+  constexpr int S = DP + 2;                        // shared row: DP coordinates, alpha_j, pad (16-byte rows)
+  const int slot = a.sel[blockIdx.y];
+  int ti, tj;
+  tri_decode(blockIdx.x, ti, tj);
+  const int D = a.D, Np = a.Np, N = a.N;
+  double* xcs = bsm;                               // [128][S]
+  double* red = bsm + T * S;                       // [8][NACC]
+  const double* xs = a.xs + (long long)slot * D * Np;
+  const double* alpha = a.alpha + (long long)slot * Np;
+  for (int e = threadIdx.x; e < DP * T; e += blockDim.x) {
+    const int k = e / T, j = e % T;
+    xcs[j * S + k] = (k < D) ? xs[(long long)k * Np + tj * T + j] : 0.0;
+  }
+  if (threadIdx.x < T) {
+    xcs[threadIdx.x * S + DP] = alpha[tj * T + threadIdx.x];
+    xcs[threadIdx.x * S + DP + 1] = 0.0;
+  }
+  const int il = threadIdx.x & (T - 1), half = threadIdx.x >> 7;
+  const int gi = ti * T + il;
+  double xr[DP];
+#pragma unroll
+  for (int k = 0; k < DP; ++k) xr[k] = (k < D) ? xs[(long long)k * Np + gi] : 0.0;
+  const double ar = alpha[gi];
+  const SlotP p = a.sp[slot];
+  const double inv_sl = 1.0 / p.sl;
+  const double half_over_a = 0.5 / p.rq_a;
+  __syncthreads();
+
+  // columns this warp visits: its half of the tile, cut at N and (diagonal tile) at its last row
+  const bool diag = (ti == tj);
+  const int j0 = half * 64;
+  int jend = min(64, N - tj * T - j0);
+  if (diag) jend = min(jend, (il | 31) + 1 - j0);
+  const bool rowok = gi < N;
+  const double* Acol = a.Abuf + slot * a.smat + (long long)(tj * T + j0) * Np + gi;
+
+  double acc[NACC];
+#pragma unroll
+  for (int q = 0; q < NACC; ++q) acc[q] = 0.0;
+
+  double av = (jend > 0) ? Acol[0] : 0.0;
+  for (int jj = 0; jj < jend; ++jj) {
+    const int jl = j0 + jj;
+    const double avn = Acol[(long long)min(jj + 1, 63) * Np];      // next column's element, early
+    const double2* xc2 = reinterpret_cast<const double2*>(xcs + jl * S);
+    double d2[DP];
+#pragma unroll
+    for (int k = 0; k < DP; k += 2) {
+      const double2 c = xc2[k / 2];
+      const double da = xr[k] - c.x, db = xr[k + 1] - c.y;
+      d2[k] = da * da;
+      d2[k + 1] = db * db;
+    }
+    const double ac = xcs[jl * S + DP];
+    double r2 = d2[0];
+#pragma unroll
+    for (int k = 1; k < DP; ++k) r2 += d2[k];
+    double kf, cf, sh;
+    radial_factors<KIND>(r2, p.rq_a, half_over_a, kf, cf, sh);
+    double Q = fma(av, inv_sl, -(ar * ac));                         // gaussian_process.py:2477-2484
+    if (diag && il == jl) Q *= 0.5;
+    const bool valid = rowok && (!diag || il >= jl);
+    Q = valid ? Q : 0.0;
+    acc[NACC - 2] = fma(Q, kf, acc[NACC - 2]);
+    if (KIND == 2) acc[NACC - 1] = fma(Q, sh, acc[NACC - 1]);
+    double cw = Q * cf;
+    if (KIND == 1) cw = valid ? cw : 0.0;                           // cf = inf on masked r = 0 pairs
+#pragma unroll
+    for (int k = 0; k < DP; ++k) acc[k] = fma(cw, d2[k], acc[k]);
+    av = avn;
+  }
+  // deterministic reduction: warp xor-tree, then warps in order
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < NACC; ++q) {
+    double v = acc[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp * NACC + q] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < a.cov_n) {
+    const int pidx = threadIdx.x;
+    const int q = (pidx < D) ? pidx : (pidx == D ? NACC - 2 : NACC - 1);
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += red[w * NACC + q];
+    s *= (pidx == D) ? 2 * p.sf2 : p.sf2;                           // dK/dlog(sf) = 2K
+    const long long ntiles = (long long)a.Nt * (a.Nt + 1) / 2;
+    a.gpart[((long long)slot * ntiles + blockIdx.x) * a.cov_n + pidx] = s;
+  }
+}
+
 struct GradFinalArgs {
   Model md;
   int N, Np, Nt;

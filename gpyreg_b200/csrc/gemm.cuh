@@ -49,6 +49,12 @@ struct GemmTile {
   int K;
   int b_alt;                          // LOADER 2: B lives in the launch's alternate B array (TmaOperands::b_alt)
   int mvalid, nvalid;                 // rows / columns of the 128x128 tile that hold data (rest is padding)
+  // Triangular operand tiles (the diagonal tiles D_k, D_k^T, W_ii): the K steps in which a warp's rows or
+  // columns only meet the stored zeros of the triangle are skipped (adding 0 * x changes no bit).
+  //   tri_lo bit 0: first tile (k < T), operand zero for k < m;  bit 1: zero for k < n
+  //   hi_m_off / hi_n_off >= 0: in the tile that starts at this k offset the operand is zero for
+  //   k - off > m  /  k - off > n
+  int tri_lo, hi_m_off, hi_n_off;
   double alpha, cscale;               // result = alpha * (cscale * C + A B^T); cscale = beta / alpha
   bool valid;
 };
@@ -190,9 +196,26 @@ gemm_nt_kernel(const __grid_constant__ Op op, const __grid_constant__ typename T
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, tq = lane & 3;
-  const int wm = (warp % MW) * 32, wn = (warp / MW) * WN;
+  // warp -> sub-tile: warps w and w+4 share a scheduler; the second four are permuted so that a scheduler's
+  // two warps sit at opposite ends of the tile -- with a triangular operand one of them skips many K steps,
+  // the other few, and every scheduler ends up with the same amount of DMMA work
+  const int lw = (warp < 4) ? warp : ((MW == 2) ? (warp ^ 2) : 11 - warp);
+  const int wm = (lw % MW) * 32, wn = (lw / MW) * WN;
   const int KT = t.K / BK;
   const bool wact = (wm < mv) && (wn < nv);
+  // K steps this warp needs [klo, khi) and this CTA loads [cklo, ckhi)
+  int klo = 0, khi = KT, cklo = 0, ckhi = KT;
+  if (t.tri_lo & 1) { klo = (hm * BM_ + wm) / BK; cklo = hm * BM_ / BK; }
+  if (t.tri_lo & 2) { klo = max(klo, (hn * BN_ + wn) / BK); cklo = max(cklo, hn * BN_ / BK); }
+  if (t.hi_m_off >= 0) {
+    khi = min(khi, (t.hi_m_off + hm * BM_ + wm + 32) / BK);
+    ckhi = min(ckhi, (t.hi_m_off + (hm + 1) * BM_) / BK);
+  }
+  if (t.hi_n_off >= 0) {
+    khi = min(khi, (t.hi_n_off + hn * BN_ + wn + WN) / BK);
+    ckhi = min(ckhi, (t.hi_n_off + (hn + 1) * BN_) / BK);
+  }
+  const int KT2 = max(ckhi - cklo, 0);                // K steps of this CTA; step `it` is k tile cklo + it
 
   auto load_stage = [&](int kt, int stage) {
     const int k0 = kt * BK;
@@ -278,12 +301,12 @@ gemm_nt_kernel(const __grid_constant__ Op op, const __grid_constant__ typename T
     __syncthreads();
     if (warp == 0) {
       for (int s = 0; s < NSTAGE - 1; ++s)
-        if (s < KT) { if (LOADER == 2) tma_stage(s, s); else bulk_stage(s, s); }
+        if (s < KT2) { if (LOADER == 2) tma_stage(cklo + s, s); else bulk_stage(cklo + s, s); }
     }
   } else {
 #pragma unroll
     for (int s = 0; s < NSTAGE - 1; ++s) {
-      if (s < KT) load_stage(s, s);
+      if (s < KT2) load_stage(cklo + s, s);
       cp_async_commit();
     }
   }
@@ -309,26 +332,27 @@ gemm_nt_kernel(const __grid_constant__ Op op, const __grid_constant__ typename T
       for (int ni = 0; ni < NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
   }
 
-  for (int kt = 0; kt < KT; ++kt) {
+  for (int it = 0; it < KT2; ++it) {
+    const int kt = cklo + it;
     if (LOADER >= 1) {
-      const int nk = kt + NSTAGE - 1;
-      if (warp == 0 && nk < KT) {
+      const int nk = it + NSTAGE - 1;
+      if (warp == 0 && nk < KT2) {
         const int ns = nk % NSTAGE;
-        // the slot was last read in iteration kt-1: wait until all 8 warps have released it
+        // the slot was last read in iteration it-1: wait until all 8 warps have released it
         if (nk >= NSTAGE) mbar_wait(empty_bar + ns, ((nk / NSTAGE) - 1) & 1);
-        if (LOADER == 2) tma_stage(nk, ns); else bulk_stage(nk, ns);
+        if (LOADER == 2) tma_stage(cklo + nk, ns); else bulk_stage(cklo + nk, ns);
       }
-      mbar_wait(full_bar + (kt % NSTAGE), (kt / NSTAGE) & 1);
+      mbar_wait(full_bar + (it % NSTAGE), (it / NSTAGE) & 1);
     } else {
       cp_async_wait<NSTAGE - 2>();
       __syncthreads();
-      const int nk = kt + NSTAGE - 1;
-      if (nk < KT) load_stage(nk, nk % NSTAGE);
+      const int nk = it + NSTAGE - 1;
+      if (nk < KT2) load_stage(cklo + nk, nk % NSTAGE);
       cp_async_commit();
     }
-    const double* as = As + (kt % NSTAGE) * BK * PA;
-    const double* bs = Bs + (kt % NSTAGE) * BK * PB;
-    if (wact) {
+    const double* as = As + (it % NSTAGE) * BK * PA;
+    const double* bs = Bs + (it % NSTAGE) * BK * PB;
+    if (wact && kt >= klo && kt < khi) {
 #pragma unroll
       for (int k4 = 0; k4 < BK / 4; ++k4) {
         double a[4], b[NI];
@@ -344,7 +368,7 @@ gemm_nt_kernel(const __grid_constant__ Op op, const __grid_constant__ typename T
     }
     if (LOADER >= 1) {                       // this warp is done with the slot
       __syncwarp();
-      if (lane == 0) mbar_arrive(empty_bar + (kt % NSTAGE));
+      if (lane == 0) mbar_arrive(empty_bar + (it % NSTAGE));
     }
   }
   if (LOADER == 0) cp_async_wait<0>();
@@ -369,7 +393,7 @@ gemm_nt_kernel(const __grid_constant__ Op op, const __grid_constant__ typename T
       }
       s += __shfl_xor_sync(0xffffffffu, s, 1);
       s += __shfl_xor_sync(0xffffffffu, s, 2);
-      if (tq == 0) red[(warp / MW) * BM_ + m] = s;
+      if (tq == 0) red[(lw / MW) * BM_ + m] = s;
     }
     __syncthreads();
     if (tid < BM_) {
@@ -523,6 +547,8 @@ __device__ __forceinline__ GemmTile empty_tile() {
   t.b_alt = 0;
   t.mvalid = BM;
   t.nvalid = BN;
+  t.tri_lo = 0;
+  t.hi_m_off = t.hi_n_off = -1;
   t.alpha = 1.0;
   t.cscale = 0.0;
   t.valid = true;
@@ -586,6 +612,7 @@ struct OpPanel {
     t.B = b.Dbuf + ((long long)slot * b.Nt + k) * T * T; t.ldb = T;
     t.C = tile; t.ldc = b.Np;
     t.K = T;
+    t.hi_n_off = 0;                        // D_k(n, q) = 0 for q > n
     t.mvalid = b.N - i * T;
     if (zvec) {
       t.vdot = zvec + (long long)slot * b.Np + (long long)k * T;
@@ -755,6 +782,7 @@ struct OpRecX {
     t.B0 = b.DTbuf + ((long long)slot * b.Nt + j) * T * T; t.ldb0 = T;      // W(j,j)^T = D_j^T
     t.Ct = A + (long long)j * T + (long long)i * T * b.Np; t.ldct = b.Np;
     t.K = min((mid - j) * T, b.n16() - j * T);
+    t.tri_lo = 2;                          // first K tile: D_j^T(n, q) = 0 for q < n
     return t;
   }
 };
@@ -778,6 +806,7 @@ struct OpRecW {
     t.C = W + (long long)i * T + (long long)j * T * b.Np; t.ldc = b.Np;
     t.Ct = W + (long long)j * T + (long long)i * T * b.Np; t.ldct = b.Np;
     t.K = min((i - mid + 1) * T, b.n16() - mid * T); t.alpha = -1.0;
+    t.hi_m_off = (i - mid) * T;            // last K tile: W(i,i)(m, q) = D_i(m, q) = 0 for q > m
     return t;
   }
 };
@@ -800,6 +829,7 @@ struct OpSyrk2 {
     t.B = W + (long long)c * T + (long long)a * T * b.Np; t.ldb = b.Np;
     t.A0 = DTa; t.lda0 = T;
     if (a == c) { t.B0 = DTa; t.ldb0 = T; }
+    t.tri_lo = (a == c) ? 3 : 1;           // first K tile: D_a^T(m, q) = 0 for q < m (and for q < n on the diagonal)
     t.C = b.Abuf + slot * b.smat + (long long)a * T + (long long)c * T * b.Np; t.ldc = b.Np;
     t.K = min((b.Nt - a) * T, b.n16() - a * T);
     t.mvalid = b.N - a * T;
@@ -833,6 +863,7 @@ struct OpPred {
     t.b_alt = tri ? 0 : 1;
     const int n16 = (N + BK - 1) / BK * BK;
     t.K = tri ? min((nt + 1) * T, n16) : n16;
+    if (tri) t.hi_n_off = nt * T;            // last K tile: the diagonal tile of W, zero for k > m
     t.mvalid = mc - jt * BM;
     t.nvalid = N - nt * BN;
     if (!tri) { t.E = bt + (long long)jt * BM + (long long)nt * BN * ldbt; t.lde = ldbt; }
