@@ -475,6 +475,7 @@ __global__ void __launch_bounds__(256, (DP <= 6 ? 3 : 2)) grad_rows_kernel(GradA
   extern __shared__ double bsm[];
   constexpr int NACC = DP + 2;                     // length scales | sf | rq shape
   constexpr int S = DP + 2;                        // shared row: DP coordinates, alpha_j, pad (16-byte rows)
+  constexpr int PF = (DP <= 6) ? 4 : 6;            // Ainv loads in flight per warp
   const int slot = a.sel[blockIdx.y];
   int ti, tj;
   tri_decode(blockIdx.x, ti, tj);
@@ -514,10 +515,7 @@ __global__ void __launch_bounds__(256, (DP <= 6 ? 3 : 2)) grad_rows_kernel(GradA
 #pragma unroll
   for (int q = 0; q < NACC; ++q) acc[q] = 0.0;
 
-  double av = (jend > 0) ? Acol[0] : 0.0;
-  for (int jj = 0; jj < jend; ++jj) {
-    const int jl = j0 + jj;
-    const double avn = Acol[(long long)min(jj + 1, 63) * Np];      // next column's element, early
+  auto pair = [&](const int jl, const double av) {
     const double2* xc2 = reinterpret_cast<const double2*>(xcs + jl * S);
     double d2[DP];
 #pragma unroll
@@ -543,7 +541,22 @@ __global__ void __launch_bounds__(256, (DP <= 6 ? 3 : 2)) grad_rows_kernel(GradA
     if (KIND == 1) cw = valid ? cw : 0.0;                           // cf = inf on masked r = 0 pairs
 #pragma unroll
     for (int k = 0; k < DP; ++k) acc[k] = fma(cw, d2[k], acc[k]);
-    av = avn;
+  };
+  // The elements of Ainv arrive one 256-byte row segment per warp and column, PF loads in flight per warp.
+  // The column loop is unrolled PF times so that every slot of the ring is a fixed register that is
+  // re-loaded right after it has been consumed: a rotating ring (or a single look-ahead element) is
+  // implemented with register moves FROM the load's destination, which wait for the load -- ncu showed
+  // 32 % of all stall samples on that move and the same run time with or without the look-ahead.
+  double ring[PF];
+#pragma unroll
+  for (int u = 0; u < PF; ++u) ring[u] = (jend > 0) ? Acol[(long long)u * Np] : 0.0;
+  for (int jj = 0; jj < jend; jj += PF) {
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      const double av = ring[u];
+      ring[u] = Acol[(long long)min(jj + u + PF, 63) * Np];          // unconditional: the slot IS the destination
+      if (jj + u < jend) pair(j0 + jj + u, av);                      // warp-uniform
+    }
   }
   // deterministic reduction: warp xor-tree, then warps in order
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

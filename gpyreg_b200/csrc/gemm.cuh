@@ -55,6 +55,9 @@ struct GemmTile {
   //   hi_m_off / hi_n_off >= 0: in the tile that starts at this k offset the operand is zero for
   //   k - off > m  /  k - off > n
   int tri_lo, hi_m_off, hi_n_off;
+  // diagonal output tile of a symmetric result (potrf trailing update, W^T W): only its lower triangle is ever
+  // read, so the warps whose 32 x WN block lies strictly above the diagonal sit the product out
+  int lower_only;
   double alpha, cscale;               // result = alpha * (cscale * C + A B^T); cscale = beta / alpha
   bool valid;
 };
@@ -190,6 +193,7 @@ gemm_nt_kernel(const __grid_constant__ Op op, const __grid_constant__ typename T
   const int nv = t.nvalid - hn * BN_;
   const int mv = t.mvalid - hm * BM_;
   if (!(MODE & GM_REDUCE) && (mv <= 0 || nv <= 0)) return;
+  if (t.lower_only && (hm + 1) * BM_ <= hn * BN_) return;      // this part of a diagonal tile is all above the diagonal
 
   double* As = gsm;
   double* Bs = gsm + NSTAGE * BK * PA;
@@ -202,7 +206,7 @@ gemm_nt_kernel(const __grid_constant__ Op op, const __grid_constant__ typename T
   const int lw = (warp < 4) ? warp : ((MW == 2) ? (warp ^ 2) : 11 - warp);
   const int wm = (lw % MW) * 32, wn = (lw / MW) * WN;
   const int KT = t.K / BK;
-  const bool wact = (wm < mv) && (wn < nv);
+  const bool wact = (wm < mv) && (wn < nv) && !(t.lower_only && hm * BM_ + wm + 32 <= hn * BN_ + wn);
   // K steps this warp needs [klo, khi) and this CTA loads [cklo, ckhi)
   int klo = 0, khi = KT, cklo = 0, ckhi = KT;
   if (t.tri_lo & 1) { klo = (hm * BM_ + wm) / BK; cklo = hm * BM_ / BK; }
@@ -549,6 +553,7 @@ __device__ __forceinline__ GemmTile empty_tile() {
   t.nvalid = BN;
   t.tri_lo = 0;
   t.hi_m_off = t.hi_n_off = -1;
+  t.lower_only = 0;
   t.alpha = 1.0;
   t.cscale = 0.0;
   t.valid = true;
@@ -707,6 +712,7 @@ struct OpSyrk {
     t.K = kw * T; t.alpha = -1.0; t.cscale = -1.0;
     t.mvalid = b.N - i * T;
     t.nvalid = b.N - j * T;
+    t.lower_only = (i == j);
     return t;
   }
 };
@@ -829,6 +835,7 @@ struct OpSyrk2 {
     t.B = W + (long long)c * T + (long long)a * T * b.Np; t.ldb = b.Np;
     t.A0 = DTa; t.lda0 = T;
     if (a == c) { t.B0 = DTa; t.ldb0 = T; }
+    t.lower_only = (a == c);
     t.tri_lo = (a == c) ? 3 : 1;           // first K tile: D_a^T(m, q) = 0 for q < m (and for q < n on the diagonal)
     t.C = b.Abuf + slot * b.smat + (long long)a * T + (long long)c * T * b.Np; t.ldc = b.Np;
     t.K = min((b.Nt - a) * T, b.n16() - a * T);
