@@ -400,9 +400,9 @@ __global__ void __launch_bounds__(256, (DP <= 12 ? 4 : (DP <= 16 ? 3 : (DP <= 32
 // of dK/dlog(sf) are applied once per tile after the reduction.
 // ---------------------------------------------------------------------------------
 
-// exp(x) for x <= 0 without a slow path: Cody-Waite reduction by ln2 (hi/lo), degree-12 Taylor
-// polynomial on |r| <= ln2/2 (truncation 1.7e-16), 2^n added into the exponent field.  Arguments below
-// -708 are evaluated at -708 (3e-308 instead of a denormal or 0: nothing downstream can tell at the
+// exp(-x) for x >= 0 without a slow path: Cody-Waite reduction by ln2 (hi/lo), degree-12 Taylor
+// polynomial on |r| <= ln2/2 (truncation 1.7e-16), 2^n added into the exponent field.  Arguments above
+// 708 are evaluated at 708 (3e-308 instead of a denormal or 0: nothing downstream can tell at the
 // gradient tolerance); NaN stays NaN.
 __constant__ double EXP_C[16] = {
     1.4426950408889634, 6755399441055744.0 /* 1.5 * 2^52 */, -6.93147180559945286e-01, -2.31904681384629956e-17,
@@ -411,12 +411,13 @@ __constant__ double EXP_C[16] = {
     8.33333333333333333e-03, 4.16666666666666667e-02, 1.66666666666666667e-01, 0.5, 1.0};
 // (the constants sit in constant memory so that each is an operand of its FMA: as immediates the
 // compiler rebuilt them with two uniform moves per use, 22 extra issue slots per pair)
-__device__ __forceinline__ double exp_nonpos(double x) {
-  x = (x < -708.0) ? -708.0 : x;
-  const double t = fma(x, EXP_C[0], EXP_C[1]);
+// exp(-x) for x >= 0
+__device__ __forceinline__ double exp_neg(double x) {
+  x = (x > 708.0) ? 708.0 : x;
+  const double t = fma(x, -EXP_C[0], EXP_C[1]);
   const int n = __double2loint(t);
-  const double nf = t - EXP_C[1];
-  double r = fma(nf, EXP_C[2], x);
+  const double nf = t - EXP_C[1];                 // -round(x / ln 2)
+  double r = fma(nf, EXP_C[2], -x);
   r = fma(nf, EXP_C[3], r);
   double p = EXP_C[4];
 #pragma unroll
@@ -448,7 +449,7 @@ __device__ __forceinline__ void radial_factors(double r2, double a_rq, double ha
                                                double& kf, double& cf, double& sh) {
   sh = 0.0;
   if (KIND == 0) {
-    kf = exp_nonpos(-0.5 * r2);
+    kf = exp_neg(0.5 * r2);
     cf = kf;
   } else if (KIND == 2) {
     const double Mq = fma(r2, half_over_a, 1.0);
@@ -459,7 +460,7 @@ __device__ __forceinline__ void radial_factors(double r2, double a_rq, double ha
   } else {
     double r, rinv;
     sqrt_rsqrt_nonneg(r2, r, rinv);
-    const double e = exp_nonpos(-r);
+    const double e = exp_neg(r);
     if (KIND == 1) { kf = e; cf = rinv * e; }                       // inf at r = 0, as the reference
     else if (KIND == 3) { kf = fma(r, e, e); cf = e; }
     else {
@@ -471,11 +472,11 @@ __device__ __forceinline__ void radial_factors(double r2, double a_rq, double ha
 }
 
 template <int KIND, int DP>
-__global__ void __launch_bounds__(256, (DP <= 6 ? 3 : 2)) grad_rows_kernel(GradArgs a) {
+__global__ void __launch_bounds__(256, 2) grad_rows_kernel(GradArgs a) {
   extern __shared__ double bsm[];
   constexpr int NACC = DP + 2;                     // length scales | sf | rq shape
   constexpr int S = DP + 2;                        // shared row: DP coordinates, alpha_j, pad (16-byte rows)
-  constexpr int PF = (DP <= 6) ? 4 : 6;            // Ainv loads in flight per warp
+  constexpr int PF = 6;                            // Ainv loads in flight per warp
   const int slot = a.sel[blockIdx.y];
   int ti, tj;
   tri_decode(blockIdx.x, ti, tj);

@@ -459,6 +459,9 @@ _TOGGLE_CACHE = {}
     ({"GPB_LOADER": "auto_bulk"}, True),                   # round-1 default
     ({"GPB_QUARTER": "0"}, True),                          # no 64x64 CTAs for the small trailing updates
     ({"GPB_PDL": "0"}, True),                              # ordinary launches instead of programmatic dependent launch
+    ({"GPB_LEFT": "1", "GPB_LOOKAHEAD": "0"}, True),       # left-looking column updates inside the outer blocks
+    ({"GPB_LEFT": "1", "GPB_LA_OB": "4", "GPB_LA_WIDE": "0"}, True),   # ... with look-ahead and wide blocks
+    ({"GPB_GRAD_ROWS": "0"}, False),                       # gradient by the four-rows-per-thread kernel
     ({"GPB_TRTRI": "0"}, False),                           # column-recurrence triangular inverse
     ({"GPB_GEMM_BN": "128"}, False),                       # one CTA per tile: other reduction shapes
 ])
@@ -473,7 +476,8 @@ def test_schedule_toggles_do_not_change_results(env, exact):
 
     def run(extra):
         e = dict(os.environ)
-        for k in ("GPB_LOOKAHEAD", "GPB_LA_OB", "GPB_OUTER_BLOCK", "GPB_LOADER", "GPB_TRTRI", "GPB_GEMM_BN", "GPB_PDL", "GPB_QUARTER"):
+        for k in ("GPB_LOOKAHEAD", "GPB_LA_OB", "GPB_LA_WIDE", "GPB_OUTER_BLOCK", "GPB_LOADER", "GPB_TRTRI", "GPB_GEMM_BN",
+                  "GPB_PDL", "GPB_QUARTER", "GPB_LEFT", "GPB_GRAD_ROWS"):
             e.pop(k, None)
         e.update(extra)
         root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -581,3 +585,35 @@ def test_wide_inputs_up_to_64_dimensions(eng, D, cov_kind, mean_kind):
     assert np.max(np.abs(mu - rmu)) <= TOL_PRED * (1 + np.max(np.abs(rmu)))
     assert np.max(np.abs(v - rv)) <= TOL_PRED * np.max(np.abs(rv))
     post.free()
+
+
+@pytest.mark.parametrize("cov_kind,degree", [(0, 0), (1, 1), (1, 3), (1, 5), (2, 0)])
+@pytest.mark.parametrize("D", [1, 2, 3, 5, 6, 7, 9, 10, 11, 13, 16, 17])
+def test_gradient_row_kernel_every_width(eng, D, cov_kind, degree):
+    """The row-per-thread gradient kernel is instantiated for 4, 6, 8, 10, 12 and 16 length scales (inputs are
+    zero-padded up to the next one; D = 17 takes the four-rows-per-thread kernel): every instantiation and every
+    radial function -- with its own branch-free exp / sqrt -- against the oracle's gradient, on a size with a ragged
+    last tile (diagonal tiles, trimmed columns, masked rows).  Matern-1 keeps the reference's NaN on the
+    length-scale derivatives (inf * 0 on the diagonal)."""
+    rng = np.random.default_rng(100 * D + 10 * cov_kind + degree)
+    N = 300
+    X = rng.uniform(-2, 2, (N, D))
+    y = (np.cos(X[:, :2].sum(1)) + 0.1 * rng.standard_normal(N)).reshape(-1, 1)
+    spec = orc.ModelSpec(D=D, cov_kind=cov_kind, degree=degree, ard=True, mean_kind=1)
+    B = 3
+    cols = [np.log(2.0) + 0.4 * rng.standard_normal((B, D)), 0.2 * rng.standard_normal((B, 1))]
+    if cov_kind == 2:
+        cols.append(0.3 * rng.standard_normal((B, 1)))
+    cols += [np.full((B, 1), np.log(0.2)), 0.1 * rng.standard_normal((B, 1))]
+    hyp = np.concatenate(cols, axis=1)
+    assert hyp.shape[1] == spec.hyp_n
+    setup_engine(eng, spec, X, y, None)
+    nlz, dnlz, mult, status = eng.nlz_batch(hyp, want_grad=True)
+    ref_nlz, ref_dnlz = orc.nlz_batch(spec, hyp, X, y, None, True)
+    assert not status.any() and np.all(mult == 1)
+    assert rel_err(nlz, ref_nlz) <= TOL_NLZ
+    assert np.array_equal(np.isnan(dnlz), np.isnan(ref_dnlz))
+    if cov_kind == 1 and degree == 1:
+        assert np.isnan(ref_dnlz[:, :D]).all()                 # the reference's own NaN pattern
+    ok = ~np.isnan(ref_dnlz)
+    assert np.max(np.abs(dnlz[ok] - ref_dnlz[ok])) <= TOL_GRAD * np.max(np.abs(ref_dnlz[ok]))
