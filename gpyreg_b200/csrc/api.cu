@@ -33,6 +33,11 @@ struct Bufs {              // device storage for `cap` batch slots
   int cap = 0;
   bool has_w = false;
   bool cap_is_max = false;   // cap is limited by device memory, not by the request
+  // W = L^-1 is its own allocation with its own capacity (slots 0 .. wcap-1): a gradient call of a few rows
+  // after a large nlZ-only batch adds a small W next to the big arena instead of releasing and
+  // re-partitioning it (cudaFree + cudaMalloc of ~100 GB was 0.6-1.0 s of a 10 s cfg3 fit)
+  int wcap = 0;
+  bool wcap_is_max = false;
   int Np = 0, Nt = 0, D = 0, P = 0, cov_n = 0;
   double *Abuf = nullptr, *Wbuf = nullptr, *Dbuf = nullptr, *DTbuf = nullptr;
   double *xs = nullptr, *resid = nullptr, *sn2v = nullptr, *bvec = nullptr, *zvec = nullptr,
@@ -445,6 +450,8 @@ static void free_bufs(Bufs& b) {
   b.cap = 0;
   b.has_w = false;
   b.cap_is_max = false;
+  b.wcap = 0;
+  b.wcap_is_max = false;
 }
 
 extern "C" void gpb_destroy(gpb_ctx* ctx) {
@@ -614,7 +621,7 @@ static void build_tensor_maps(Bufs& b) {
   b.tm_ok = false;
   double* bases[4] = {b.Abuf, b.Wbuf, b.Dbuf, b.DTbuf};
   const long long rows[4] = {b.Np, b.Np, T, T};
-  const long long cols[4] = {(long long)b.cap * b.Np, (long long)b.cap * b.Np, (long long)b.cap * b.Nt * T,
+  const long long cols[4] = {(long long)b.cap * b.Np, (long long)b.wcap * b.Np, (long long)b.cap * b.Nt * T,
                              (long long)b.cap * b.Nt * T};
   bool ok = true;
   for (int i = 0; i < 4; ++i) {
@@ -623,6 +630,24 @@ static void build_tensor_maps(Bufs& b) {
     ok = ok && encode_map(&b.tm[i][1], bases[i], rows[i], cols[i], BM / 2 + 4);
   }
   b.tm_ok = ok;
+}
+
+// (re)allocate W for `wcap` slots of an existing buffer set
+static int alloc_w(gpb_ctx* ctx, Bufs& b, int wcap) {
+  if (b.Wbuf) cudaFree(b.Wbuf);
+  b.Wbuf = nullptr;
+  b.wcap = 0;
+  b.has_w = false;
+  b.wcap_is_max = false;
+  const size_t bytes = (size_t)b.Np * b.Np * 8 * (size_t)wcap;
+  CK(cudaMalloc(&b.Wbuf, bytes));
+  // padded rows/columns of W are never written by the (padding-skipping) kernels: zero once
+  CK(cudaMemsetAsync(b.Wbuf, 0, bytes, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  b.wcap = wcap;
+  b.has_w = true;
+  build_tensor_maps(b);
+  return GPB_OK;
 }
 
 static int alloc_bufs(gpb_ctx* ctx, Bufs& b, int cap, bool with_w, int Np, int D, const Model& md) {
@@ -635,12 +660,6 @@ static int alloc_bufs(gpb_ctx* ctx, Bufs& b, int cap, bool with_w, int Np, int D
   const size_t smat = (size_t)Np * Np;
   const size_t nt = b.Nt;
   CK(cudaMalloc(&b.Abuf, smat * 8 * cap));
-  if (with_w) {
-    CK(cudaMalloc(&b.Wbuf, smat * 8 * cap));
-    // padded rows/columns of W are never written by the (padding-skipping) kernels: zero once
-    CK(cudaMemsetAsync(b.Wbuf, 0, smat * 8 * cap, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-  }
   CK(cudaMalloc(&b.Dbuf, nt * T * T * 8 * cap));
   CK(cudaMalloc(&b.DTbuf, nt * T * T * 8 * cap));
   // diag_kernel only stores the non-zero 32x32 blocks of D_k and D_k^T
@@ -672,7 +691,7 @@ static int alloc_bufs(gpb_ctx* ctx, Bufs& b, int cap, bool with_w, int Np, int D
   CK(cudaMemsetAsync(b.prep_ticket, 0, sizeof(int) * cap, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   b.cap = cap;
-  b.has_w = with_w;
+  if (with_w) return alloc_w(ctx, b, cap);
   build_tensor_maps(b);
   return GPB_OK;
 }
@@ -680,24 +699,51 @@ static int alloc_bufs(gpb_ctx* ctx, Bufs& b, int cap, bool with_w, int Np, int D
 static int ensure_ws(gpb_ctx* ctx, long long B, bool with_w) {
   Bufs& w = ctx->ws;
   const Model& md = ctx->md;
-  const bool shape_ok = w.cap > 0 && (w.has_w || !with_w) && w.Np == ctx->Np && w.D == ctx->D &&
-                        w.P == md.P && w.cov_n == md.cov_n;
-  // fast path (no cudaMemGetInfo): big enough, or already as big as memory allows
-  if (shape_ok && (w.cap >= B || w.cap_is_max)) return GPB_OK;
+  const size_t smat_b = (size_t)ctx->Np * ctx->Np * 8;
+  auto realloc_all = [&](bool want_w) -> int {
+    size_t freeb = 0, totalb = 0;
+    CK(cudaMemGetInfo(&freeb, &totalb));
+    size_t have = 0;
+    if (w.cap) have = per_slot_bytes(w.Np, w.D, w.P, w.cov_n, false) * w.cap + (size_t)w.smat() * 8 * w.wcap;
+    const size_t limit = ctx->ws_limit ? ctx->ws_limit : (size_t)((freeb + have) * 0.70);
+    const size_t per = per_slot_bytes(ctx->Np, ctx->D, md.P, md.cov_n, want_w);
+    const long long fit = (long long)(limit / per);
+    if (fit < 1) FAIL(GPB_ENOMEM, "workspace for one matrix does not fit in device memory");
+    const int want = (int)std::min<long long>(std::min<long long>(B, fit), 32768);
+    ctx->cache.valid = false;
+    int rc = alloc_bufs(ctx, w, want, want_w, ctx->Np, ctx->D, md);
+    if (rc != GPB_OK) return rc;
+    w.cap_is_max = (want == fit);
+    w.wcap_is_max = want_w && w.cap_is_max;
+    return GPB_OK;
+  };
+  const bool shape_ok = w.cap > 0 && w.Np == ctx->Np && w.D == ctx->D && w.P == md.P && w.cov_n == md.cov_n;
+  // fast path (no cudaMemGetInfo): big enough, or already as big as memory allows.  A W left over from an
+  // earlier gradient call stays where it is when an nlZ-only call grows the rest.
+  if (!(shape_ok && (w.cap >= B || w.cap_is_max))) {
+    int rc = realloc_all(with_w);
+    if (rc != GPB_OK) return rc;
+  }
+  if (!with_w) return GPB_OK;
+  const long long needw = std::min<long long>(B, w.cap);
+  if (w.wcap >= needw || w.wcap_is_max) return GPB_OK;
+  // grow W alone, next to the slots that are there
   size_t freeb = 0, totalb = 0;
   CK(cudaMemGetInfo(&freeb, &totalb));
-  size_t have = 0;
-  if (w.cap) have = per_slot_bytes(w.Np, w.D, w.P, w.cov_n, w.has_w) * w.cap;
-  const size_t limit = ctx->ws_limit ? ctx->ws_limit : (size_t)((freeb + have) * 0.70);
-  const bool keep_w = with_w || (w.has_w && w.Np == ctx->Np);
-  const size_t per = per_slot_bytes(ctx->Np, ctx->D, md.P, md.cov_n, keep_w);
-  const long long fit = (long long)(limit / per);
-  if (fit < 1) FAIL(GPB_ENOMEM, "workspace for one matrix does not fit in device memory");
-  const int want = (int)std::min<long long>(std::min<long long>(B, fit), 32768);
-  ctx->cache.valid = false;
-  int rc = alloc_bufs(ctx, w, want, keep_w, ctx->Np, ctx->D, md);
+  const size_t have_w = smat_b * (size_t)w.wcap;
+  size_t avail;
+  if (ctx->ws_limit) {
+    const size_t rest = per_slot_bytes(w.Np, w.D, w.P, w.cov_n, false) * w.cap;
+    avail = ctx->ws_limit > rest ? ctx->ws_limit - rest : 0;
+  } else {
+    avail = (size_t)((freeb + have_w) * 0.70);
+  }
+  const long long fitw = (long long)(avail / smat_b);
+  if (fitw < 1) return realloc_all(true);        // no room beside the arena: re-partition it (A and W, same slots)
+  const int wantw = (int)std::min<long long>(needw, fitw);
+  int rc = alloc_w(ctx, w, wantw);
   if (rc != GPB_OK) return rc;
-  w.cap_is_max = (want == fit);
+  w.wcap_is_max = (wantw == fitw) && wantw < needw;
   return GPB_OK;
 }
 
@@ -1128,8 +1174,9 @@ static int nlz_batch_impl(gpb_ctx* ctx, const double* hyp, bool hyp_on_device, i
   std::vector<int> status_h;
   std::vector<double> mult_h;
 
-  for (int64_t row0 = 0; row0 < B; row0 += b.cap) {
-    const int n = (int)std::min<int64_t>(b.cap, B - row0);
+  const int chunk = want_grad ? std::min(b.cap, b.wcap) : b.cap;     // W may hold fewer slots than the rest
+  for (int64_t row0 = 0; row0 < B; row0 += chunk) {
+    const int n = (int)std::min<int64_t>(chunk, B - row0);
     if (P > 0) CK(cudaMemcpyAsync(b.hyp, hyp + row0 * P, sizeof(double) * n * P, kin, ctx->stream));
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     {

@@ -211,3 +211,35 @@ def test_gp_deepcopy_and_pickle_rebuild_their_factors():
     posts = copy.deepcopy(gp.posteriors)
     np.testing.assert_array_equal(posts[1].L, L0)
     assert posts[1]._batch is None
+
+
+def test_gradient_after_large_nlz_batch_adds_w_beside_the_arena():
+    """W = L^-1 has its own allocation and capacity: a gradient call after a large nlZ-only batch allocates a small W
+    next to the slots that are there (it used to release and re-partition the whole workspace: ~1 s of a cfg3 fit), a
+    larger gradient call grows W, a workspace limit that leaves no room beside the arena re-partitions it.  Every
+    result is bit-identical to a fresh context's."""
+    spec, X, y, hyp = _problem(N=300, D=3, B=40)
+    fresh = _engine(spec, X, y)
+    ref_nlz = fresh.nlz_batch(hyp)[0]
+    ref_g = fresh.nlz_batch(hyp, want_grad=True)
+    fresh.close()
+
+    e = _engine(spec, X, y)
+    np.testing.assert_array_equal(e.nlz_batch(hyp)[0], ref_nlz)                 # 40 slots, no W
+    for rows in (slice(0, 3), slice(5, 7), slice(0, 17), slice(0, 40), slice(2, 3)):   # W: 3 slots -> 17 -> 40
+        got = e.nlz_batch(hyp[rows], want_grad=True)
+        np.testing.assert_array_equal(got[0], ref_g[0][rows])
+        np.testing.assert_array_equal(got[1], ref_g[1][rows])
+        np.testing.assert_array_equal(e.nlz_batch(hyp[:9])[0], ref_nlz[:9])     # nlZ-only calls in between
+    e.close()
+
+    # a limit with room for ~6 slots without W: the gradient call must re-partition (3 slots with W) and chunk
+    e = _engine(spec, X, y)
+    per_noW = (384 * 384 + 2 * 3 * 128 * 128) * 8 + 64 * 1024
+    e.set_workspace_limit(6 * per_noW)
+    np.testing.assert_array_equal(e.nlz_batch(hyp)[0], ref_nlz)
+    got = e.nlz_batch(hyp, want_grad=True)
+    np.testing.assert_array_equal(got[0], ref_g[0])
+    np.testing.assert_array_equal(got[1], ref_g[1])
+    np.testing.assert_array_equal(e.nlz_batch(hyp)[0], ref_nlz)
+    e.close()
