@@ -2332,11 +2332,18 @@ extern "C" int gpb_debug_potrf(gpb_ctx* ctx, double* A, int n, int32_t* info) {
   int failh = 0;
   if (e == cudaSuccess) e = cudaMemcpy(&failh, b.fail, sizeof(int), cudaMemcpyDeviceToHost);
   if (e == cudaSuccess && ctx->diag_dbg) {
-    long long st[33];
+    long long st[64];
     cudaMemcpy(st, ctx->diag_dbg, sizeof st, cudaMemcpyDeviceToHost);
     fprintf(stderr, "diag_kernel phase cycles (n=%d):", n);
     for (int i = 1; i < (int)st[0]; ++i) fprintf(stderr, " %lld", st[1 + i] - st[i]);
     fprintf(stderr, "  total %lld\n", st[st[0]] - st[1]);
+    // the factor warp's own timeline: (start, end) of each 32x32 block factorisation, relative to the kernel's first stamp
+    fprintf(stderr, "  factor warp (start..end of each block factorisation):");
+    for (int i = 0; i + 1 < (int)st[40] && i + 1 < 16; i += 2)
+      fprintf(stderr, " %lld..%lld (%lld = pivot loop %lld + 16x16 inverses %lld + off-diagonal block %lld)", st[41 + i] - st[1],
+              st[42 + i] - st[1], st[42 + i] - st[41 + i], st[56 + i] - st[41 + i], st[57 + i] - st[56 + i],
+              st[42 + i] - st[57 + i]);
+    fprintf(stderr, "\n");
   }
   free_bufs(b);
   if (e != cudaSuccess) FAIL(GPB_ECUDA, cudaGetErrorString(e));

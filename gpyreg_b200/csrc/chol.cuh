@@ -130,16 +130,18 @@ __device__ __forceinline__ void inv16_all(const double* Lcol, const double* rd, 
 // Factor the 32x32 diagonal block at (c0, c0) of the tile S (one warp): Cholesky in registers,
 // factor back to S, inverse of the factor to Ivp.  Kept out of line so that its register
 // allocation and instruction schedule do not depend on the rest of diag_kernel.
-__device__ __noinline__ int factor_block32(double* S, double* Ivp, double* Tm, int c0, int lane) {
+__device__ __noinline__ int factor_block32(double* S, double* Ivp, double* Tm, int c0, int lane, long long* tdbg) {
+  // tdbg (GPB_DIAG_DBG only): clock stamps after the pivot loop and after the 16x16 inverses
+#define FSTAMP(i) do { if (tdbg) { if (lane == 0) tdbg[i] = clock64(); __syncwarp(); } } while (0)
   const int g = lane >> 2, tq = lane & 3;
   double* colbuf = Tm;               // [2][32] column broadcast buffers
   double* rd = Tm + 2 * SB;          // [32] 1 / L_rr
+  int failed = 0;
+  double rdiag = 0.0;                // 1 / L_rr of the lane's own row
   double arow[SB];                   // strictly lower part of the lane's row; the diagonal is dg
 #pragma unroll
   for (int c = 0; c < SB; ++c) arow[c] = (c < lane) ? S[(c0 + c) * DP_PITCH + c0 + lane] : 0.0;
   double dg = S[(c0 + lane) * DP_PITCH + c0 + lane];
-  int failed = 0;
-  double rdiag = 0.0;                // 1 / L_rr of the lane's own row
   double piv = __shfl_sync(0xffffffffu, dg, 0);
   chol32_all(arow, dg, rdiag, piv, lane, failed, colbuf, std::make_integer_sequence<int, SB>{});
 #pragma unroll
@@ -148,6 +150,7 @@ __device__ __noinline__ int factor_block32(double* S, double* Ivp, double* Tm, i
   S[(c0 + lane) * DP_PITCH + c0 + lane] = dg;
   rd[lane] = rdiag;
   __syncwarp();
+  FSTAMP(0);
   // inverses of the two 16x16 diagonal halves
   const int h = lane & HB;
   double inv[HB];
@@ -157,6 +160,8 @@ __device__ __noinline__ int factor_block32(double* S, double* Ivp, double* Tm, i
 #pragma unroll
   for (int q = 0; q < HB; ++q) Ivp[lane * IVP + h + q] = inv[q];     // column `lane`, rows h..h+15
   __syncwarp();
+  FSTAMP(1);
+#undef FSTAMP
   // Inv_21 = -Inv_22 (L_21 Inv_11): four 8x8 output blocks, K = 16, on DMMA
   double t[2][2][2];
 #pragma unroll
@@ -288,6 +293,7 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
 #define STAMP() do { if (a.dbg && threadIdx.x == 224 && nst < 32) stamps[nst++] = clock64(); } while (0)
   // second timeline, kept by the factor warp itself (explicitly re-converged before it goes on)
   __shared__ long long stamps0[16];
+  __shared__ long long fstamps[8];       // inside factor_block32: end of the pivot loop, end of the 16x16 inverses
   int nst0 = 0;
 #define STAMP0() do { if (a.dbg) { if (threadIdx.x == 0 && nst0 < 16) stamps0[nst0++] = clock64(); __syncwarp(); } } while (0)
   STAMP();
@@ -360,7 +366,7 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
       STAMP0();
       // ---- the serial part: diagonal block p in registers, lane r owns row r (single call site: the
       // function is 40 KB of unrolled code)
-      if (factor_block32(S, Iv + p * SB * IVP, Tm, c0, lane)) s_failed = 1;
+      if (factor_block32(S, Iv + p * SB * IVP, Tm, c0, lane, a.dbg ? fstamps + 2 * p : nullptr)) s_failed = 1;
       STAMP0();
     } else if (p > 0) {
       bar_sync(3, 256);                                  // every panel row of block p-1 is written
@@ -601,6 +607,7 @@ __global__ void __launch_bounds__(256) diag_kernel(DiagArgs a) {
   if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) {
     a.dbg[40] = nst0;
     for (int i = 0; i < nst0; ++i) a.dbg[41 + i] = stamps0[i];
+    for (int i = 0; i < 8; ++i) a.dbg[56 + i] = fstamps[i];
   }
   if (a.dbg && blockIdx.x == 0 && threadIdx.x == 224) {
     a.dbg[0] = nst;
