@@ -162,36 +162,57 @@ __device__ __noinline__ int factor_block32(double* S, double* Ivp, double* Tm, i
   __syncwarp();
   FSTAMP(1);
 #undef FSTAMP
-  // Inv_21 = -Inv_22 (L_21 Inv_11): four 8x8 output blocks, K = 16, on DMMA
+  // Inv_21 = -Inv_22 (L_21 Inv_11): four 8x8 output blocks, K = 16, on DMMA.  k is the OUTER loop: the DMMAs are
+  // volatile asm statements and keep their program order, so with the output block outermost the four dependent
+  // chains of a stage ran one after the other (16 x the DMMA latency: 1.5 k cycles for the two stages)
   double t[2][2][2];
 #pragma unroll
   for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-    for (int ni = 0; ni < 2; ++ni) {
-      t[mi][ni][0] = t[mi][ni][1] = 0.0;
+    for (int ni = 0; ni < 2; ++ni) t[mi][ni][0] = t[mi][ni][1] = 0.0;
 #pragma unroll
-      for (int k4 = 0; k4 < 4; ++k4) {
-        const double af = S[(c0 + k4 * 4 + tq) * DP_PITCH + c0 + HB + mi * 8 + g];   // L_21(m, k)
-        const double bf = Ivp[(ni * 8 + g) * IVP + k4 * 4 + tq];                     // Inv_11(k, n)
-        dmma_t(t[mi][ni][0], t[mi][ni][1], af, bf);
-      }
-      Tm[(ni * 8 + 2 * tq) * IVP + mi * 8 + g] = t[mi][ni][0];
-      Tm[(ni * 8 + 2 * tq + 1) * IVP + mi * 8 + g] = t[mi][ni][1];
-    }
-  __syncwarp();
+  for (int k4 = 0; k4 < 4; ++k4) {
+    double af[2], bf[2];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) af[mi] = S[(c0 + k4 * 4 + tq) * DP_PITCH + c0 + HB + mi * 8 + g];   // L_21(m, k)
+#pragma unroll
+    for (int ni = 0; ni < 2; ++ni) bf[ni] = Ivp[(ni * 8 + g) * IVP + k4 * 4 + tq];                     // Inv_11(k, n)
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 2; ++ni) dmma_t(t[mi][ni][0], t[mi][ni][1], af[mi], bf[ni]);
+  }
 #pragma unroll
   for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
     for (int ni = 0; ni < 2; ++ni) {
-      double d0 = 0.0, d1 = 0.0;
+      Tm[(ni * 8 + 2 * tq) * IVP + mi * 8 + g] = t[mi][ni][0];
+      Tm[(ni * 8 + 2 * tq + 1) * IVP + mi * 8 + g] = t[mi][ni][1];
+    }
+  __syncwarp();
+  double d[2][2][2];
 #pragma unroll
-      for (int k4 = 0; k4 < 4; ++k4) {
-        const double af = -Ivp[(HB + k4 * 4 + tq) * IVP + HB + mi * 8 + g];          // -Inv_22(m, k)
-        const double bf = Tm[(ni * 8 + g) * IVP + k4 * 4 + tq];                      // T(k, n)
-        dmma_t(d0, d1, af, bf);
-      }
-      Ivp[(ni * 8 + 2 * tq) * IVP + HB + mi * 8 + g] = d0;
-      Ivp[(ni * 8 + 2 * tq + 1) * IVP + HB + mi * 8 + g] = d1;
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 2; ++ni) d[mi][ni][0] = d[mi][ni][1] = 0.0;
+#pragma unroll
+  for (int k4 = 0; k4 < 4; ++k4) {
+    double af[2], bf[2];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) af[mi] = -Ivp[(HB + k4 * 4 + tq) * IVP + HB + mi * 8 + g];          // -Inv_22(m, k)
+#pragma unroll
+    for (int ni = 0; ni < 2; ++ni) bf[ni] = Tm[(ni * 8 + g) * IVP + k4 * 4 + tq];                      // T(k, n)
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 2; ++ni) dmma_t(d[mi][ni][0], d[mi][ni][1], af[mi], bf[ni]);
+  }
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 2; ++ni) {
+      Ivp[(ni * 8 + 2 * tq) * IVP + HB + mi * 8 + g] = d[mi][ni][0];
+      Ivp[(ni * 8 + 2 * tq + 1) * IVP + HB + mi * 8 + g] = d[mi][ni][1];
     }
   return failed;
 }
