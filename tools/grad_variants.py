@@ -1,4 +1,4 @@
-"""A/B of gradient-kernel builds: gradient-phase time of one warm step per library in build/var/
+"""A/B of kernel builds: gradient-phase time of one warm step per library in build/var/ (built by hand with nvcc -D... -o build/var/lib_<tag>.so gpyreg_b200/csrc/api.cu)
 (each build loaded in its own process through GPYREG_B200_LIB).  usage: python tools/grad_variants.py"""
 import glob
 import os
