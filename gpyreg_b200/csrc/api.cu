@@ -94,9 +94,10 @@ struct gpb_ctx {
   bool cache_enabled = true;    // env GPB_NLZ_CACHE=0 disables
   bool grad_rows = true;        // env GPB_GRAD_ROWS=0: gradient by grad_kernel for every shape (A/B)
   int left_looking = 2;         // env GPB_LEFT: left-looking column updates inside wide outer blocks -- 0 never,
-                                // 1 always, 2 (default) for batches of >= 24 matrices, with outer blocks of 8 tile columns
-                                // (measured at N=5000: potrf of 64 matrices 89.2 -> 87.5 ms; slower below 16 matrices,
-                                // where the chain diag -> panel -> next column decides)
+                                // 1 always, 2 (default) for batches of >= 24 matrices of >= 16 tile columns, with outer
+                                // blocks of 8 tile columns (measured at N=5000: potrf of 64 matrices 89.2 -> 87.5 ms;
+                                // slower below 16 matrices, where the chain diag -> panel -> next column decides, and
+                                // for small matrices: N=1000, 32 matrices nlZ 1.10 -> 1.28 ms, N=1500 x 64 3.69 -> 3.83)
   bool outer_block_set = false; // GPB_OUTER_BLOCK given: use it for every batch size
   double timings[6] = {0, 0, 0, 0, 0, 0};
   long long launches = 0;
@@ -842,7 +843,7 @@ static void run_potrf(gpb_ctx* ctx, Bufs& b, long long N, const int* sel, int ns
   // (measured, N=5000, one matrix: 5.0 -> 4.1 ms at width 1).  The choice never changes a bit of
   // the result: every element sees the same FP64 operations in the same order for any blocking.
   const int narrow = ctx->la_ob > 0 ? ctx->la_ob : (nsel <= 2 ? 1 : 2);
-  const bool left_on = ctx->left_looking == 1 || (ctx->left_looking == 2 && nsel >= 24);
+  const bool left_on = ctx->left_looking == 1 || (ctx->left_looking == 2 && nsel >= 24 && Nt >= 16);
   const int wide = (left_on && !ctx->outer_block_set) ? 8 : ctx->outer_block;
   auto width_at = [&](int k0) {
     if (!look0) return wide;
